@@ -1,0 +1,173 @@
+"""Pin the CPU oracle against golden vectors produced by the reference modules themselves
+(tests/golden/make_golden.py, run in the build container).  CPU only."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import decoder_oracle as DO
+from oracle import encoder_oracle as EO
+from oracle import latent as OL
+from oracle import vocab as OV
+from oracle import weights as W
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+SHAPES = {"tiny": (W.TINY, OV.TINY_LAYOUT), "c512_b32": (W.C512, {}), "c512b_b4": (W.C512B, {}),
+          "c576_b4": (W.C576, {})}
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _setup(golden_dir, name):
+    shape, layout = SHAPES[name]
+    g = _load(golden_dir, name)
+    B, seed = g["meta"]["B"], g["meta"]["seed_in"]
+    sd = W.make_decoder_state_dict(shape, 0)
+    z = W.make_latents(B, shape.latent_dim, seed)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, seed)
+    masks = OV.type_masks(**layout)
+    return shape, g, sd, z, stoich, heads, masks
+
+
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4", "c576_b4"])
+def test_decoder_oracle_matches_reference(golden_dir, name):
+    shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, name)
+    nh = shape.nhead
+    mem = DO.build_memory(sd, z, None, stoich, heads)
+    assert mem.shape[1] == int(g["memory_shapes"][0])
+    assert DO.build_memory(sd, z, None, stoich, None).shape[1] == int(g["memory_shapes"][1])
+    assert DO.build_memory(sd, z, None, None, None).shape[1] == int(g["memory_shapes"][2])
+    torch.testing.assert_close(mem[:2], g["memory24_rows"], rtol=1e-4, atol=1e-5)
+
+    t, lp, en = DO.generate_with_kv_cache(sd, nh, z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                          heads_pred=heads, type_masks=masks, stop_boost=10.0,
+                                          hard_stop_threshold=0.8, return_log_probs=True, return_entropy=True)
+    assert torch.equal(t.to(torch.int16), g["greedy_masked_tokens"])
+    torch.testing.assert_close(en[0], g["greedy_masked_entropy_row0"], rtol=1e-5, atol=1e-5)
+    assert float(lp.abs().max()) == 0.0
+
+    trace = {}
+    t, _, en = DO.generate_with_kv_cache(sd, nh, z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                         heads_pred=heads, return_entropy=True, trace=trace)
+    assert torch.equal(t.to(torch.int16), g["greedy_plain_tokens"])
+    n = g["greedy_plain_entropy"].shape[0]
+    torch.testing.assert_close(en[:n], g["greedy_plain_entropy"], rtol=1e-4, atol=1e-4)
+    for i, s in enumerate(g["greedy_plain_logit_steps"].tolist()):
+        r = g["greedy_plain_logits"].shape[1]
+        torch.testing.assert_close(trace["raw_logits"][s][:r], g["greedy_plain_logits"][i], rtol=1e-4, atol=2e-5)
+
+    t, _, _ = DO.generate_with_kv_cache(sd, nh, z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                        heads_pred=heads, stop_boost=10.0)
+    assert torch.equal(t.to(torch.int16), g["greedy_stopboost_tokens"])
+    t, _, _ = DO.generate_with_kv_cache(sd, nh, z=z, stoich_pred=stoich, temperature=0.001)
+    assert torch.equal(t.to(torch.int16), g["greedy_m20_tokens"])
+    # H1: temperature 0.0 is not greedy in the reference; the oracle reproduces it
+    t, _, _ = DO.generate_with_kv_cache(sd, nh, z, stoich_pred=stoich, temperature=0.0, max_len=shape.max_len,
+                                        heads_pred=heads, type_masks=masks, stop_boost=10.0, hard_stop_threshold=0.8)
+    assert torch.equal(t.to(torch.int16), g["t0_masked_tokens"])
+    t, _, _ = DO.generate_with_kv_cache(sd, nh, z, stoich_pred=stoich, temperature=0.0,
+                                        max_len=min(shape.max_len, 8), heads_pred=heads)
+    assert torch.equal(t.to(torch.int16), g["t0_plain_tokens"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4"])
+def test_decoder_oracle_sampling_matches_reference_rng(golden_dir, name):
+    shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, name)
+    nh = shape.nhead
+    torch.manual_seed(77)
+    t, lp, en, mk = DO.sample_for_reinforce(sd, nh, z, stoich_pred=stoich, temperature=1.2, max_len=shape.max_len,
+                                            stop_boost=10.0, heads_pred=heads)
+    assert torch.equal(t.to(torch.int16), g["sample_tokens"])
+    torch.testing.assert_close(lp, g["sample_logprobs"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(en, g["sample_entropy"], rtol=1e-4, atol=1e-4)
+    assert torch.equal(mk, g["sample_mask"])
+    # H2: with hard masks the reference samples uniformly; log-prob = -ln V, entropy = ln V
+    torch.manual_seed(78)
+    t, lp, en, mk = DO.sample_for_reinforce(sd, nh, z, stoich_pred=stoich, temperature=1.2, max_len=shape.max_len,
+                                            stop_boost=10.0, hard_stop_threshold=0.8, heads_pred=heads,
+                                            type_masks=masks)
+    assert torch.equal(t.to(torch.int16), g["sample_masked_tokens"])
+    torch.testing.assert_close(lp, g["sample_masked_logprobs"], rtol=1e-5, atol=1e-5)
+    assert abs(float(lp[0, 0]) + math.log(shape.vocab_size)) < 1e-4
+    torch.testing.assert_close(en, g["sample_masked_entropy"], rtol=1e-5, atol=1e-5)
+    assert torch.equal(mk, g["sample_masked_mask"])
+
+
+def test_decoder_oracle_topk_topp(golden_dir):
+    shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    torch.manual_seed(5)
+    t, lp, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.9, top_k=7,
+                                         heads_pred=heads, return_log_probs=True)
+    assert torch.equal(t.to(torch.int16), g["topk_tokens"])
+    torch.testing.assert_close(lp, g["topk_logprobs"], rtol=1e-4, atol=1e-4)
+    torch.manual_seed(6)
+    t, lp, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.9, top_p=0.8,
+                                         heads_pred=heads, return_log_probs=True)
+    assert torch.equal(t.to(torch.int16), g["topp_tokens"])
+    torch.testing.assert_close(lp, g["topp_logprobs"], rtol=1e-4, atol=1e-4)
+
+
+def test_decoder_oracle_c512_b32_greedy(golden_dir):
+    """BASELINE config 1 (batch 32, max_len 64): masked + stop, and the full 63-step decode."""
+    shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, "c512_b32")
+    t, _, _ = DO.generate_with_kv_cache(sd, 8, z, stoich_pred=stoich, temperature=0.001, max_len=64,
+                                        heads_pred=heads, type_masks=masks, stop_boost=10.0, hard_stop_threshold=0.8)
+    assert torch.equal(t.to(torch.int16), g["greedy_masked_tokens"])
+    trace = {}
+    t, _, _ = DO.generate_with_kv_cache(sd, 8, z, stoich_pred=stoich, temperature=0.001, max_len=64,
+                                        heads_pred=heads, trace=trace)
+    assert torch.equal(t.to(torch.int16), g["greedy_plain_tokens"])
+    for i, s in enumerate(g["greedy_plain_logit_steps"].tolist()):
+        torch.testing.assert_close(trace["raw_logits"][s][:4], g["greedy_plain_logits"][i], rtol=1e-4, atol=2e-5)
+
+
+def test_skip_connection_memory(golden_dir):
+    g = _load(golden_dir, "tiny_skip")
+    shape = W.TINY_SKIP
+    sd = W.make_decoder_state_dict(shape, 0)
+    B = g["meta"]["B"]
+    z = W.make_latents(B, shape.latent_dim, 99)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, 99)
+    mem = DO.build_memory(sd, z, g["skip"], stoich, heads)
+    torch.testing.assert_close(mem, g["memory"], rtol=1e-4, atol=1e-5)
+    t, _, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, encoder_skip=g["skip"], stoich_pred=stoich,
+                                        temperature=0.001, heads_pred=heads)
+    assert torch.equal(t.to(torch.int16), g["tokens"])
+
+
+def test_heads_batch_mismatch_raises():
+    shape = W.TINY
+    sd = W.make_decoder_state_dict(shape, 0)
+    z = W.make_latents(4, shape.latent_dim)
+    stoich, heads = W.make_conditioning(3, shape.stoich_input_dim)
+    with pytest.raises(RuntimeError):
+        DO.build_memory(sd, z, None, None, heads)
+
+
+def test_encoder_oracle_matches_reference(golden_dir):
+    g = _load(golden_dir, "encoder_default")
+    sd = W.make_encoder_state_dict(W.ENC_DEFAULT, 1)
+    idx, frac, mask, magpie, tc = W.make_compositions(g["meta"]["B"], g["meta"]["seed_in"])
+    out = EO.forward(sd, idx, frac, mask, magpie, tc)
+    for k, v in g.items():
+        if k == "meta":
+            continue
+        torch.testing.assert_close(out[k], v, rtol=2e-4, atol=2e-5, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_slerp_matches_reference(golden_dir):
+    g = _load(golden_dir, "slerp")
+    torch.testing.assert_close(OL.slerp(g["z1"], g["z2"], g["t"]), g["slerp"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(OL.slerp(g["z1"], g["z1"] * 2.0, 0.25), g["slerp_parallel"], rtol=1e-5, atol=1e-6)
+
+
+def test_vocab_layout_matches_reference(golden_dir):
+    g = _load(golden_dir, "tokenizer")
+    m = OV.type_masks(g["n_fractions"], g["n_isotopes"])
+    assert m.shape == (5, g["vocab_size"]) == (5, 4752)
+    assert m.sum(dim=1).tolist() == g["mask_row_sums"].tolist() == [118, 20, 4317, 296, 1]
+    assert int(m.sum()) == g["vocab_size"]
