@@ -1,0 +1,169 @@
+/*
+ * scvae_b200 - C ABI of the B200-native KV-cache decode engine.
+ *
+ * The reference (jamesconde/superconductor-vae) has no FFI: its boundary for this path is the
+ * Python method surface of two nn.Modules.  This header is the boundary a
+ * Python host binds with ctypes: plain pointers and sizes, no torch types.
+ * Every entry point cites the reference interface it replaces
+ * (paths relative to the reference root, src/superconductor/...).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller unless the comment says HOST;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it unless stated;
+ *   - return value 0 = ok, non-zero = error, message via scv_last_error() (thread local);
+ *   - no exceptions cross this boundary; one host thread per engine.
+ */
+#ifndef SCVAE_B200_H
+#define SCVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCV_ABI_VERSION 1
+
+typedef struct scv_decoder scv_decoder;
+typedef struct scv_encoder scv_encoder;
+
+/* ---------------------------------------------------------------- general */
+int scv_abi_version(void);
+const char* scv_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
+int64_t scv_launch_count(void);
+
+/* Per-category kernel timing with CUDA events on the launch stream (bench.py roofline pass; adds overhead,
+ * never enabled inside a timed region).  Categories are indexed 0..n-1, see scv_profile_category_name. */
+int scv_profile_begin(void);
+int scv_profile_end(int32_t n_cats, int32_t* counts, double* ms, double* flops, double* bytes);
+const char* scv_profile_category_name(int32_t cat);
+
+/* ---------------------------------------------------------------- decoder */
+/* Constructor arguments of EnhancedTransformerDecoder (models/autoregressive_decoder.py:564-598). */
+typedef struct scv_decoder_config {
+  int32_t d_model, nhead, num_layers, dim_feedforward, vocab_size;
+  int32_t pe_len;                 /* rows of pos_encoding.pe (= constructor max_len) */
+  int32_t latent_dim, n_memory_tokens, memory_bottleneck_dim; /* 0 = pre-V15 direct MLP (:638-644) */
+  int32_t stoich_input_dim, n_stoich_tokens;                  /* 0 tokens = no stoich conditioning */
+  int32_t heads_input_dim, heads_n_tokens;                    /* :756-765 */
+  int32_t encoder_skip_dim, skip_n_tokens;                    /* 0 tokens = use_skip_connection=False */
+} scv_decoder_config;
+
+int scv_decoder_create(const scv_decoder_config* cfg, scv_decoder** out);
+void scv_decoder_destroy(scv_decoder* dec);
+
+/* Copy one state_dict entry (fp32, contiguous, device) into engine-owned storage; matrices are
+ * rounded to bf16 once here.  `name` is the reference's state_dict key
+ * (SURVEY.md section 8b "State-dict layout"), e.g.
+ * "transformer_decoder.layers.3.self_attn.in_proj_weight".  Unknown names return 1. */
+int scv_decoder_load_weight(scv_decoder* dec, const char* name, const float* src, int64_t numel, void* stream);
+/* 0 when every tensor the config requires has been loaded, else the count missing
+ * (first missing name in scv_last_error()). */
+int scv_decoder_missing_weights(scv_decoder* dec);
+
+/* _create_memory / precompute_memory (models/autoregressive_decoder.py:779-899).
+ * z [B, latent_dim]; skip [B, encoder_skip_dim] or NULL; stoich [B, stoich_input_dim] or NULL;
+ * heads_in [B, heads_input_dim] or NULL (already concatenated in the order of :845-858).
+ * memory_out [B, n_tokens, d_model] fp32 where n_tokens = n_memory_tokens (+skip) (+stoich) (+heads)
+ * for the non-NULL inputs; *n_tokens_out (HOST) receives it. */
+int scv_decoder_build_memory(scv_decoder* dec, int32_t batch, const float* z, const float* skip,
+                             const float* stoich, const float* heads_in, float* memory_out,
+                             int32_t* n_tokens_out, void* stream);
+
+#define SCV_FLAG_H2_UNIFORM_FALLBACK 1u /* reproduce :1464-1466/:1512-1513 (batch-global degenerate guard) */
+#define SCV_FLAG_SYNC_EVERY_STEP 2u     /* debugging: synchronise after every step */
+
+/* generate_with_kv_cache (models/autoregressive_decoder.py:1321-1557). */
+typedef struct scv_generate_args {
+  int32_t batch;
+  int32_t n_memory;        /* memory tokens per row (16, 20, 24, +8 with skip) */
+  int32_t max_len;         /* reference max_len; executed steps <= min(max_len, pe_len) - 1 */
+  const float* memory;     /* [batch, n_memory, d_model] fp32 (cached_memory) */
+  float temperature;       /* < 0.01 -> argmax (:1506); 0.0 reproduces the reference's divide */
+  int32_t top_k;           /* <= 0: off */
+  float top_p;             /* >= 1: off */
+  float stop_boost, hard_stop_threshold, site_dup_threshold;
+  const uint8_t* type_masks; /* [5, vocab] 0/1 or NULL */
+  int32_t want_log_probs, want_entropy;
+  uint32_t flags;
+  uint64_t seed, offset;   /* Philox key / counter offset for multinomial */
+  int64_t* out_tokens;     /* [batch, max_len-1] row stride = max_len-1 (clamped) */
+  float* out_log_probs;    /* same shape or NULL */
+  float* out_entropy;      /* same shape or NULL */
+  int32_t* out_steps;      /* HOST: number of executed steps L (columns >= L are not written) */
+  const int64_t* forced_tokens; /* optional [batch, max_len-1]: teacher-forced replay (tests) */
+} scv_generate_args;
+
+/* Enqueues the decode loop and synchronises `stream` once at the end to read *out_steps. */
+int scv_decoder_generate(scv_decoder* dec, const scv_generate_args* args, void* stream);
+
+/* Debug taps (tests): copy engine-internal fp32 state of the LAST executed step to `dst`.
+ * what: 0 final hidden [B,d]; 1 raw logits [B,V]; 2 type logits [B,5]; 3 stop logit [B] */
+int scv_decoder_debug_read(scv_decoder* dec, int32_t what, float* dst, int64_t numel, void* stream);
+
+/* ---------------------------------------------------------------- encoder */
+/* Constructor arguments of FullMaterialsVAE (models/attention_vae.py:350-362). */
+typedef struct scv_encoder_config {
+  int32_t n_element_rows;   /* rows of element_embed.weight (n_elements + 1) */
+  int32_t element_embed_dim, n_attention_heads, max_elements;
+  int32_t magpie_dim, fusion_dim, latent_dim;
+  int32_t n_encoder_hidden; int32_t encoder_hidden[4];
+  int32_t n_decoder_hidden; int32_t decoder_hidden[4];
+} scv_encoder_config;
+
+int scv_encoder_create(const scv_encoder_config* cfg, scv_encoder** out);
+void scv_encoder_destroy(scv_encoder* enc);
+int scv_encoder_load_weight(scv_encoder* enc, const char* name, const float* src, int64_t numel, void* stream);
+int scv_encoder_missing_weights(scv_encoder* enc);
+
+/* FullMaterialsVAE.encode (models/attention_vae.py:625-676).
+ * element_indices int64 [B, E]; fractions fp32 [B, E]; mask uint8 [B, E]; magpie [B, magpie_dim];
+ * tc [B].  Outputs: z [B, latent], attention_weights [B, E] (may be NULL), fused [B, 3*fusion] (may be NULL). */
+int scv_encoder_encode(scv_encoder* enc, int32_t batch, const int64_t* element_indices,
+                       const float* element_fractions, const uint8_t* element_mask, const float* magpie,
+                       const float* tc, float* z_out, float* attention_weights_out, float* fused_out,
+                       void* stream);
+
+/* FullMaterialsVAE.decode + head section of forward (attention_vae.py:678-709, 733-770, 236-307).
+ * Every output may be NULL. */
+typedef struct scv_encoder_heads_out {
+  float* tc_pred;            /* [B] */
+  float* magpie_pred;        /* [B, magpie_dim] */
+  float* attended_input;     /* [B, fusion_dim] */
+  float* tc_class_logits;    /* [B, 5] */
+  float* competence;         /* [B] */
+  float* fraction_pred;      /* [B, max_elements] */
+  float* element_count_pred; /* [B] */
+  float* hp_pred;            /* [B] */
+  float* sc_pred;            /* [B] */
+  float* family_coarse_logits;      /* [B, 7] */
+  float* family_cuprate_sub_logits; /* [B, 6] */
+  float* family_iron_sub_logits;    /* [B, 2] */
+  float* family_composed_14;        /* [B, 14] */
+  float* stoich_pred;        /* [B, max_elements+1] = cat(fraction_pred, count) (train_v12_clean.py:5249) */
+  float* heads_input;        /* [B, 24] in the order the decoder concatenates (autoregressive_decoder.py:845-858) */
+} scv_encoder_heads_out;
+
+int scv_encoder_heads(scv_encoder* enc, int32_t batch, const float* z, const scv_encoder_heads_out* out,
+                      void* stream);
+
+/* slerp (scripts/holdout/holdout_search.py:128-146), rows z1[i1[r]], z2[i2[r]], t[r] -> out[r].
+ * The reference's batch-global lerp fallback (:137-138) is applied when *any* row is near-parallel. */
+int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const int32_t* i2, const float* t,
+                   int64_t n_rows, float* out, int32_t* fallback_flag_dev, void* stream);
+
+/* ---------------------------------------------------------------- kernel-level taps (tests) */
+/* y[M,N] = act(x[M,K] * w[N,K]^T + bias) (+ residual); w is bf16 with row stride ldw (elements).
+ * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 0 auto, 1 SIMT fp32, 2 tcgen05 hi/lo bf16. */
+int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t ldw, const float* bias,
+                  const float* residual, int32_t ldr, float* y, int32_t ldy, int32_t M, int32_t N, int32_t K,
+                  int32_t act, int32_t impl, void* stream);
+int scv_op_pack_bf16(const float* src, uint16_t* dst, int32_t rows, int32_t cols, int32_t ld_dst, void* stream);
+int scv_op_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, float* y, int32_t ldy,
+                     int32_t M, int32_t N, int32_t act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCVAE_B200_H */

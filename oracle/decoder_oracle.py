@@ -190,7 +190,7 @@ def generate_with_kv_cache(
     stop_boost: float = 0.0, hard_stop_threshold: float = 0.0, heads_pred=None, type_masks=None,
     site_dup_threshold: float = 0.0, *, generator: Optional[torch.Generator] = None,
     forced_tokens: Optional[torch.Tensor] = None, trace: Optional[dict] = None, kv_round=None,
-    stop_when_all_finished: bool = True,
+    stop_when_all_finished: bool = True, max_steps: Optional[int] = None,
 ):
     """Same signature and semantics as the reference (:1321-1557).
 
@@ -282,6 +282,8 @@ def generate_with_kv_cache(
         if stop_when_all_finished and bool(finished.all()):
             break
         if forced_tokens is not None and position + 1 >= forced_tokens.shape[1]:
+            break
+        if max_steps is not None and position + 1 >= max_steps:      # bench.py: bounded CPU sample
             break
     generated = torch.cat(toks, dim=1)
     return (generated,

@@ -1,0 +1,197 @@
+// Error reporting, launch accounting, weight store and the kernel-level C-ABI taps.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/scvae_b200.h"
+#include "common.cuh"
+#include "weights.cuh"
+
+namespace scv {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ profiling
+struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+bool prof_enabled() { return g_prof; }
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(int cat, cudaStream_t s, double flops, double bytes) : idx_(-1), s_(s) {
+  if (!g_prof) return;
+  ProfRec r{cat, get_event(), get_event(), flops, bytes};
+  cudaEventRecord(r.a, s);
+  idx_ = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx_ >= 0) cudaEventRecord(g_recs[idx_].b, s_);
+}
+
+// ------------------------------------------------------------------ WeightStore
+WeightStore::~WeightStore() {
+  for (void* p : allocs_) cudaFree(p);
+}
+
+__nv_bfloat16* WeightStore::add_matrix(const std::string& name, int rows, int cols, int* ld_out) {
+  const int ld = round_up(cols, 8);      // 16-byte rows for vector loads
+  void* p = nullptr;
+  const size_t bytes = (size_t)rows * ld * sizeof(__nv_bfloat16);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed for %s", bytes, name.c_str());
+    return nullptr;
+  }
+  cudaMemset(p, 0, bytes);
+  allocs_.push_back(p);
+  Slot s;
+  s.dst = p; s.is_matrix = true; s.rows = rows; s.cols = cols; s.ld = ld; s.numel = (int64_t)rows * cols;
+  slots_[name] = s;
+  order_.push_back(name);
+  if (ld_out) *ld_out = ld;
+  return static_cast<__nv_bfloat16*>(p);
+}
+
+float* WeightStore::add_vector(const std::string& name, int64_t numel) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, (size_t)numel * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc failed for %s", name.c_str());
+    return nullptr;
+  }
+  allocs_.push_back(p);
+  Slot s;
+  s.dst = p; s.numel = numel;
+  slots_[name] = s;
+  order_.push_back(name);
+  return static_cast<float*>(p);
+}
+
+int WeightStore::add_linear(const std::string& prefix, int N, int K, Lin* out, bool bias) {
+  out->N = N; out->K = K;
+  out->w = add_matrix(prefix + ".weight", N, K, &out->ldw);
+  if (!out->w) return 2;
+  if (bias) {
+    out->b = add_vector(prefix + ".bias", N);
+    if (!out->b) return 2;
+  }
+  return 0;
+}
+
+int WeightStore::add_layernorm(const std::string& prefix, int N, LNp* out) {
+  out->N = N;
+  out->g = add_vector(prefix + ".weight", N);
+  out->b = add_vector(prefix + ".bias", N);
+  return (out->g && out->b) ? 0 : 2;
+}
+
+void WeightStore::mark_optional(const std::string& name) {
+  auto it = slots_.find(name);
+  if (it != slots_.end()) it->second.optional = true;
+}
+
+int WeightStore::load(const char* name, const float* src, int64_t numel, cudaStream_t s) {
+  auto it = slots_.find(name);
+  SCV_REQUIRE(it != slots_.end(), "unknown state_dict key '%s'", name);
+  Slot& sl = it->second;
+  SCV_REQUIRE(sl.numel == numel, "state_dict key '%s': expected %lld elements, got %lld", name,
+              (long long)sl.numel, (long long)numel);
+  if (sl.is_matrix) {
+    SCV_TRY(launch_pack_bf16(src, static_cast<__nv_bfloat16*>(sl.dst), sl.rows, sl.cols, sl.ld, s));
+  } else {
+    SCV_TRY(launch_copy_f32(src, static_cast<float*>(sl.dst), numel, s));
+  }
+  sl.loaded = true;
+  return 0;
+}
+
+int WeightStore::missing(std::string* first) const {
+  int n = 0;
+  for (const auto& name : order_) {
+    const Slot& s = slots_.at(name);
+    if (!s.loaded && !s.optional) {
+      if (n == 0 && first) *first = name;
+      ++n;
+    }
+  }
+  return n;
+}
+
+int launch_linear(const LinearArgs& a, int impl, cudaStream_t s) {
+  (void)impl;   // the tcgen05 path is selected here once it is wired in
+  return launch_linear_simt(a, s);
+}
+
+}  // namespace scv
+
+using namespace scv;
+
+extern "C" {
+
+int scv_abi_version(void) { return SCV_ABI_VERSION; }
+const char* scv_last_error(void) { return g_err; }
+int64_t scv_launch_count(void) { return g_launches.load(); }
+
+int scv_profile_begin(void) {
+  for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_recs.clear();
+  g_prof = true;
+  return 0;
+}
+
+int scv_profile_end(int32_t n_cats, int32_t* counts, double* ms, double* flops, double* bytes) {
+  g_prof = false;
+  SCV_REQUIRE(n_cats >= PC_COUNT && counts && ms && flops && bytes, "profile_end: need room for %d categories", (int)PC_COUNT);
+  SCV_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n_cats; ++i) { counts[i] = 0; ms[i] = flops[i] = bytes[i] = 0.0; }
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    SCV_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    counts[r.cat] += 1; ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes;
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return 0;
+}
+
+const char* scv_profile_category_name(int32_t cat) {
+  static const char* names[PC_COUNT] = {"linear_simt", "layernorm", "attention_self", "attention_cross", "sampler",
+                                        "embed", "misc", "gemm_tcgen05"};
+  return (cat >= 0 && cat < PC_COUNT) ? names[cat] : "";
+}
+
+int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t ldw, const float* bias,
+                  const float* residual, int32_t ldr, float* y, int32_t ldy, int32_t M, int32_t N, int32_t K,
+                  int32_t act, int32_t impl, void* stream) {
+  LinearArgs a;
+  a.x = x; a.ldx = ldx; a.w = reinterpret_cast<const __nv_bfloat16*>(w_bf16); a.ldw = ldw; a.bias = bias;
+  a.residual = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K; a.act = act;
+  return launch_linear(a, impl, static_cast<cudaStream_t>(stream));
+}
+
+int scv_op_pack_bf16(const float* src, uint16_t* dst, int32_t rows, int32_t cols, int32_t ld_dst, void* stream) {
+  SCV_REQUIRE(ld_dst >= cols, "pack: ld_dst < cols");
+  return launch_pack_bf16(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols, ld_dst,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int scv_op_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, float* y, int32_t ldy,
+                     int32_t M, int32_t N, int32_t act, void* stream) {
+  return launch_layernorm(x, ldx, gamma, beta, y, ldy, M, N, act, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Shared helpers for the scvae_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace scv {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SCV_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::scv::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+#define SCV_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::scv::set_error(__VA_ARGS__);           \
+      return 1;                                \
+    }                                          \
+  } while (0)
+
+#define SCV_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+#define SCV_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    ::scv::count_launch();                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::scv::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+// Optional per-category kernel timing (CUDA events on the launch stream), used by bench.py's roofline pass.
+enum ProfCat : int { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_SELF, PC_ATTN_CROSS, PC_SAMPLER, PC_EMBED, PC_MISC,
+                     PC_GEMM_TC, PC_COUNT };
+bool prof_enabled();
+struct ProfScope {
+  ProfScope(int cat, cudaStream_t s, double flops, double bytes);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t s_;
+};
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+
+constexpr int kEndIdx = 2;    // END_IDX (models/autoregressive_decoder.py:97)
+constexpr int kStartIdx = 1;  // START_IDX (:96)
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return gelu_erf(v);
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_SIGMOID: return sigmoidf_(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the multinomial sampler ----
+struct Philox {
+  __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ static inline void run(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+  }
+  // uniform in [0, 1) with 24 random bits
+  __device__ static inline float uniform(uint64_t seed, uint64_t offset, uint32_t row, uint32_t step) {
+    uint32_t c[4] = {step, row, (uint32_t)offset, (uint32_t)(offset >> 32)};
+    run(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (float)(c[0] >> 8) * (1.0f / 16777216.0f);
+  }
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ---------------- kernel launchers shared between translation units ----------------
+struct LinearArgs {
+  const float* x = nullptr; int ldx = 0;
+  const __nv_bfloat16* w = nullptr; int ldw = 0;   // [N, ldw] bf16, zero padded beyond K
+  const float* bias = nullptr;
+  const float* residual = nullptr; int ldr = 0;    // may alias y
+  float* y = nullptr; int ldy = 0;
+  int M = 0, N = 0, K = 0;
+  int act = ACT_NONE;
+  const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
+};
+int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
+int launch_linear(const LinearArgs& a, int impl, cudaStream_t s);   // impl 0 auto, 1 simt, 2 tcgen05
+
+int launch_pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int ld_dst, cudaStream_t s);
+int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t s);
+int launch_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy, int M,
+                     int N, int act, const int* done_flag, cudaStream_t s);
+
+}  // namespace scv

@@ -1,0 +1,481 @@
+// Per-step decode kernels: token embedding + positional encoding, warp-level flash-decode attention over
+// the paged self-attention KV cache (and over the per-layer projected memory tokens for cross-attention),
+// and the fused sampling epilogue (type mask, stop head, degenerate guard, entropy, temperature,
+// argmax / Philox multinomial, log-prob, finished bookkeeping).
+#include <limits.h>
+
+#include "decode_kernels.cuh"
+
+namespace scv {
+
+// ---------------------------------------------------------------------------------------------
+// x = token_embedding[cur] + pe[step]   (models/autoregressive_decoder.py:1405, 1233)
+// Also grows the row's KV page list when the step crosses a page boundary.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
+  if (a.st->done) return;
+  const int b = blockIdx.x;
+  const int step = a.st->step;
+  if (threadIdx.x == 0 && (step & (kPagePos - 1)) == 0) {
+    a.page_table[b * a.pages_per_seq + (step >> kPageShift)] = atomicAdd(&a.st->next_free_page, 1);
+  }
+  const int tok = a.cur_tokens[b];
+  const __nv_bfloat16* row = a.table + (size_t)tok * a.ld_table;
+  const float* pe = a.pe + (size_t)step * a.d;
+  float* x = a.x + (size_t)b * a.d;
+  for (int i = threadIdx.x; i < a.d; i += blockDim.x) x[i] = __bfloat162float(row[i]) + pe[i];
+}
+
+int launch_embed(const EmbedArgs& a, cudaStream_t s) {
+  ProfScope prof(PC_EMBED, s, 1.0 * a.B * a.d, 6.0 * a.B * a.d);
+  embed_kernel<<<a.B, 128, 0, s>>>(a);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flash-decode attention for ONE query token per (row, head): one warp per (row, head).
+//   self  (:1259-1290): append this step's k,v to the paged cache, attend over positions 0..step
+//   cross (:1302-1307): attend over the n_memory projected memory tokens of this layer
+// fp32 throughout (scores, softmax, accumulation), same operation order as the reference:
+// (q.k) * scale -> softmax (exp(x-max)/sum) -> sum_p w_p v_p.
+// Lane l owns head-dim elements l, l+32, ... so every cache row is read as coalesced 128-byte segments.
+// ---------------------------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs a) {
+  extern __shared__ float sc_all[];
+  if (a.st->done) return;
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (gw >= a.B * a.nhead) return;
+  const int b = gw / a.nhead, h = gw % a.nhead;
+  const int hd = a.hd;
+  const int n = a.fixed_len >= 0 ? a.fixed_len : a.st->step + 1;
+  float* sc = sc_all + (size_t)warp_in_block * a.max_n;
+
+  float qv[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const int e = lane + 32 * j;
+    qv[j] = e < hd ? a.q[(size_t)b * a.ldq + h * hd + e] : 0.f;
+  }
+  const bool paged = a.page_table != nullptr;
+  const int* pt = paged ? a.page_table + (size_t)b * a.pages_per_seq : nullptr;
+  auto row_off = [&](int p) -> size_t {
+    if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
+    return (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * hd;
+  };
+
+  if (a.knew != nullptr) {   // append (torch.cat in the reference, :1266-1267)
+    const size_t off = row_off(n - 1);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + 32 * j;
+      if (e < hd) {
+        a.kcache[off + e] = a.knew[(size_t)b * a.ldn + h * hd + e];
+        a.vcache[off + e] = a.vnew[(size_t)b * a.ldn + h * hd + e];
+      }
+    }
+  }
+
+  // scores
+  for (int p0 = 0; p0 < n; p0 += 4) {
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u;
+      float d = 0.f;
+      if (p < n) {
+        const float* kp = a.kcache + row_off(p);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const int e = lane + 32 * j;
+          if (e < hd) d = fmaf(qv[j], kp[e], d);
+        }
+      }
+      part[u] = d;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part[u] = warp_sum(part[u]);
+    float sel = part[0];
+    if (lane == 1) sel = part[1];
+    if (lane == 2) sel = part[2];
+    if (lane == 3) sel = part[3];
+    if (lane < 4 && p0 + lane < n) sc[p0 + lane] = sel * a.scale;
+  }
+  __syncwarp();
+  float m = -INFINITY;
+  for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int p = lane; p < n; p += 32) {
+    const float e = expf(sc[p] - m);
+    sc[p] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
+  __syncwarp();
+
+  float acc[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+  int p = 0;
+  for (; p + 4 <= n; p += 4) {
+    float vv[4][EPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* vp = a.vcache + row_off(p + u);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const int e = lane + 32 * j;
+        vv[u][j] = e < hd ? vp[e] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float w = sc[p + u];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) acc[j] = fmaf(w, vv[u][j], acc[j]);
+    }
+  }
+  for (; p < n; ++p) {
+    const float* vp = a.vcache + row_off(p);
+    const float w = sc[p];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + 32 * j;
+      if (e < hd) acc[j] = fmaf(w, vp[e], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const int e = lane + 32 * j;
+    if (e < hd) a.out[(size_t)b * a.ldo + h * hd + e] = acc[j];
+  }
+}
+
+int launch_attention(const AttnArgs& a, cudaStream_t s) {
+  SCV_REQUIRE(a.hd >= 1 && a.hd <= 128, "attention: head_dim %d not in 1..128", a.hd);
+  SCV_REQUIRE(a.max_n >= 1, "attention: max_n must be positive");
+  const int warps = 8;
+  const int blocks = ceil_div(a.B * a.nhead, warps);
+  const size_t smem = (size_t)warps * a.max_n * sizeof(float);
+  const int epl = ceil_div(a.hd, 32);
+  const double n_hint = a.fixed_len >= 0 ? a.fixed_len : a.host_len_hint;
+  // algorithmic traffic: K and V rows of every attended position (fp32) + q, out, and the appended row
+  ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
+                 4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
+  switch (epl) {
+    case 1: attention_decode_kernel<1><<<blocks, warps * 32, smem, s>>>(a); break;
+    case 2: attention_decode_kernel<2><<<blocks, warps * 32, smem, s>>>(a); break;
+    case 3: attention_decode_kernel<3><<<blocks, warps * 32, smem, s>>>(a); break;
+    default: attention_decode_kernel<4><<<blocks, warps * 32, smem, s>>>(a); break;
+  }
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampling epilogue (:1415-1548).  One CTA per row, the row's logits staged once in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSamplerThreads = 256;
+
+__device__ __forceinline__ bool arg_better(float a, int ia, float b, int ib) {
+  const bool an = isnan(a), bn = isnan(b);     // torch.argmax treats NaN as the maximum
+  if (an != bn) return an;
+  if (!an && a != b) return a > b;
+  return ia < ib;                              // first occurrence wins ties
+}
+
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSamplerThreads / 32; ++i) t += red[i];
+  return t;
+}
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSamplerThreads / 32; ++i) t = fmaxf(t, red[i]);
+  return t;
+}
+__device__ int block_argmax(const float* sl, int V, float* redv, int* redi) {
+  float bv = -INFINITY;
+  int bi = INT_MAX;
+  for (int v = threadIdx.x; v < V; v += kSamplerThreads)
+    if (arg_better(sl[v], v, bv, bi)) { bv = sl[v]; bi = v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { redv[w] = bv; redi[w] = bi; }
+  __syncthreads();
+  bv = redv[0]; bi = redi[0];
+#pragma unroll
+  for (int i = 1; i < kSamplerThreads / 32; ++i)
+    if (arg_better(redv[i], redi[i], bv, bi)) { bv = redv[i]; bi = redi[i]; }
+  return bi;
+}
+
+// Stage the row's logits with type mask (:1416-1422), stop boost (:1438-1441), hard stop (:1444-1448) and
+// length boost (:1455-1457) applied, in the reference's order.  Returns bit0: row has nan/+-inf,
+// bit1: row has nan/+inf (a genuine numerical failure rather than a mask).
+__device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
+  int pred_type = 0;
+  if (a.type_masks != nullptr) {
+    const float* tl = a.type_logits + (size_t)b * a.ldt;
+    float bv = tl[0];
+    for (int t = 1; t < 5; ++t)
+      if (arg_better(tl[t], t, bv, pred_type)) { bv = tl[t]; pred_type = t; }
+  }
+  const bool stop_on = a.stop_boost > 0.f;
+  float sp = 0.f;
+  bool force = false;
+  if (stop_on) {
+    sp = sigmoidf_(a.stop_logits[b]);
+    force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
+  }
+  const float length_boost =
+      (stop_on && step > 10) ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
+  const float* lg = a.logits + (size_t)b * a.ldl;
+  const uint8_t* mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
+  int bad = 0;
+  for (int v = threadIdx.x; v < a.V; v += kSamplerThreads) {
+    float l = lg[v];
+    if (mk != nullptr && mk[v] == 0) l = -INFINITY;
+    if (v == kEndIdx && stop_on) l = l + a.stop_boost * sp;
+    if (force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
+    if (v == kEndIdx && stop_on && step > 10) l = l + length_boost;
+    sl[v] = l;
+    if (isnan(l) || isinf(l)) bad |= 1;
+    if (isnan(l) || (isinf(l) && l > 0.f)) bad |= 2;
+  }
+  return bad;
+}
+
+__device__ void commit_token(const SamplerArgs& a, int b, int step, int token, float logprob) {
+  // single thread
+  if (a.forced != nullptr) token = (int)a.forced[(size_t)b * a.out_ld + step];
+  a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
+  if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
+  a.cur_tokens[b] = token;
+  if (token == kEndIdx && a.finished[b] == 0) {
+    a.finished[b] = 1;
+    atomicSub(&a.st->n_unfinished, 1);
+  }
+}
+
+// Phase 1: stage logits, publish the degenerate flag; when the call is plain greedy, also pick the token.
+__global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(SamplerArgs a, int finalize) {
+  extern __shared__ float sl[];
+  __shared__ float redv[kSamplerThreads / 32];
+  __shared__ int redi[kSamplerThreads / 32];
+  if (a.st->done) return;
+  const int b = blockIdx.x, step = a.st->step;
+  const int bad = stage_logits(a, b, step, sl);
+  const int row_bad = __syncthreads_or(bad & 1);
+  if (threadIdx.x == 0 && row_bad) atomicOr(&a.st->degenerate, 1);
+  if (!finalize) return;
+  if (a.temperature != 1.0f) {
+    for (int v = threadIdx.x; v < a.V; v += kSamplerThreads) sl[v] = sl[v] / a.temperature;   // (:1485-1486)
+    __syncthreads();
+  }
+  const int tok = block_argmax(sl, a.V, redv, redi);                                          // (:1507)
+  if (threadIdx.x == 0) commit_token(a, b, step, tok, 0.f);
+}
+
+// Phase 2: entropy, temperature, multinomial (or argmax) and log-prob, given the batch-global flag.
+__global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(SamplerArgs a) {
+  extern __shared__ float sl[];
+  __shared__ float redv[kSamplerThreads / 32];
+  __shared__ int redi[kSamplerThreads / 32];
+  __shared__ float scan[kSamplerThreads];
+  __shared__ int pick;
+  if (a.st->done) return;
+  const int b = blockIdx.x, step = a.st->step, V = a.V, tid = threadIdx.x;
+  const int bad = stage_logits(a, b, step, sl);
+  const int row_real_bad = __syncthreads_or(bad & 2);
+  const bool degenerate = (a.flags & 1u) ? (a.st->degenerate != 0) : (row_real_bad != 0);
+
+  if (a.out_entropy != nullptr) {                                                   // (:1470-1482)
+    float H;
+    if (degenerate) {
+      H = logf((float)max(V, 1));
+    } else {
+      float m = -INFINITY;
+      for (int v = tid; v < V; v += kSamplerThreads) m = fmaxf(m, sl[v]);
+      m = block_max(m, redv);
+      float s = 0.f;
+      for (int v = tid; v < V; v += kSamplerThreads) s += expf(sl[v] - m);
+      s = block_sum(s, redv);
+      float h = 0.f;
+      for (int v = tid; v < V; v += kSamplerThreads) {
+        const float p = fmaxf(expf(sl[v] - m) / s, 1e-8f);
+        h += p * logf(p);
+      }
+      H = -block_sum(h, redv);
+    }
+    if (tid == 0) a.out_entropy[(size_t)b * a.out_ld + step] = H;
+  }
+  if (a.temperature != 1.0f) {
+    __syncthreads();
+    for (int v = tid; v < V; v += kSamplerThreads) sl[v] = sl[v] / a.temperature;
+  }
+  __syncthreads();
+  if (a.temperature < 0.01f) {
+    const int tok = block_argmax(sl, V, redv, redi);
+    if (tid == 0) commit_token(a, b, step, tok, 0.f);
+    return;
+  }
+  // probs = softmax(logits) (:1511); uniform when degenerate (:1512-1513)
+  const float u = Philox::uniform(a.seed, a.offset, (uint32_t)b, (uint32_t)step);
+  if (degenerate) {
+    if (tid == 0) {
+      int tok = min((int)(u * (float)V), V - 1);
+      commit_token(a, b, step, tok, logf(fmaxf(1.0f / (float)V, 1e-8f)));
+    }
+    return;
+  }
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += kSamplerThreads) m = fmaxf(m, sl[v]);
+  m = block_max(m, redv);
+  // contiguous chunk per thread so that the inverse-CDF walk is in token-id order
+  const int chunk = (V + kSamplerThreads - 1) / kSamplerThreads;
+  const int v0 = min(tid * chunk, V), v1 = min(v0 + chunk, V);
+  float csum = 0.f;
+  int last_pos = -1;
+  for (int v = v0; v < v1; ++v) {
+    const float e = expf(sl[v] - m);
+    sl[v] = e;
+    csum += e;
+    if (e > 0.f) last_pos = v;
+  }
+  scan[tid] = csum;
+  if (tid == 0) pick = -1;
+  __syncthreads();
+  // exclusive scan over 256 chunk sums by one warp (8 values per lane)
+  if (tid < 32) {
+    float loc[kSamplerThreads / 32];
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSamplerThreads / 32; ++i) { loc[i] = run; run += scan[tid * (kSamplerThreads / 32) + i]; }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += t;
+    }
+    const float excl = incl - run;
+#pragma unroll
+    for (int i = 0; i < kSamplerThreads / 32; ++i) scan[tid * (kSamplerThreads / 32) + i] = excl + loc[i];
+    if (tid == 31) redv[0] = incl;   // total
+  }
+  __syncthreads();
+  const float total = redv[0];
+  const float target = u * total;
+  const float excl = scan[tid];
+  const float next_excl = (tid + 1 < kSamplerThreads) ? scan[tid + 1] : INFINITY;
+  if (target >= excl && target < next_excl && v0 < v1) {
+    float run = excl;
+    int found = -1, cand = -1;
+    for (int v = v0; v < v1; ++v) {
+      run += sl[v];
+      if (sl[v] > 0.f) {
+        cand = v;
+        if (run > target) { found = v; break; }
+      }
+    }
+    if (found < 0) found = cand;   // summation-order rounding at the chunk edge
+    if (found >= 0) pick = found;
+  }
+  // fallback for rounding at chunk edges: the last token with non-zero probability at or before ... any
+  int lp = last_pos;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lp = max(lp, __shfl_xor_sync(0xffffffffu, lp, o));
+  __syncthreads();
+  if ((tid & 31) == 0) redi[tid >> 5] = lp;
+  __syncthreads();
+  if (tid == 0) {
+    int tok = pick;
+    if (tok < 0) {
+      tok = 0;
+      for (int i = 0; i < kSamplerThreads / 32; ++i) tok = max(tok, redi[i]);
+    }
+    if (a.forced != nullptr) tok = (int)a.forced[(size_t)b * a.out_ld + step];
+    const float p = sl[tok] / total;
+    commit_token(a, b, step, tok, logf(fmaxf(p, 1e-8f)));                            // (:1518)
+  }
+}
+
+int launch_sampler(const SamplerArgs& a, cudaStream_t s) {
+  SCV_REQUIRE(a.top_k <= 0 && !(a.top_p < 1.0f), "sampler: top_k/top_p filtering is not implemented in this build");
+  const size_t smem = (size_t)a.V * sizeof(float);
+  const bool two_phase = !(a.temperature < 0.01f) || a.want_entropy;
+  ProfScope prof(PC_SAMPLER, s, 4.0 * a.B * a.V, 4.0 * a.B * a.V * (two_phase ? 2 : 1));
+  static bool attr_set = false;
+  if (!attr_set && smem > 40 * 1024) {
+    SCV_CUDA(cudaFuncSetAttribute(sampler_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SCV_CUDA(cudaFuncSetAttribute(sampler_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  SCV_REQUIRE(smem <= 200 * 1024, "sampler: vocabulary of %d tokens does not fit in shared memory", a.V);
+  sampler_phase1_kernel<<<a.B, kSamplerThreads, smem, s>>>(a, two_phase ? 0 : 1);
+  SCV_LAUNCH_CHECK();
+  if (two_phase) {
+    sampler_phase2_kernel<<<a.B, kSamplerThreads, smem, s>>>(a);
+    SCV_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+__global__ void step_end_kernel(StepState* st, int max_steps) {
+  if (st->done) return;
+  const int s = st->step + 1;
+  st->step = s;
+  st->degenerate = 0;
+  if (st->n_unfinished <= 0 || s >= max_steps) {   // finished.all() -> break (:1547-1548)
+    st->done = 1;
+    st->out_len = s;
+  }
+}
+
+int launch_step_end(StepState* st, int max_steps, cudaStream_t s) {
+  step_end_kernel<<<1, 1, 0, s>>>(st, max_steps);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B, StepState* st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    cur_tokens[i] = kStartIdx;     // (:1392)
+    finished[i] = 0;
+  }
+  if (i == 0) {
+    st->step = 0; st->done = 0; st->n_unfinished = B; st->out_len = 0; st->degenerate = 0; st->next_free_page = 0;
+  }
+}
+
+int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, cudaStream_t s) {
+  init_rows_kernel<<<ceil_div(B, 256), 256, 0, s>>>(cur_tokens, finished, B, st);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace scv

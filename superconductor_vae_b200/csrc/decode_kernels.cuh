@@ -1,0 +1,68 @@
+// Device-side state and launchers of the per-step decode kernels.
+#pragma once
+#include "common.cuh"
+
+namespace scv {
+
+constexpr int kPageShift = 4;               // 16 cached positions per KV page
+constexpr int kPagePos = 1 << kPageShift;
+
+// Lives in device memory; every per-step kernel reads it instead of taking the position as a launch
+// argument, so the same launch sequence (or CUDA graph) serves every step and the host never has to
+// synchronise inside the loop (the reference syncs 3-5 times per step: finished.all(), .any() ...).
+struct StepState {
+  int step;            // position being decoded (range(max_len - 1), autoregressive_decoder.py:1403)
+  int done;            // set once every row has emitted END (:1547) or the step budget is used up
+  int n_unfinished;    // rows that have not emitted END yet
+  int out_len;         // number of executed steps L
+  int degenerate;      // batch-global "logits contain nan/inf" flag of the current step (:1464-1466)
+  int next_free_page;  // bump allocator over the KV page pool
+  int pad[2];
+};
+
+struct EmbedArgs {
+  const __nv_bfloat16* table; int ld_table;     // token_embedding.weight [V, d] (bf16, padded rows)
+  const float* pe; int d;                        // pos_encoding.pe [pe_len, d]
+  const int* cur_tokens;                         // [B]
+  float* x; int B;
+  int* page_table; int pages_per_seq;
+  StepState* st;
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t s);
+
+struct AttnArgs {
+  const float* q = nullptr; int ldq = 0;
+  const float* knew = nullptr; const float* vnew = nullptr; int ldn = 0;   // self-attention: row to append
+  float* kcache = nullptr; float* vcache = nullptr;     // layer / k-v offsets already applied
+  const int* page_table = nullptr; int pages_per_seq = 0; long long page_stride = 0;   // paged (self)
+  long long seq_stride = 0; int row_stride = 0;          // contiguous (cross): b*seq_stride + p*row_stride
+  float* out = nullptr; int ldo = 0;
+  int B = 0, nhead = 0, hd = 0; float scale = 1.f;
+  int fixed_len = -1;                                    // cross: memory tokens; self: -1 -> step + 1
+  int max_n = 0;                                         // smem scores per warp
+  int host_len_hint = 0;                                 // host's view of step + 1 (profiling byte counts only)
+  const StepState* st = nullptr;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t s);
+
+struct SamplerArgs {
+  const float* logits = nullptr; int ldl = 0;
+  const float* type_logits = nullptr; int ldt = 0;
+  const float* stop_logits = nullptr;
+  const uint8_t* type_masks = nullptr;
+  int B = 0, V = 0, max_len = 0;
+  float temperature = 1.f; int top_k = 0; float top_p = 1.f;
+  float stop_boost = 0.f, hard_stop = 0.f;
+  int want_logprobs = 0, want_entropy = 0; unsigned flags = 0;
+  unsigned long long seed = 0, offset = 0;
+  long long* out_tokens = nullptr; float* out_logprobs = nullptr; float* out_entropy = nullptr; int out_ld = 0;
+  int* cur_tokens = nullptr; unsigned char* finished = nullptr;
+  const long long* forced = nullptr;
+  StepState* st = nullptr;
+};
+// one or two kernels (the second only when sampling or entropy is requested)
+int launch_sampler(const SamplerArgs& a, cudaStream_t s);
+int launch_step_end(StepState* st, int max_steps, cudaStream_t s);
+int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, cudaStream_t s);
+
+}  // namespace scv

@@ -1,0 +1,425 @@
+// EnhancedTransformerDecoder engine: weight layout, memory builder, KV-cache decode loop.
+// Reference: src/superconductor/models/autoregressive_decoder.py:544-899 (module + memory),
+// :1175-1557 (KV-cache decode).  See DESIGN.md for the data layout and the kernel list.
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/scvae_b200.h"
+#include "decode_kernels.cuh"
+#include "weights.cuh"
+
+using namespace scv;
+
+namespace {
+
+struct DecLayer {
+  LNp n1, n2, n3;
+  __nv_bfloat16* sa_in_w = nullptr; float* sa_in_b = nullptr; int sa_in_ld = 0;   // [3d, d]
+  Lin sa_out;
+  __nv_bfloat16* ca_in_w = nullptr; float* ca_in_b = nullptr; int ca_in_ld = 0;   // [3d, d] rows q;k;v
+  Lin ca_out;
+  Lin ff1, ff2;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    SCV_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct scv_decoder {
+  scv_decoder_config cfg{};
+  WeightStore ws;
+  __nv_bfloat16* emb = nullptr; int ld_emb = 0;
+  float* pe = nullptr;
+  Lin l2m_a, l2m_b; LNp l2m_ln;
+  Lin s2m_a, s2m_b; LNp s2m_ln;
+  Lin h2m_a, h2m_b, h2m_c; LNp h2m_ln;
+  Lin skip_a, skip_b;
+  std::vector<DecLayer> layers;
+  LNp out_ln; Lin out_a, out_b;
+  Lin stop_a, stop_b, dup_a, dup_b;
+  LNp tt_ln; Lin tt_a, tt_b, tt_c;
+  // workspaces (engine-owned, grown on demand)
+  DevBuf x, xn, qkv, attn, q2, ff, h1, h2, t3, logits, tlog, slog, ckv, kvpool, cur, fin, ptab, state, mtmp;
+  int* pinned = nullptr;              // host-pinned: [0..1] done polls, [2..9] StepState copy
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int last_B = 0;
+
+  ~scv_decoder() {
+    for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
+                      &fin, &ptab, &state, &mtmp})
+      b->release();
+    if (pinned) cudaFreeHost(pinned);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+};
+
+static int dec_register(scv_decoder* D) {
+  const scv_decoder_config& c = D->cfg;
+  const int d = c.d_model;
+  WeightStore& W = D->ws;
+  D->emb = W.add_matrix("token_embedding.weight", c.vocab_size, d, &D->ld_emb);
+  D->pe = W.add_vector("pos_encoding.pe", (int64_t)c.pe_len * d);
+  if (!D->emb || !D->pe) return 2;
+  const int n_lat = d * c.n_memory_tokens;
+  if (c.memory_bottleneck_dim > 0) {
+    SCV_TRY(W.add_linear("latent_to_memory.0", c.memory_bottleneck_dim, c.latent_dim, &D->l2m_a));
+    SCV_TRY(W.add_layernorm("latent_to_memory.1", c.memory_bottleneck_dim, &D->l2m_ln));
+    SCV_TRY(W.add_linear("latent_to_memory.3", n_lat, c.memory_bottleneck_dim, &D->l2m_b));
+  } else {
+    SCV_TRY(W.add_linear("latent_to_memory.0", n_lat / 2, c.latent_dim, &D->l2m_a));
+    SCV_TRY(W.add_linear("latent_to_memory.2", n_lat, n_lat / 2, &D->l2m_b));
+  }
+  if (c.skip_n_tokens > 0) {
+    const int n_skip = d * c.skip_n_tokens;
+    SCV_TRY(W.add_linear("skip_to_memory.0", n_skip / 2, c.encoder_skip_dim, &D->skip_a));
+    SCV_TRY(W.add_linear("skip_to_memory.2", n_skip, n_skip / 2, &D->skip_b));
+  }
+  if (c.n_stoich_tokens > 0) {
+    SCV_TRY(W.add_linear("stoich_to_memory.0", d, c.stoich_input_dim, &D->s2m_a));
+    SCV_TRY(W.add_layernorm("stoich_to_memory.1", d, &D->s2m_ln));
+    SCV_TRY(W.add_linear("stoich_to_memory.3", d * c.n_stoich_tokens, d, &D->s2m_b));
+  }
+  if (c.heads_n_tokens > 0) {
+    SCV_TRY(W.add_linear("heads_to_memory.0", d / 2, c.heads_input_dim, &D->h2m_a));
+    SCV_TRY(W.add_layernorm("heads_to_memory.1", d / 2, &D->h2m_ln));
+    SCV_TRY(W.add_linear("heads_to_memory.3", d, d / 2, &D->h2m_b));
+    SCV_TRY(W.add_linear("heads_to_memory.5", d * c.heads_n_tokens, d, &D->h2m_c));
+  }
+  D->layers.resize(c.num_layers);
+  for (int i = 0; i < c.num_layers; ++i) {
+    DecLayer& L = D->layers[i];
+    const std::string p = "transformer_decoder.layers." + std::to_string(i) + ".";
+    L.sa_in_w = W.add_matrix(p + "self_attn.in_proj_weight", 3 * d, d, &L.sa_in_ld);
+    L.sa_in_b = W.add_vector(p + "self_attn.in_proj_bias", 3 * d);
+    L.ca_in_w = W.add_matrix(p + "multihead_attn.in_proj_weight", 3 * d, d, &L.ca_in_ld);
+    L.ca_in_b = W.add_vector(p + "multihead_attn.in_proj_bias", 3 * d);
+    if (!L.sa_in_w || !L.sa_in_b || !L.ca_in_w || !L.ca_in_b) return 2;
+    SCV_TRY(W.add_linear(p + "self_attn.out_proj", d, d, &L.sa_out));
+    SCV_TRY(W.add_linear(p + "multihead_attn.out_proj", d, d, &L.ca_out));
+    SCV_TRY(W.add_linear(p + "linear1", c.dim_feedforward, d, &L.ff1));
+    SCV_TRY(W.add_linear(p + "linear2", d, c.dim_feedforward, &L.ff2));
+    SCV_TRY(W.add_layernorm(p + "norm1", d, &L.n1));
+    SCV_TRY(W.add_layernorm(p + "norm2", d, &L.n2));
+    SCV_TRY(W.add_layernorm(p + "norm3", d, &L.n3));
+  }
+  SCV_TRY(W.add_layernorm("output_proj.0", d, &D->out_ln));
+  SCV_TRY(W.add_linear("output_proj.1", d, d, &D->out_a));
+  SCV_TRY(W.add_linear("output_proj.4", c.vocab_size, d, &D->out_b));
+  SCV_TRY(W.add_linear("stop_head.0", d / 4, d, &D->stop_a));
+  SCV_TRY(W.add_linear("stop_head.2", 1, d / 4, &D->stop_b));
+  SCV_TRY(W.add_linear("site_dup_head.0", d / 4, d, &D->dup_a));
+  SCV_TRY(W.add_linear("site_dup_head.2", 1, d / 4, &D->dup_b));
+  for (const char* n : {"site_dup_head.0.weight", "site_dup_head.0.bias", "site_dup_head.2.weight", "site_dup_head.2.bias"})
+    W.mark_optional(n);   // older checkpoints lack it; only used when site_dup_threshold > 0
+  SCV_TRY(W.add_layernorm("token_type_head.0", d, &D->tt_ln));
+  SCV_TRY(W.add_linear("token_type_head.1", d, d, &D->tt_a));
+  SCV_TRY(W.add_linear("token_type_head.4", d / 4, d, &D->tt_b));
+  SCV_TRY(W.add_linear("token_type_head.7", 5, d / 4, &D->tt_c));
+  return 0;
+}
+
+static LinearArgs lin_args(const float* x, int ldx, const Lin& L, float* y, int ldy, int M, int act,
+                           const int* done = nullptr) {
+  LinearArgs a;
+  a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.bias = L.b; a.y = y; a.ldy = ldy;
+  a.M = M; a.N = L.N; a.K = L.K; a.act = act; a.done_flag = done;
+  return a;
+}
+
+extern "C" {
+
+int scv_decoder_create(const scv_decoder_config* cfg, scv_decoder** out) {
+  SCV_REQUIRE(cfg && out, "null argument");
+  SCV_REQUIRE(cfg->d_model > 0 && cfg->nhead > 0 && cfg->d_model % cfg->nhead == 0,
+              "d_model %d must be a positive multiple of nhead %d", cfg->d_model, cfg->nhead);
+  SCV_REQUIRE(cfg->d_model / cfg->nhead <= 128, "head_dim > 128 is not supported");
+  SCV_REQUIRE(cfg->num_layers > 0 && cfg->vocab_size > kEndIdx && cfg->pe_len > 1 && cfg->dim_feedforward > 0,
+              "bad decoder shape");
+  SCV_REQUIRE(cfg->latent_dim > 0 && cfg->n_memory_tokens > 0, "bad memory shape");
+  int dev = 0;
+  SCV_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SCV_CUDA(cudaGetDeviceProperties(&prop, dev));
+  SCV_REQUIRE(prop.major == 10, "scvae_b200 is built for sm_100a; device %s is sm_%d%d", prop.name, prop.major,
+              prop.minor);
+  scv_decoder* D = new scv_decoder();
+  D->cfg = *cfg;
+  int rc = dec_register(D);
+  if (rc == 0 && cudaMallocHost(reinterpret_cast<void**>(&D->pinned), 16 * sizeof(int)) != cudaSuccess) {
+    set_error("cudaMallocHost failed");
+    rc = 2;
+  }
+  if (rc == 0) {
+    for (auto& e : D->ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { set_error("event create failed"); rc = 2; }
+  }
+  if (rc != 0) { delete D; return rc; }
+  *out = D;
+  return 0;
+}
+
+void scv_decoder_destroy(scv_decoder* dec) { delete dec; }
+
+int scv_decoder_load_weight(scv_decoder* dec, const char* name, const float* src, int64_t numel, void* stream) {
+  SCV_REQUIRE(dec && name && src, "null argument");
+  return dec->ws.load(name, src, numel, static_cast<cudaStream_t>(stream));
+}
+
+int scv_decoder_missing_weights(scv_decoder* dec) {
+  std::string first;
+  const int n = dec->ws.missing(&first);
+  if (n > 0) set_error("%d state_dict entries not loaded, first: %s", n, first.c_str());
+  return n;
+}
+
+int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const float* skip, const float* stoich,
+                             const float* heads_in, float* memory_out, int32_t* n_tokens_out, void* stream) {
+  SCV_REQUIRE(D && z && memory_out && B > 0, "build_memory: bad arguments");
+  SCV_REQUIRE(scv_decoder_missing_weights(D) == 0, "build_memory: weights missing");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const scv_decoder_config& c = D->cfg;
+  const int d = c.d_model;
+  const bool use_skip = skip != nullptr && c.skip_n_tokens > 0;          // (:806)
+  const bool use_stoich = stoich != nullptr && c.n_stoich_tokens > 0;    // (:813)
+  const bool use_heads = heads_in != nullptr && c.heads_n_tokens > 0;    // (:821)
+  const int M = c.n_memory_tokens + (use_skip ? c.skip_n_tokens : 0) + (use_stoich ? c.n_stoich_tokens : 0) +
+                (use_heads ? c.heads_n_tokens : 0);
+  if (n_tokens_out) *n_tokens_out = M;
+  const int ldm = M * d;
+  const int hid = std::max(std::max(D->l2m_a.N, d), c.skip_n_tokens > 0 ? D->skip_a.N : 0);
+  SCV_TRY(D->mtmp.ensure((size_t)B * (hid + d) * sizeof(float)));
+  float* t0 = D->mtmp.as<float>();
+  float* t1 = t0 + (size_t)B * hid;
+  int col = 0;
+  // latent tokens (:800-801)
+  if (c.memory_bottleneck_dim > 0) {
+    SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, D->l2m_a.N, B, ACT_NONE), 0, s));
+    SCV_TRY(launch_layernorm(t0, D->l2m_a.N, D->l2m_ln.g, D->l2m_ln.b, t0, D->l2m_a.N, B, D->l2m_a.N, ACT_GELU, nullptr, s));
+  } else {
+    SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, D->l2m_a.N, B, ACT_GELU), 0, s));
+  }
+  SCV_TRY(launch_linear(lin_args(t0, D->l2m_a.N, D->l2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
+  col += c.n_memory_tokens * d;
+  if (use_skip) {                                                          // (:806-809)
+    SCV_TRY(launch_linear(lin_args(skip, c.encoder_skip_dim, D->skip_a, t0, D->skip_a.N, B, ACT_GELU), 0, s));
+    SCV_TRY(launch_linear(lin_args(t0, D->skip_a.N, D->skip_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    col += c.skip_n_tokens * d;
+  }
+  if (use_stoich) {                                                        // (:813-816)
+    SCV_TRY(launch_linear(lin_args(stoich, c.stoich_input_dim, D->s2m_a, t0, d, B, ACT_NONE), 0, s));
+    SCV_TRY(launch_layernorm(t0, d, D->s2m_ln.g, D->s2m_ln.b, t0, d, B, d, ACT_GELU, nullptr, s));
+    SCV_TRY(launch_linear(lin_args(t0, d, D->s2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    col += c.n_stoich_tokens * d;
+  }
+  if (use_heads) {                                                         // (:858-868)
+    SCV_TRY(launch_linear(lin_args(heads_in, c.heads_input_dim, D->h2m_a, t0, d / 2, B, ACT_NONE), 0, s));
+    SCV_TRY(launch_layernorm(t0, d / 2, D->h2m_ln.g, D->h2m_ln.b, t0, d / 2, B, d / 2, ACT_GELU, nullptr, s));
+    SCV_TRY(launch_linear(lin_args(t0, d / 2, D->h2m_b, t1, d, B, ACT_GELU), 0, s));
+    SCV_TRY(launch_linear(lin_args(t1, d, D->h2m_c, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    col += c.heads_n_tokens * d;
+  }
+  return 0;
+}
+
+static int ensure_workspace(scv_decoder* D, int B, int M) {
+  const scv_decoder_config& c = D->cfg;
+  const size_t d = c.d_model, f = sizeof(float);
+  const int pps = ceil_div(c.pe_len, kPagePos);
+  SCV_TRY(D->x.ensure(B * d * f));
+  SCV_TRY(D->xn.ensure(B * d * f));
+  SCV_TRY(D->qkv.ensure(B * 3 * d * f));
+  SCV_TRY(D->attn.ensure(B * d * f));
+  SCV_TRY(D->q2.ensure(B * d * f));
+  SCV_TRY(D->ff.ensure((size_t)B * c.dim_feedforward * f));
+  SCV_TRY(D->h1.ensure(B * d * f));
+  SCV_TRY(D->h2.ensure(B * d * f));
+  SCV_TRY(D->t3.ensure(B * d * f));
+  SCV_TRY(D->logits.ensure((size_t)B * c.vocab_size * f));
+  SCV_TRY(D->tlog.ensure((size_t)B * 8 * f));
+  SCV_TRY(D->slog.ensure((size_t)B * f));
+  SCV_TRY(D->ckv.ensure((size_t)c.num_layers * B * M * 2 * d * f));
+  SCV_TRY(D->kvpool.ensure((size_t)B * pps * c.num_layers * 2 * kPagePos * d * f));
+  SCV_TRY(D->cur.ensure((size_t)B * sizeof(int)));
+  SCV_TRY(D->fin.ensure((size_t)B));
+  SCV_TRY(D->ptab.ensure((size_t)B * pps * sizeof(int)));
+  SCV_TRY(D->state.ensure(sizeof(StepState)));
+  return 0;
+}
+
+static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max, int host_step, cudaStream_t s) {
+  const scv_decoder_config& c = D->cfg;
+  const int B = A->batch, M = A->n_memory, d = c.d_model, hd = d / c.nhead;
+  StepState* st = D->state.as<StepState>();
+  const int* done = &st->done;
+  const int pps = ceil_div(c.pe_len, kPagePos);
+  const float scale = (float)(1.0 / std::sqrt((double)hd));
+  float* x = D->x.as<float>(); float* xn = D->xn.as<float>(); float* qkv = D->qkv.as<float>();
+  float* attn = D->attn.as<float>(); float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>();
+
+  EmbedArgs e;
+  e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>(); e.x = x; e.B = B;
+  e.page_table = D->ptab.as<int>(); e.pages_per_seq = pps; e.st = st;
+  SCV_TRY(launch_embed(e, s));
+
+  const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& L = D->layers[li];
+    // ---- self attention (:1244-1296)
+    SCV_TRY(launch_layernorm(x, d, L.n1.g, L.n1.b, xn, d, B, d, ACT_NONE, done, s));
+    LinearArgs a;
+    a.x = xn; a.ldx = d; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
+    a.M = B; a.N = 3 * d; a.K = d; a.done_flag = done;
+    SCV_TRY(launch_linear(a, 0, s));
+    AttnArgs sa;
+    sa.q = qkv; sa.ldq = 3 * d; sa.knew = qkv + d; sa.vnew = qkv + 2 * d; sa.ldn = 3 * d;
+    sa.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
+    sa.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d;
+    sa.page_table = D->ptab.as<int>(); sa.pages_per_seq = pps; sa.page_stride = page_stride; sa.row_stride = d;
+    sa.out = attn; sa.ldo = d; sa.B = B; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale; sa.fixed_len = -1;
+    sa.max_n = std::max(c.pe_len, M); sa.st = st; sa.host_len_hint = host_step + 1;
+    SCV_TRY(launch_attention(sa, s));
+    LinearArgs o = lin_args(attn, d, L.sa_out, x, d, B, ACT_NONE, done);
+    o.residual = x; o.ldr = d;
+    SCV_TRY(launch_linear(o, 0, s));
+    // ---- cross attention to the memory tokens (:1299-1308)
+    SCV_TRY(launch_layernorm(x, d, L.n2.g, L.n2.b, xn, d, B, d, ACT_NONE, done, s));
+    LinearArgs q;
+    q.x = xn; q.ldx = d; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
+    q.M = B; q.N = d; q.K = d; q.done_flag = done;
+    SCV_TRY(launch_linear(q, 0, s));
+    AttnArgs ca;
+    float* ckv = D->ckv.as<float>() + (size_t)li * B * M * 2 * d;
+    ca.q = q2; ca.ldq = d; ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d;
+    ca.row_stride = 2 * d; ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
+    ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
+    SCV_TRY(launch_attention(ca, s));
+    LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
+    co.residual = x; co.ldr = d;
+    SCV_TRY(launch_linear(co, 0, s));
+    // ---- feed forward (:1311-1313)
+    SCV_TRY(launch_layernorm(x, d, L.n3.g, L.n3.b, xn, d, B, d, ACT_NONE, done, s));
+    SCV_TRY(launch_linear(lin_args(xn, d, L.ff1, ff, c.dim_feedforward, B, ACT_GELU, done), 0, s));
+    LinearArgs f2 = lin_args(ff, c.dim_feedforward, L.ff2, x, d, B, ACT_NONE, done);
+    f2.residual = x; f2.ldr = d;
+    SCV_TRY(launch_linear(f2, 0, s));
+  }
+  // ---- heads (:1413, 1417, 1439)
+  float* h1 = D->h1.as<float>(); float* h2 = D->h2.as<float>(); float* t3 = D->t3.as<float>();
+  SCV_TRY(launch_layernorm(x, d, D->out_ln.g, D->out_ln.b, h1, d, B, d, ACT_NONE, done, s));
+  SCV_TRY(launch_linear(lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done), 0, s));
+  SCV_TRY(launch_linear(lin_args(h2, d, D->out_b, D->logits.as<float>(), c.vocab_size, B, ACT_NONE, done), 0, s));
+  if (A->type_masks != nullptr) {
+    SCV_TRY(launch_layernorm(x, d, D->tt_ln.g, D->tt_ln.b, h1, d, B, d, ACT_NONE, done, s));
+    SCV_TRY(launch_linear(lin_args(h1, d, D->tt_a, h2, d, B, ACT_GELU, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(h2, d, D->tt_b, t3, d / 4, B, ACT_GELU, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, D->tlog.as<float>(), 8, B, ACT_NONE, done), 0, s));
+  }
+  if (A->stop_boost > 0.f) {
+    SCV_TRY(launch_linear(lin_args(x, d, D->stop_a, t3, d / 4, B, ACT_GELU, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, D->slog.as<float>(), 1, B, ACT_NONE, done), 0, s));
+  }
+  SamplerArgs sp;
+  sp.logits = D->logits.as<float>(); sp.ldl = c.vocab_size;
+  sp.type_logits = D->tlog.as<float>(); sp.ldt = 8; sp.stop_logits = D->slog.as<float>();
+  sp.type_masks = A->type_masks; sp.B = B; sp.V = c.vocab_size; sp.max_len = steps_max + 1;
+  sp.temperature = A->temperature; sp.top_k = A->top_k; sp.top_p = A->top_p;
+  sp.stop_boost = A->stop_boost; sp.hard_stop = A->hard_stop_threshold;
+  sp.want_logprobs = A->want_log_probs; sp.want_entropy = A->want_entropy; sp.flags = A->flags;
+  sp.seed = A->seed; sp.offset = A->offset;
+  sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens);
+  sp.out_logprobs = A->want_log_probs ? A->out_log_probs : nullptr;
+  sp.out_entropy = A->want_entropy ? A->out_entropy : nullptr;
+  sp.out_ld = steps_max; sp.cur_tokens = D->cur.as<int>(); sp.finished = D->fin.as<unsigned char>();
+  sp.forced = reinterpret_cast<const long long*>(A->forced_tokens); sp.st = st;
+  SCV_TRY(launch_sampler(sp, s));
+  SCV_TRY(launch_step_end(st, steps_max, s));
+  return 0;
+}
+
+int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* stream) {
+  SCV_REQUIRE(D && A, "generate: null argument");
+  SCV_REQUIRE(A->batch > 0 && A->memory && A->out_tokens && A->out_steps, "generate: bad arguments");
+  SCV_REQUIRE(A->n_memory > 0, "generate: n_memory must be positive");
+  SCV_REQUIRE(!(A->site_dup_threshold > 0.f), "generate: site_dup gating is not implemented in this build");
+  SCV_REQUIRE(!A->want_log_probs || A->out_log_probs, "generate: out_log_probs is NULL");
+  SCV_REQUIRE(!A->want_entropy || A->out_entropy, "generate: out_entropy is NULL");
+  SCV_REQUIRE(scv_decoder_missing_weights(D) == 0, "generate: weights missing");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const scv_decoder_config& c = D->cfg;
+  const int max_len = std::min(A->max_len, c.pe_len);        // silent clamp (:1372-1375)
+  const int steps_max = max_len - 1;
+  SCV_REQUIRE(steps_max >= 1, "generate: max_len %d leaves no step to run", A->max_len);
+  const int B = A->batch, M = A->n_memory, d = c.d_model;
+  SCV_TRY(ensure_workspace(D, B, M));
+  StepState* st = D->state.as<StepState>();
+  SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, s));
+  // per-layer K/V projection of the memory tokens, once per call instead of once per step and layer
+  // (the reference re-projects them inside nn.MultiheadAttention at every step, :1302-1307)
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& L = D->layers[li];
+    LinearArgs a;
+    a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld;
+    a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
+    a.M = B * M; a.N = 2 * d; a.K = d;
+    SCV_TRY(launch_linear(a, 0, s));
+  }
+  D->pinned[0] = D->pinned[1] = 0;
+  bool used[2] = {false, false};
+  const bool sync_each = (A->flags & SCV_FLAG_SYNC_EVERY_STEP) != 0;
+  for (int step = 0; step < steps_max; ++step) {
+    SCV_TRY(decode_step(D, A, steps_max, step, s));
+    if (sync_each) {
+      SCV_CUDA(cudaStreamSynchronize(s));
+    }
+    if ((step & 7) == 7 && step + 1 < steps_max) {
+      // bound the host's run-ahead to <= 16 steps and stop enqueueing once every row has finished
+      const int k = (step >> 3) & 1;
+      if (used[k]) {
+        SCV_CUDA(cudaEventSynchronize(D->ev[k]));
+        if (D->pinned[k] != 0) break;
+      }
+      SCV_CUDA(cudaMemcpyAsync(&D->pinned[k], &st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+      SCV_CUDA(cudaEventRecord(D->ev[k], s));
+      used[k] = true;
+    }
+  }
+  SCV_CUDA(cudaMemcpyAsync(&D->pinned[2], st, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+  SCV_CUDA(cudaStreamSynchronize(s));
+  const StepState* hs = reinterpret_cast<const StepState*>(&D->pinned[2]);
+  *A->out_steps = hs->done ? hs->out_len : hs->step;
+  D->last_B = B;
+  return 0;
+}
+
+int scv_decoder_debug_read(scv_decoder* D, int32_t what, float* dst, int64_t numel, void* stream) {
+  SCV_REQUIRE(D && dst && D->last_B > 0, "debug_read: nothing has been decoded yet");
+  const int B = D->last_B;
+  const float* src = nullptr;
+  int64_t n = 0;
+  switch (what) {
+    case 0: src = D->x.as<float>(); n = (int64_t)B * D->cfg.d_model; break;
+    case 1: src = D->logits.as<float>(); n = (int64_t)B * D->cfg.vocab_size; break;
+    case 2: src = D->tlog.as<float>(); n = (int64_t)B * 8; break;
+    case 3: src = D->slog.as<float>(); n = B; break;
+    default: SCV_REQUIRE(false, "debug_read: unknown tap %d", what);
+  }
+  SCV_REQUIRE(numel == n, "debug_read: tap %d holds %lld floats, caller asked for %lld", what, (long long)n,
+              (long long)numel);
+  return launch_copy_f32(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Spherical interpolation of latent rows for latent-space candidate generation.
+// Reference: scripts/holdout/holdout_search.py:128-146 (identical copy in
+// notebooks/generative_evaluation.ipynb cell 12).  One CTA per output row.
+#include "../../include/scvae_b200.h"
+#include "common.cuh"
+
+using namespace scv;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RowStats { float n1, n2, dot; };
+
+__device__ RowStats row_stats(const float* a, const float* b, int dim, float* red) {
+  float s1 = 0.f, s2 = 0.f, d = 0.f;
+  for (int i = threadIdx.x; i < dim; i += kThreads) {
+    const float x = a[i], y = b[i];
+    s1 = fmaf(x, x, s1); s2 = fmaf(y, y, s2); d = fmaf(x, y, d);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2); d = warp_sum(d);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { red[w * 3 + 0] = s1; red[w * 3 + 1] = s2; red[w * 3 + 2] = d; }
+  __syncthreads();
+  float t1 = 0.f, t2 = 0.f, td = 0.f;
+  for (int i = 0; i < kThreads / 32; ++i) { t1 += red[i * 3]; t2 += red[i * 3 + 1]; td += red[i * 3 + 2]; }
+  RowStats r;
+  r.n1 = sqrtf(t1); r.n2 = sqrtf(t2);
+  // dot of the F.normalize()d rows: x / max(||x||, 1e-12)
+  r.dot = td / (fmaxf(r.n1, 1e-12f) * fmaxf(r.n2, 1e-12f));
+  return r;
+}
+
+__device__ float omega_of(float dot) { return fmaxf(acosf(fminf(fmaxf(dot, -1.0f), 1.0f)), 1e-6f); }
+
+__global__ void __launch_bounds__(kThreads)
+slerp_flag_kernel(const float* anchors, int dim, const int* i1, const int* i2, long long n, int* flag) {
+  __shared__ float red[kThreads / 32 * 3];
+  const long long r = blockIdx.x;
+  if (r >= n) return;
+  const RowStats st = row_stats(anchors + (size_t)i1[r] * dim, anchors + (size_t)i2[r] * dim, dim, red);
+  if (threadIdx.x == 0 && fabsf(sinf(omega_of(st.dot))) < 1e-6f) atomicOr(flag, 1);   // (:137)
+}
+
+__global__ void __launch_bounds__(kThreads)
+slerp_rows_kernel(const float* anchors, int dim, const int* i1, const int* i2, const float* t, long long n,
+                  float* out, const int* flag) {
+  __shared__ float red[kThreads / 32 * 3];
+  const long long r = blockIdx.x;
+  if (r >= n) return;
+  const float* a = anchors + (size_t)i1[r] * dim;
+  const float* b = anchors + (size_t)i2[r] * dim;
+  float* o = out + (size_t)r * dim;
+  const float tt = t[r];
+  if (*flag != 0) {                                   // batch-global lerp fallback (:137-138)
+    for (int i = threadIdx.x; i < dim; i += kThreads) o[i] = (1.0f - tt) * a[i] + tt * b[i];
+    return;
+  }
+  const RowStats st = row_stats(a, b, dim, red);
+  const float om = omega_of(st.dot), so = sinf(om);
+  const float s1 = sinf((1.0f - tt) * om) / so, s2 = sinf(tt * om) / so;
+  const float mag = (1.0f - tt) * st.n1 + tt * st.n2;
+  const float inv1 = 1.0f / fmaxf(st.n1, 1e-12f), inv2 = 1.0f / fmaxf(st.n2, 1e-12f);
+  for (int i = threadIdx.x; i < dim; i += kThreads) o[i] = (s1 * (a[i] * inv1) + s2 * (b[i] * inv2)) * mag;
+}
+
+}  // namespace
+
+extern "C" int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const int32_t* i2, const float* t,
+                              int64_t n_rows, float* out, int32_t* fallback_flag_dev, void* stream) {
+  SCV_REQUIRE(anchors && i1 && i2 && t && out && fallback_flag_dev && dim > 0 && n_rows > 0, "slerp: bad arguments");
+  SCV_REQUIRE(n_rows < (1ll << 31), "slerp: too many rows for one call");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SCV_CUDA(cudaMemsetAsync(fallback_flag_dev, 0, sizeof(int), s));
+  slerp_flag_kernel<<<(unsigned)n_rows, kThreads, 0, s>>>(anchors, dim, i1, i2, n_rows, fallback_flag_dev);
+  SCV_LAUNCH_CHECK();
+  slerp_rows_kernel<<<(unsigned)n_rows, kThreads, 0, s>>>(anchors, dim, i1, i2, t, n_rows, out, fallback_flag_dev);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}

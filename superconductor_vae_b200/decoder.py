@@ -1,0 +1,352 @@
+"""Drop-in `EnhancedTransformerDecoder` whose KV-cache generation runs on the B200 engine.
+
+Mirrors the reference's public surface for the decode path
+(src/superconductor/models/autoregressive_decoder.py):
+
+  * constructor arguments and state_dict key names / shapes            :564-765
+  * precompute_memory(z, encoder_skip, stoich_pred, heads_pred)         :875-899
+  * generate_with_kv_cache(...)  same parameter order and defaults      :1321-1338
+  * sample_for_reinforce(...)                                           :1559-1572
+
+The module holds ordinary fp32 ``nn.Parameter``s under the reference's names (so
+``load_state_dict`` of a reference checkpoint works and an optimiser can keep updating them); before
+each engine call, parameters whose version changed are re-uploaded and rounded to bf16 once.
+The teacher-forced training ``forward`` is outside this engine's scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+PAD_IDX, START_IDX, END_IDX = 0, 1, 2
+N_TOKEN_TYPES = 5
+HEADS_ORDER = ("tc_pred", "sc_pred", "hp_pred", "tc_class_logits", "competence", "element_count_pred")
+
+
+class _PositionalEncoding(nn.Module):
+    """Holds the sinusoidal ``pe`` buffer [1, max_len, d_model] (reference :392-413)."""
+
+    def __init__(self, d_model: int, max_len: int, dropout: float):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, d_model)
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+
+class EnhancedTransformerDecoder(nn.Module):
+    def __init__(self, latent_dim: int = 2048, d_model: int = 512, nhead: int = 8, num_layers: int = 12,
+                 dim_feedforward: int = 2048, dropout: float = 0.1, max_len: int = 80, n_memory_tokens: int = 16,
+                 encoder_skip_dim: int = 256, use_skip_connection: bool = True, use_stoich_conditioning: bool = True,
+                 max_elements: int = 12, n_stoich_tokens: int = 4, use_gradient_checkpointing: bool = False,
+                 use_position_dependent_tf: bool = False, tf_position_decay: float = 0.5,
+                 vocab_size: Optional[int] = None, stoich_input_dim: Optional[int] = None,
+                 memory_bottleneck_dim: int = 1024):
+        super().__init__()
+        self.latent_dim, self.d_model, self.nhead, self.num_layers = latent_dim, d_model, nhead, num_layers
+        self.dim_feedforward = dim_feedforward
+        self.max_len = max_len
+        self.vocab_size = vocab_size if vocab_size is not None else 148      # legacy VOCAB_SIZE (:107)
+        self.n_memory_tokens = n_memory_tokens
+        self.use_skip_connection = use_skip_connection
+        self.use_stoich_conditioning = use_stoich_conditioning
+        self.max_elements = max_elements
+        self.memory_bottleneck_dim = memory_bottleneck_dim
+        self.encoder_skip_dim = encoder_skip_dim
+
+        self.token_embedding = nn.Embedding(self.vocab_size, d_model, padding_idx=PAD_IDX)
+        self.pos_encoding = _PositionalEncoding(d_model, max_len, dropout)
+        n_lat = d_model * n_memory_tokens
+        if memory_bottleneck_dim > 0:
+            self.latent_to_memory = nn.Sequential(nn.Linear(latent_dim, memory_bottleneck_dim),
+                                                  nn.LayerNorm(memory_bottleneck_dim), nn.GELU(),
+                                                  nn.Linear(memory_bottleneck_dim, n_lat))
+        else:
+            self.latent_to_memory = nn.Sequential(nn.Linear(latent_dim, n_lat // 2), nn.GELU(),
+                                                  nn.Linear(n_lat // 2, n_lat))
+        if use_skip_connection:
+            self.skip_n_tokens = 8
+            n_skip = d_model * self.skip_n_tokens
+            self.skip_to_memory = nn.Sequential(nn.Linear(encoder_skip_dim, n_skip // 2), nn.GELU(),
+                                                nn.Linear(n_skip // 2, n_skip))
+        else:
+            self.skip_n_tokens = 0
+        if use_stoich_conditioning:
+            self.stoich_n_tokens = n_stoich_tokens
+            if stoich_input_dim is None:
+                stoich_input_dim = max_elements * 3 + 1
+            self.stoich_input_dim = stoich_input_dim
+            self.stoich_to_memory = nn.Sequential(nn.Linear(stoich_input_dim, d_model), nn.LayerNorm(d_model),
+                                                  nn.GELU(), nn.Linear(d_model, d_model * n_stoich_tokens))
+        else:
+            self.stoich_n_tokens = 0
+            self.stoich_input_dim = 0
+        layer = nn.TransformerDecoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward,
+                                           dropout=dropout, activation="gelu", batch_first=True, norm_first=True)
+        self.transformer_decoder = nn.TransformerDecoder(layer, num_layers=num_layers)
+        self.output_proj = nn.Sequential(nn.LayerNorm(d_model), nn.Linear(d_model, d_model), nn.GELU(),
+                                         nn.Dropout(dropout), nn.Linear(d_model, self.vocab_size))
+        self.stop_head = nn.Sequential(nn.Linear(d_model, d_model // 4), nn.GELU(), nn.Linear(d_model // 4, 1))
+        self.site_dup_head = nn.Sequential(nn.Linear(d_model, d_model // 4), nn.GELU(), nn.Linear(d_model // 4, 1))
+        self.token_type_head = nn.Sequential(nn.LayerNorm(d_model), nn.Linear(d_model, d_model), nn.GELU(),
+                                             nn.Dropout(dropout), nn.Linear(d_model, d_model // 4), nn.GELU(),
+                                             nn.Dropout(dropout), nn.Linear(d_model // 4, N_TOKEN_TYPES))
+        self.heads_input_dim = 24
+        self.heads_n_tokens = 4
+        self.heads_to_memory = nn.Sequential(nn.Linear(self.heads_input_dim, d_model // 2),
+                                             nn.LayerNorm(d_model // 2), nn.GELU(), nn.Linear(d_model // 2, d_model),
+                                             nn.GELU(), nn.Linear(d_model, d_model * self.heads_n_tokens))
+        for p in self.parameters():          # same init rule as the reference (:769-772)
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._engine = None
+        self._engine_versions: Dict[str, Tuple[int, int]] = {}
+        self.max_rows_per_call = 8192        # rows decoded per engine call; larger batches are chunked
+        self.h2_uniform_fallback = True      # reproduce the reference's batch-global degenerate guard
+        self.last_steps: Optional[int] = None
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], nhead: int = 8, device="cuda", **overrides):
+        """Infer every shape from the checkpoint the way the reference's loaders do
+        (scripts/holdout/holdout_search.py:223-252) and load it."""
+        sd = {k.replace("_orig_mod.", ""): v for k, v in sd.items()}      # torch.compile prefixes (:4042-4058)
+        d = sd["token_embedding.weight"].shape[1]
+        layers = 0
+        while f"transformer_decoder.layers.{layers}.self_attn.in_proj_weight" in sd:
+            layers += 1
+        if "latent_to_memory.3.weight" in sd:
+            bottleneck = sd["latent_to_memory.0.weight"].shape[0]
+            n_lat = sd["latent_to_memory.3.weight"].shape[0] // d
+        else:
+            bottleneck = 0
+            n_lat = sd["latent_to_memory.2.weight"].shape[0] // d
+        kw = dict(latent_dim=sd["latent_to_memory.0.weight"].shape[1], d_model=d, nhead=nhead, num_layers=layers,
+                  dim_feedforward=sd["transformer_decoder.layers.0.linear1.weight"].shape[0],
+                  max_len=sd["pos_encoding.pe"].shape[1], n_memory_tokens=n_lat,
+                  use_skip_connection="skip_to_memory.0.weight" in sd,
+                  vocab_size=sd["token_embedding.weight"].shape[0],
+                  use_stoich_conditioning="stoich_to_memory.0.weight" in sd,
+                  memory_bottleneck_dim=bottleneck)
+        if "skip_to_memory.0.weight" in sd:
+            kw["encoder_skip_dim"] = sd["skip_to_memory.0.weight"].shape[1]
+        if "stoich_to_memory.0.weight" in sd:
+            kw["stoich_input_dim"] = sd["stoich_to_memory.0.weight"].shape[1]
+            kw["n_stoich_tokens"] = sd["stoich_to_memory.3.weight"].shape[0] // d
+        kw.update(overrides)
+        m = cls(**kw)
+        k_heads = sd["heads_to_memory.0.weight"].shape[1] if "heads_to_memory.0.weight" in sd else m.heads_input_dim
+        if k_heads != m.heads_input_dim:      # V14.3 checkpoints predate the 14 family dims (SURVEY 8 "Configurations")
+            m.heads_input_dim = k_heads
+            m.heads_to_memory[0] = nn.Linear(k_heads, d // 2)
+        m.load_state_dict(sd, strict=False)
+        return m.to(device).eval()
+
+    @classmethod
+    def from_reference(cls, module: nn.Module, device="cuda"):
+        """Build from an instance of the reference class (same state_dict layout)."""
+        return cls.from_state_dict(module.state_dict(), nhead=module.nhead, device=device)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("teacher-forced training forward is outside the B200 decode engine "
+                                  "(SURVEY.md section 8f row 3); use the reference module for training")
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _config(self) -> _lib.DecoderConfig:
+        return _lib.DecoderConfig(
+            d_model=self.d_model, nhead=self.nhead, num_layers=self.num_layers, dim_feedforward=self.dim_feedforward,
+            vocab_size=self.vocab_size, pe_len=self.pos_encoding.pe.shape[1], latent_dim=self.latent_dim,
+            n_memory_tokens=self.n_memory_tokens, memory_bottleneck_dim=self.memory_bottleneck_dim,
+            stoich_input_dim=self.stoich_input_dim, n_stoich_tokens=self.stoich_n_tokens,
+            heads_input_dim=self.heads_input_dim, heads_n_tokens=self.heads_n_tokens,
+            encoder_skip_dim=self.encoder_skip_dim if self.use_skip_connection else 0,
+            skip_n_tokens=self.skip_n_tokens)
+
+    def _sync_engine(self):
+        """Create the engine on first use and upload every tensor whose storage or version changed."""
+        L = _lib.lib()
+        dev = self.token_embedding.weight.device
+        _lib.require_cuda(self.token_embedding.weight, "EnhancedTransformerDecoder parameters")
+        if self._engine is None:
+            h = C.c_void_p()
+            cfg = self._config()
+            with torch.cuda.device(dev):
+                _lib.check(L.scv_decoder_create(C.byref(cfg), C.byref(h)), "scv_decoder_create")
+            self._engine = h
+            self._engine_device = dev
+            self._engine_versions = {}
+        elif self._engine_device != dev:
+            raise _lib.EngineError("module was moved to another device after its engine was created")
+        stream = _lib.current_stream()
+        for name, t in self.state_dict(keep_vars=True).items():
+            key = (t.data_ptr(), t._version)
+            if self._engine_versions.get(name) == key:
+                continue
+            src = t.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            _lib.check(L.scv_decoder_load_weight(self._engine, name.encode(), _lib.ptr(src), src.numel(), stream),
+                       f"load_weight({name})")
+            self._engine_versions[name] = key      # (a temporary `src` is safe to drop: same-stream reuse is ordered)
+        return L
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                _lib.lib().scv_decoder_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        _lib.require_cuda(t, name)
+        return t.detach().to(torch.float32).contiguous()
+
+    def _heads_matrix(self, heads_pred: Dict[str, torch.Tensor], batch: int, device) -> torch.Tensor:
+        """[B, 24] in the order tc, sc, hp, tc_class(5), competence, count, family(14) (:845-858)."""
+        fam = heads_pred.get("family_composed_14")
+        for name in HEADS_ORDER + (("family_composed_14",) if fam is not None else ()):
+            t = heads_pred[name]
+            if t.size(0) != batch:
+                raise RuntimeError(f"heads_pred['{name}'] batch {t.size(0)} != z batch {batch}. "
+                                   f"Shapes: {name}={tuple(t.shape)}, z=[{batch}, ...]")
+        parts = [heads_pred["tc_pred"].unsqueeze(-1), heads_pred["sc_pred"].unsqueeze(-1),
+                 heads_pred["hp_pred"].unsqueeze(-1), heads_pred["tc_class_logits"],
+                 heads_pred["competence"].unsqueeze(-1), heads_pred["element_count_pred"].unsqueeze(-1)]
+        if self.heads_input_dim > 10:
+            parts.append(fam if fam is not None else torch.zeros(batch, self.heads_input_dim - 10, device=device))
+        return torch.cat([p.to(device=device, dtype=torch.float32) for p in parts], dim=-1).contiguous()
+
+    # ------------------------------------------------------------------ reference API
+    def _create_memory(self, z, encoder_skip=None, stoich_pred=None, heads_pred=None) -> torch.Tensor:
+        with torch.no_grad():
+            L = self._sync_engine()
+            z = self._f32(z, "z")
+            B = z.size(0)
+            skip = self._f32(encoder_skip, "encoder_skip") if (self.use_skip_connection and encoder_skip is not None) else None
+            stoich = self._f32(stoich_pred, "stoich_pred") if (self.use_stoich_conditioning and stoich_pred is not None) else None
+            heads = self._heads_matrix(heads_pred, B, z.device) if heads_pred is not None else None
+            M = self.n_memory_tokens + (self.skip_n_tokens if skip is not None else 0) + \
+                (self.stoich_n_tokens if stoich is not None else 0) + (self.heads_n_tokens if heads is not None else 0)
+            memory = torch.empty((B, M, self.d_model), dtype=torch.float32, device=z.device)
+            m_out = C.c_int32(0)
+            with torch.cuda.device(z.device):
+                _lib.check(L.scv_decoder_build_memory(self._engine, B, _lib.ptr(z), _lib.ptr(skip), _lib.ptr(stoich),
+                                                      _lib.ptr(heads), _lib.ptr(memory), C.byref(m_out),
+                                                      _lib.current_stream()), "build_memory")
+            assert m_out.value == M
+            return memory
+
+    def precompute_memory(self, z, encoder_skip=None, stoich_pred=None, heads_pred=None) -> torch.Tensor:
+        return self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
+
+    def generate_with_kv_cache(self, z, encoder_skip=None, stoich_pred=None, temperature: float = 1.0,
+                               top_k: Optional[int] = None, top_p: Optional[float] = None,
+                               max_len: Optional[int] = None, return_log_probs: bool = False,
+                               return_entropy: bool = False, cached_memory: Optional[torch.Tensor] = None,
+                               stop_boost: float = 0.0, hard_stop_threshold: float = 0.0,
+                               heads_pred: Optional[Dict[str, torch.Tensor]] = None,
+                               type_masks: Optional[torch.Tensor] = None, site_dup_threshold: float = 0.0,
+                               *, _forced_tokens: Optional[torch.Tensor] = None, _seed: Optional[int] = None
+                               ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+        self.eval()                                                         # side effect kept (:1368)
+        if site_dup_threshold and site_dup_threshold > 0:
+            raise NotImplementedError("site_dup gating (reference :1426-1435, SURVEY H5) is not built yet")
+        max_len = max_len or self.max_len
+        pe_max = self.pos_encoding.pe.shape[1]
+        if max_len > pe_max:
+            max_len = pe_max                                                # silent clamp (:1372-1375)
+        with torch.no_grad():
+            L = self._sync_engine()
+            memory = self._f32(cached_memory, "cached_memory") if cached_memory is not None else \
+                self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
+            device = memory.device
+            B, M = memory.size(0), memory.size(1)
+            steps_max = max_len - 1
+            if steps_max < 1:
+                raise RuntimeError("max_len leaves no decoding step (the reference fails in torch.cat here)")
+            masks_u8 = None
+            if type_masks is not None:
+                masks_u8 = type_masks.to(device=device).to(torch.uint8).contiguous()
+                if tuple(masks_u8.shape) != (N_TOKEN_TYPES, self.vocab_size):
+                    raise RuntimeError(f"type_masks must be [{N_TOKEN_TYPES}, {self.vocab_size}], got {tuple(masks_u8.shape)}")
+            tokens = torch.zeros((B, steps_max), dtype=torch.int64, device=device)
+            lps = torch.zeros((B, steps_max), dtype=torch.float32, device=device) if return_log_probs else None
+            ents = torch.zeros((B, steps_max), dtype=torch.float32, device=device) if return_entropy else None
+            forced = None
+            if _forced_tokens is not None:
+                forced = torch.zeros((B, steps_max), dtype=torch.int64, device=device)
+                n = min(steps_max, _forced_tokens.size(1))
+                forced[:, :n] = _forced_tokens[:, :n].to(device)
+            if _seed is None:
+                _seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if not (temperature < 0.01) else 0
+            flags = _lib.FLAG_H2_UNIFORM_FALLBACK if self.h2_uniform_fallback else 0
+            steps_done = 0
+            chunk = max(1, int(self.max_rows_per_call))
+            with torch.cuda.device(device):
+                stream = _lib.current_stream()
+                for lo in range(0, B, chunk):
+                    hi = min(B, lo + chunk)
+                    out_steps = C.c_int32(0)
+                    args = _lib.GenerateArgs(
+                        batch=hi - lo, n_memory=M, max_len=max_len, memory=memory[lo:hi].data_ptr(),
+                        temperature=float(temperature), top_k=int(top_k) if top_k else 0,
+                        top_p=float(top_p) if top_p is not None else 1.0, stop_boost=float(stop_boost),
+                        hard_stop_threshold=float(hard_stop_threshold), site_dup_threshold=0.0,
+                        type_masks=masks_u8.data_ptr() if masks_u8 is not None else None,
+                        want_log_probs=int(return_log_probs), want_entropy=int(return_entropy), flags=flags,
+                        seed=_seed, offset=lo,
+                        out_tokens=tokens[lo:hi].data_ptr(),
+                        out_log_probs=lps[lo:hi].data_ptr() if lps is not None else None,
+                        out_entropy=ents[lo:hi].data_ptr() if ents is not None else None,
+                        out_steps=C.pointer(out_steps),
+                        forced_tokens=forced[lo:hi].data_ptr() if forced is not None else None)
+                    _lib.check(L.scv_decoder_generate(self._engine, C.byref(args), stream), "generate")
+                    steps_done = max(steps_done, out_steps.value)
+                    self._last_B = hi - lo
+            self.last_steps = steps_done
+            gen = tokens[:, :steps_done].contiguous()
+            return (gen, lps[:, :steps_done].contiguous() if lps is not None else None,
+                    ents[:, :steps_done].contiguous() if ents is not None else None)
+
+    def sample_for_reinforce(self, z, encoder_skip=None, stoich_pred=None, temperature: float = 0.8,
+                             max_len: Optional[int] = None, cached_memory: Optional[torch.Tensor] = None,
+                             stop_boost: float = 0.0, hard_stop_threshold: float = 0.0, heads_pred=None,
+                             type_masks=None, site_dup_threshold: float = 0.0, **kw
+                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        tokens, lp, ent = self.generate_with_kv_cache(
+            z=z, encoder_skip=encoder_skip, stoich_pred=stoich_pred, temperature=temperature, max_len=max_len,
+            return_log_probs=True, return_entropy=True, cached_memory=cached_memory, stop_boost=stop_boost,
+            hard_stop_threshold=hard_stop_threshold, heads_pred=heads_pred, type_masks=type_masks,
+            site_dup_threshold=site_dup_threshold, **kw)
+        B, Lq = tokens.shape                                               # mask: 1 up to and incl. first END (:1620-1639)
+        is_end = tokens == END_IDX
+        end_pos = torch.argmax(is_end.int(), dim=1)
+        end_pos = torch.where(is_end.any(dim=1), end_pos, torch.full_like(end_pos, Lq))
+        mask = (torch.arange(Lq, device=tokens.device).unsqueeze(0) <= end_pos.unsqueeze(1)).float()
+        return tokens, lp, ent, mask
+
+    def debug_tap(self, what: int) -> torch.Tensor:
+        """Engine-internal fp32 state of the last executed step of the last engine call (tests only):
+        0 hidden [B,d], 1 raw logits [B,V], 2 type logits [B,5], 3 stop logit [B]."""
+        L = _lib.lib()
+        B = self._last_B
+        cols = {0: self.d_model, 1: self.vocab_size, 2: 8, 3: 1}[what]
+        out = torch.empty((B, cols), dtype=torch.float32, device=self._engine_device)
+        with torch.cuda.device(self._engine_device):
+            _lib.check(L.scv_decoder_debug_read(self._engine, what, _lib.ptr(out), out.numel(), _lib.current_stream()),
+                       "debug_read")
+        torch.cuda.synchronize(self._engine_device)
+        return out[:, :5] if what == 2 else (out[:, 0] if what == 3 else out)

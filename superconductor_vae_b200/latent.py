@@ -1,0 +1,62 @@
+"""Latent-space candidate generation: SLERP walks between anchor latents, decoded on the engine.
+
+Reference call convention: scripts/holdout/holdout_search.py:128-146 (slerp), :392-436 (decode_z_batch),
+and the V14.3-complete variant in notebooks/generative_evaluation.ipynb cells 12/14/16
+(stoich_pred = fraction_head(z), heads_pred = _build_heads_pred(z), type masks, stop head).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+@torch.no_grad()
+def slerp(z1: torch.Tensor, z2: torch.Tensor, t) -> torch.Tensor:
+    """Same arithmetic as the reference's slerp for [N, D] rows (t: float or [N, 1])."""
+    _lib.require_cuda(z1, "z1")
+    n, d = z1.shape
+    anchors = torch.cat([z1, z2.expand_as(z1)], dim=0).to(torch.float32).contiguous()
+    i1 = torch.arange(n, dtype=torch.int32, device=z1.device)
+    i2 = i1 + n
+    tt = torch.as_tensor(t, dtype=torch.float32, device=z1.device).reshape(-1).expand(n).contiguous()
+    return slerp_rows(anchors, i1, i2, tt)
+
+
+@torch.no_grad()
+def slerp_rows(anchors: torch.Tensor, i1: torch.Tensor, i2: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """out[r] = slerp(anchors[i1[r]], anchors[i2[r]], t[r]) without materialising the gathered rows."""
+    L = _lib.lib()
+    _lib.require_cuda(anchors, "anchors")
+    dev = anchors.device
+    anchors = anchors.to(torch.float32).contiguous()
+    i1 = i1.to(device=dev, dtype=torch.int32).contiguous()
+    i2 = i2.to(device=dev, dtype=torch.int32).contiguous()
+    t = t.to(device=dev, dtype=torch.float32).contiguous()
+    n = i1.numel()
+    out = torch.empty((n, anchors.shape[1]), dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.scv_slerp_rows(_lib.ptr(anchors), anchors.shape[1], _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(t), n,
+                                    _lib.ptr(out), _lib.ptr(flag), _lib.current_stream()), "slerp_rows")
+    return out
+
+
+@torch.no_grad()
+def decode_z_batch(encoder, decoder, z: torch.Tensor, temperature: float = 0.001, type_masks=None,
+                   stop_boost: float = 10.0, hard_stop_threshold: float = 0.8, use_heads: bool = True,
+                   max_len: Optional[int] = None, return_log_probs: bool = False):
+    """z [N, latent] -> tokens [N, L] (+ log-probs): conditioning from z alone, then KV-cache decode.
+
+    ``use_heads=True`` is the notebook's 24-memory-token pipeline; ``False`` the scripts' 20-token one
+    (no heads, no masks, no stop head: pass type_masks=None, stop_boost=0)."""
+    if use_heads:
+        stoich, heads = encoder.conditioning(z)
+    else:
+        stoich, heads = encoder.heads_from_latent(z)["stoich_pred"], None
+    toks, lps, _ = decoder.generate_with_kv_cache(
+        z=z, stoich_pred=stoich, temperature=temperature, max_len=max_len, heads_pred=heads, type_masks=type_masks,
+        stop_boost=stop_boost, hard_stop_threshold=hard_stop_threshold, return_log_probs=return_log_probs)
+    return (toks, lps) if return_log_probs else toks

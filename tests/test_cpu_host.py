@@ -1,0 +1,169 @@
+"""CPU-only checks of the host side: C-ABI exports, state_dict layout, tokenizer ids, sharding logic
+(gloo, world_size 2), and that the product path fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import superconductor_vae_b200 as S
+from superconductor_vae_b200 import _lib, parallel
+from oracle import vocab as OV
+from oracle import weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "scvae_b200.h")).read()
+    declared = set(re.findall(r"\b(scv_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/scvae_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.scv_abi_version() == 1
+
+
+@pytest.mark.parametrize("shape", [W.C512, W.C512B, W.C576, W.TINY, W.TINY_SKIP])
+def test_decoder_state_dict_layout_matches_reference_names(shape):
+    sd = W.make_decoder_state_dict(shape)          # keys verified against the reference with strict=True
+    m = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shape.nhead, device="cpu")
+    mine = m.state_dict()
+    assert set(mine) == set(sd)
+    for k in sd:
+        assert mine[k].shape == sd[k].shape, k
+        assert torch.equal(mine[k], sd[k]), k
+
+
+def test_encoder_state_dict_layout_matches_reference_names():
+    sd = W.make_encoder_state_dict()
+    m = S.FullMaterialsVAE.from_state_dict(sd, device="cpu")
+    mine = m.state_dict()
+    assert set(mine) == set(sd)
+    for k in sd:
+        assert torch.equal(mine[k], sd[k]), k
+
+
+def test_compiled_checkpoint_prefix_is_stripped():
+    sd = W.make_decoder_state_dict(W.TINY)
+    sd2 = {k.replace("transformer_decoder.", "transformer_decoder._orig_mod."): v for k, v in sd.items()}
+    m = S.EnhancedTransformerDecoder.from_state_dict(sd2, nhead=W.TINY.nhead, device="cpu")
+    assert torch.equal(m.state_dict()["transformer_decoder.layers.1.linear2.weight"],
+                       sd["transformer_decoder.layers.1.linear2.weight"])
+
+
+def test_no_cpu_fallback():
+    sd = W.make_decoder_state_dict(W.TINY)
+    m = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=W.TINY.nhead, device="cpu")
+    with pytest.raises(S.EngineError):
+        m.generate_with_kv_cache(W.make_latents(2, W.TINY.latent_dim), temperature=0.001)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 64), torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_positional_signature_order():
+    import inspect
+    names = list(inspect.signature(S.EnhancedTransformerDecoder.generate_with_kv_cache).parameters)[1:16]
+    assert names == ["z", "encoder_skip", "stoich_pred", "temperature", "top_k", "top_p", "max_len",
+                     "return_log_probs", "return_entropy", "cached_memory", "stop_boost", "hard_stop_threshold",
+                     "heads_pred", "type_masks", "site_dup_threshold"]
+    names = list(inspect.signature(S.EnhancedTransformerDecoder.sample_for_reinforce).parameters)[1:12]
+    assert names == ["z", "encoder_skip", "stoich_pred", "temperature", "max_len", "cached_memory", "stop_boost",
+                     "hard_stop_threshold", "heads_pred", "type_masks", "site_dup_threshold"]
+
+
+# ----------------------------------------------------------------------------- tokenizer
+def _tok(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tokenizer.pt"), weights_only=False)
+    # id layout only depends on the list lengths; synthesise names where the golden did not record them
+    fr = [f"{i + 1}/{100003}" for i in range(g["n_fractions"])]
+    fr[0], fr[-1] = "1/2", "99873/100000"
+    iso = [f"{300 + i}Og" for i in range(g["n_isotopes"])]
+    iso[0], iso[-1] = "1H", "238U"
+    return g, S.FractionAwareTokenizer(max_len=64, fractions=fr, isotopes=iso)
+
+
+def test_tokenizer_layout_and_masks(golden_dir):
+    g, tok = _tok(golden_dir)
+    assert tok.vocab_size == g["vocab_size"] == 4752
+    m = tok.get_type_masks()
+    assert m.dtype == torch.bool and tuple(m.shape) == (5, 4752)
+    assert m.sum(dim=1).tolist() == g["mask_row_sums"].tolist()
+    assert torch.equal(m, OV.type_masks(g["n_fractions"], g["n_isotopes"]))
+    for i, name in g["names"].items():
+        if i in (143, 4459, 4461, 4751) or i < 143 or i == 4460:
+            assert tok.get_token_name(i) == name, (i, tok.get_token_name(i), name)
+    assert tok.encode("YBa2Cu3O7")[:12] == g["encoded_YBCO"][:12]
+    assert [tok.decode(ids) for ids in g["ids"]] == g["decoded"]
+    assert tok.decode_batch(torch.tensor(g["ids"][0]).unsqueeze(0)) == [g["decoded"][0]]
+    assert tok.compute_token_type_targets(torch.tensor([2, 5, 123, 143, 4460, 0])).tolist() == [4, 0, 1, 2, 3, 3]
+
+
+def test_tokenizer_fraction_canonicalisation():
+    tok = S.FractionAwareTokenizer(max_len=16, fractions=["1/2", "3/10"], isotopes=["18O"])
+    ids = tok.encode("La(2/4)Sr(3/10){18}O{17}O(7/9)", pad=False)
+    assert ids == [1, tok._token_to_id["La"], 143, tok._token_to_id["Sr"], 144, tok.isotope_token_start,
+                   tok.iso_unk_idx, 4, 2]
+    assert tok.decode(ids) == "La(1/2)Sr(3/10){18}O{?}?(?/?)"
+
+
+# ----------------------------------------------------------------------------- sharding + gather (gloo)
+def test_shard_bounds_cover_rows():
+    for n in (1, 7, 64, 1000003):
+        for ws in (1, 2, 3, 8):
+            b = [parallel.shard_bounds(n, ws, r) for r in range(ws)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_rloo_order_roundtrip():
+    B, k, ws = 10, 4, 3
+    full = torch.arange(B * k).unsqueeze(1)           # row id in repeat layout (i*B + b)
+    gathered = torch.cat([full[parallel.rloo_shard_rows(B, k, ws, r)] for r in range(ws)])
+    assert torch.equal(parallel.restore_rloo_order(gathered, B, k, ws), full)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, ws, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=ws)
+    n = 11
+    lo, hi = parallel.shard_bounds(n, ws, rank)
+    L = 3 + 2 * rank                                   # ragged L per shard (each stops on its own rows)
+    local = (torch.arange(lo, hi).unsqueeze(1) * 100 + torch.arange(L).unsqueeze(0)).to(torch.int32)
+    out = parallel.gather_rows(local, n, pad_value=0)
+    lp = parallel.gather_rows(local.float() * 0.5, n, pad_value=0.0)
+    if rank == 0:
+        q.put((out, lp))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world_size_2():
+    ws, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out, lp = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert tuple(out.shape) == (11, 5)
+    lo1, _ = parallel.shard_bounds(11, 2, 1)
+    assert out[:lo1, :3].tolist() == [[r * 100 + c for c in range(3)] for r in range(lo1)]
+    assert (out[:lo1, 3:] == 0).all()                  # shorter shard padded to the global L
+    assert out[lo1:].tolist() == [[r * 100 + c for c in range(5)] for r in range(lo1, 11)]
+    assert torch.equal(lp, out.float() * 0.5)

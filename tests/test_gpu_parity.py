@@ -1,0 +1,375 @@
+"""Parity of the CUDA engine (through the Python shim -> C ABI) against the CPU oracle and the golden
+vectors recorded from the reference modules.  Run on the B200 box: pytest -m gpu.
+
+Bars (BASELINE.json north_star): greedy token sequences bit-exact; logits / log-probs / entropy within the
+fp32 tolerances written next to each assert; sampling matches the reference distribution statistically.
+"""
+import math
+import os
+
+import pytest
+import torch
+
+import superconductor_vae_b200 as S
+from superconductor_vae_b200 import _lib
+from oracle import decoder_oracle as DO
+from oracle import encoder_oracle as EO
+from oracle import latent as OL
+from oracle import vocab as OV
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+SHAPES = {"tiny": (W.TINY, OV.TINY_LAYOUT), "c512_b32": (W.C512, {}), "c512b_b4": (W.C512B, {}),
+          "c576_b4": (W.C576, {})}
+_cache = {}
+
+
+def _golden(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _setup(golden_dir, name):
+    if name in _cache:
+        return _cache[name]
+    shape, layout = SHAPES[name]
+    g = _golden(golden_dir, name)
+    B, seed = g["meta"]["B"], g["meta"]["seed_in"]
+    sd = W.make_decoder_state_dict(shape, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shape.nhead, device=DEV)
+    z = W.make_latents(B, shape.latent_dim, seed)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, seed)
+    masks = OV.type_masks(**layout)
+    _cache[name] = (shape, g, sd, dec, z, stoich, heads, masks)
+    return _cache[name]
+
+
+def _cuda(x):
+    if x is None:
+        return None
+    if isinstance(x, dict):
+        return {k: v.to(DEV) for k, v in x.items()}
+    return x.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("M,N,K", [(1, 5, 1), (5, 13, 13), (33, 97, 24), (130, 512, 145), (32, 1536, 512),
+                                   (300, 256, 513), (64, 512, 2214), (257, 4752, 512), (1024, 2048, 512),
+                                   (49, 512, 2048)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_op_linear_matches_fp32(M, N, K, act):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn((M, K), generator=g)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(torch.bfloat16).float()
+    b = torch.randn((N,), generator=g)
+    r = torch.randn((M, N), generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    ref = (ref + r.double()).float()
+    L = _lib.lib()
+    ldw = (K + 7) // 8 * 8
+    xd, wd, bd, rd = x.to(DEV), w.to(DEV).contiguous(), b.to(DEV), r.to(DEV)
+    wp = torch.zeros((N, ldw), dtype=torch.bfloat16, device=DEV)
+    _lib.check(L.scv_op_pack_bf16(_lib.ptr(wd), _lib.ptr(wp), N, K, ldw, _lib.current_stream()))
+    y = torch.empty((M, N), device=DEV)
+    _lib.check(L.scv_op_linear(_lib.ptr(xd), K, _lib.ptr(wp), ldw, _lib.ptr(bd), _lib.ptr(rd), N, _lib.ptr(y), N,
+                               M, N, K, act, 1, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(wp[:, :K].float().cpu(), w)
+    torch.testing.assert_close(y.cpu(), ref, rtol=2e-5, atol=2e-5)
+
+
+def test_op_layernorm_matches_fp32():
+    g = torch.Generator().manual_seed(3)
+    for M, N in ((1, 64), (37, 512), (130, 576), (9, 1024)):
+        x = torch.randn((M, N), generator=g) * 3 + 1
+        ga, be = torch.randn((N,), generator=g), torch.randn((N,), generator=g)
+        ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (N,), ga, be, 1e-5))
+        xd, y = x.to(DEV), torch.empty((M, N), device=DEV)
+        _lib.check(_lib.lib().scv_op_layernorm(_lib.ptr(xd), N, _lib.ptr(ga.to(DEV)), _lib.ptr(be.to(DEV)),
+                                               _lib.ptr(y), N, M, N, 1, _lib.current_stream()))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ memory builder
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4", "c576_b4", "c512_b32"])
+def test_memory_matches_oracle(golden_dir, name):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    mem = dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(heads)).cpu()
+    ref = DO.build_memory(sd, z, None, stoich, heads)
+    assert tuple(mem.shape) == tuple(ref.shape) and mem.shape[1] == int(g["memory_shapes"][0])
+    torch.testing.assert_close(mem, ref, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(mem[:2], g["memory24_rows"], rtol=1e-4, atol=2e-5)
+    assert dec.precompute_memory(_cuda(z), None, _cuda(stoich), None).shape[1] == int(g["memory_shapes"][1])
+    assert dec.precompute_memory(_cuda(z), None, None, None).shape[1] == int(g["memory_shapes"][2])
+
+
+def test_memory_with_skip_connection(golden_dir):
+    g = _golden(golden_dir, "tiny_skip")
+    shape = W.TINY_SKIP
+    sd = W.make_decoder_state_dict(shape, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shape.nhead, device=DEV)
+    B = g["meta"]["B"]
+    z = W.make_latents(B, shape.latent_dim, 99)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, 99)
+    mem = dec.precompute_memory(_cuda(z), _cuda(g["skip"]), _cuda(stoich), _cuda(heads))
+    torch.testing.assert_close(mem.cpu(), g["memory"], rtol=1e-4, atol=2e-5)
+    t, _, _ = dec.generate_with_kv_cache(_cuda(z), encoder_skip=_cuda(g["skip"]), stoich_pred=_cuda(stoich),
+                                         temperature=0.001, heads_pred=_cuda(heads))
+    assert torch.equal(t.cpu().to(torch.int16), g["tokens"])
+
+
+def test_heads_batch_mismatch_raises(golden_dir):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    bad = {k: v[:3] for k, v in heads.items()}
+    with pytest.raises(RuntimeError):
+        dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(bad))
+
+
+# ------------------------------------------------------------------------------------------ greedy, bit exact
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4", "c576_b4", "c512_b32"])
+def test_greedy_tokens_bit_exact_vs_reference_goldens(golden_dir, name):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    zc, sc, hc, mc = _cuda(z), _cuda(stoich), _cuda(heads), _cuda(masks)
+    # (a) type masks + stop head + hard stop (BASELINE config 1/2 settings)
+    t, lp, en = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len,
+                                           heads_pred=hc, type_masks=mc, stop_boost=10.0, hard_stop_threshold=0.8,
+                                           return_log_probs=True, return_entropy=True)
+    assert t.dtype == torch.int64 and t.is_cuda
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_masked_tokens"]), "masked greedy tokens differ"
+    assert float(lp.abs().max()) == 0.0                         # greedy log-probs are zeros (:1508-1509)
+    # H2: any -inf in the batch -> entropy is ln V for every row
+    torch.testing.assert_close(en[0].cpu(), g["greedy_masked_entropy_row0"], rtol=1e-5, atol=1e-5)
+    # (b) plain greedy: all max_len-1 steps
+    t, _, en = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len,
+                                          heads_pred=hc, return_entropy=True)
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_plain_tokens"]), "plain greedy tokens differ"
+    n = g["greedy_plain_entropy"].shape[0]
+    torch.testing.assert_close(en[:n].cpu(), g["greedy_plain_entropy"], rtol=2e-4, atol=2e-4)
+    # (c) stop boost only, (d) 20 memory tokens, default max_len
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len,
+                                         heads_pred=hc, stop_boost=10.0)
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_stopboost_tokens"])
+    t, _, _ = dec.generate_with_kv_cache(z=zc, stoich_pred=sc, temperature=0.001)
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_m20_tokens"])
+    # (e) H1: temperature 0.0 reproduces the reference's divide-by-zero behaviour
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.0, max_len=shape.max_len, heads_pred=hc,
+                                         type_masks=mc, stop_boost=10.0, hard_stop_threshold=0.8)
+    assert torch.equal(t.cpu().to(torch.int16), g["t0_masked_tokens"])
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.0, max_len=min(shape.max_len, 8),
+                                         heads_pred=hc)
+    assert torch.equal(t.cpu().to(torch.int16), g["t0_plain_tokens"])
+    assert dec.training is False
+
+
+@pytest.mark.parametrize("name", ["tiny", "c512_b32"])
+def test_last_step_logits_within_tolerance(golden_dir, name):
+    """Raw logits / hidden state of the final executed step vs the fp32 oracle: |diff| <= 2e-4 abs."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    steps = min(shape.max_len, 9)
+    trace = {}
+    ref_t, _, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.001, max_len=steps,
+                                            heads_pred=heads, type_masks=masks, stop_boost=10.0, trace=trace,
+                                            stop_when_all_finished=False)
+    t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), temperature=0.001, max_len=steps,
+                                         heads_pred=_cuda(heads), type_masks=_cuda(masks), stop_boost=10.0)
+    L = t.shape[1]
+    assert torch.equal(t.cpu(), ref_t[:, :L])
+    torch.testing.assert_close(dec.debug_tap(0).cpu(), trace["hidden"][L - 1], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(dec.debug_tap(1).cpu(), trace["raw_logits"][L - 1], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(dec.debug_tap(2).cpu(), trace["type_logits"][L - 1], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(dec.debug_tap(3).cpu(), trace["stop_logit"][L - 1], rtol=1e-4, atol=2e-4)
+
+
+def test_max_len_is_clamped_to_pe_buffer(golden_dir):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), temperature=0.001, max_len=500,
+                                         heads_pred=_cuda(heads))
+    assert t.shape[1] == shape.max_len - 1
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_plain_tokens"])
+
+
+def test_cached_memory_and_chunking_are_equivalent(golden_dir):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    mem = dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(heads))
+    t1, _, _ = dec.generate_with_kv_cache(None, temperature=0.001, cached_memory=mem, max_len=shape.max_len)
+    assert torch.equal(t1.cpu().to(torch.int16), g["greedy_plain_tokens"])
+    old = dec.max_rows_per_call
+    try:
+        dec.max_rows_per_call = 4          # 6 rows -> chunks of 4 + 2
+        t2, _, _ = dec.generate_with_kv_cache(None, temperature=0.001, cached_memory=mem, max_len=shape.max_len)
+    finally:
+        dec.max_rows_per_call = old
+    assert torch.equal(t1, t2)
+
+
+# ------------------------------------------------------------------------------------------ sampling
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4"])
+def test_sampled_logprobs_and_entropy_match_oracle_replay(golden_dir, name):
+    """The engine samples with Philox, so tokens differ from torch.multinomial; replaying the engine's own
+    tokens through the oracle must reproduce log-prob and entropy (tolerance 1e-3 abs)."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    t, lp, en, mk = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), temperature=1.2,
+                                             max_len=shape.max_len, stop_boost=10.0, heads_pred=_cuda(heads), _seed=11)
+    t, lp, en, mk = t.cpu(), lp.cpu(), en.cpu(), mk.cpu()
+    rt, rlp, ren = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=1.2,
+                                             max_len=shape.max_len, stop_boost=10.0, heads_pred=heads,
+                                             return_log_probs=True, return_entropy=True, forced_tokens=t)
+    assert rt.shape == t.shape
+    torch.testing.assert_close(lp, rlp, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(en, ren, rtol=1e-3, atol=1e-3)
+    assert torch.equal(mk, DO.reinforce_mask(t))
+    # same seed -> same sample; different seed -> different sample
+    t2, _, _, _ = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), temperature=1.2,
+                                           max_len=shape.max_len, stop_boost=10.0, heads_pred=_cuda(heads), _seed=11)
+    assert torch.equal(t2.cpu(), t)
+    t3, _, _, _ = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), temperature=1.2,
+                                           max_len=shape.max_len, stop_boost=10.0, heads_pred=_cuda(heads), _seed=12)
+    assert not torch.equal(t3.cpu()[:, :min(t3.shape[1], t.shape[1])], t[:, :min(t3.shape[1], t.shape[1])])
+
+
+def test_sampling_distribution_matches_reference_softmax(golden_dir):
+    """First-step token histogram over 200k draws of one latent vs softmax(logits/T) of the oracle:
+    chi-square over bins with expected count >= 20 must stay below the 99.9% quantile."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    n, T = 200_000, 1.2
+    trace = {}
+    DO.generate_with_kv_cache(sd, shape.nhead, z[:1], stoich_pred=stoich[:1], temperature=T, max_len=2,
+                              heads_pred={k: v[:1] for k, v in heads.items()}, trace=trace)
+    p = trace["probs"][0][0].double()
+    mem = dec.precompute_memory(_cuda(z[:1]), None, _cuda(stoich[:1]), _cuda({k: v[:1] for k, v in heads.items()}))
+    old = dec.max_rows_per_call
+    dec.max_rows_per_call = n
+    try:
+        t, lp, _ = dec.generate_with_kv_cache(None, temperature=T, max_len=2, cached_memory=mem.expand(n, -1, -1).contiguous(),
+                                              return_log_probs=True, _seed=2024)
+    finally:
+        dec.max_rows_per_call = old
+    counts = torch.bincount(t[:, 0].cpu(), minlength=shape.vocab_size).double()
+    exp = p * n
+    big = exp >= 20
+    chi2 = float((((counts - exp) ** 2) / exp)[big].sum() + ((counts[~big].sum() - exp[~big].sum()) ** 2) / max(float(exp[~big].sum()), 1e-9))
+    dof = int(big.sum())
+    # Wilson-Hilferty upper 99.9% quantile of chi-square(dof)
+    q = dof * (1 - 2 / (9 * dof) + 3.09 * math.sqrt(2 / (9 * dof))) ** 3
+    assert chi2 < q, (chi2, q, dof)
+    torch.testing.assert_close(lp[:, 0].cpu().double(), p[t[:, 0].cpu()].clamp(min=1e-8).log(), rtol=1e-3, atol=1e-3)
+
+
+def test_h2_uniform_fallback_with_masks(golden_dir):
+    """With hard masks the reference samples uniformly over the whole vocabulary."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    t, lp, en, mk = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), temperature=1.2,
+                                             max_len=shape.max_len, stop_boost=10.0, hard_stop_threshold=0.8,
+                                             heads_pred=_cuda(heads), type_masks=_cuda(masks), _seed=5)
+    lnv = math.log(shape.vocab_size)
+    torch.testing.assert_close(lp.cpu(), torch.full_like(lp.cpu(), -lnv), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(en.cpu(), torch.full_like(en.cpu(), lnv), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(g["sample_masked_logprobs"][:, :1], torch.full((t.shape[0], 1), -lnv), rtol=1e-5, atol=1e-5)
+    # "fixed" mode: masked softmax sampling; every sampled token respects the predicted type's mask
+    dec.h2_uniform_fallback = False
+    try:
+        t, lp, en, mk = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), temperature=1.2,
+                                                 max_len=shape.max_len, stop_boost=10.0, heads_pred=_cuda(heads),
+                                                 type_masks=_cuda(masks), _seed=5)
+    finally:
+        dec.h2_uniform_fallback = True
+    rt, rlp, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=1.2,
+                                           max_len=shape.max_len, stop_boost=10.0, heads_pred=heads, type_masks=masks,
+                                           return_log_probs=True, forced_tokens=t.cpu(), trace=(tr := {}))
+    for s in range(t.shape[1]):
+        fl = tr["final_logits"][s]
+        assert torch.isfinite(fl.gather(1, t.cpu()[:, s:s + 1])).all(), "sampled a masked token"
+        ref = torch.log_softmax(fl / 1.2, dim=-1).gather(1, t.cpu()[:, s:s + 1]).squeeze(1)
+        torch.testing.assert_close(lp.cpu()[:, s], ref, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------ encoder
+def test_encoder_matches_reference_golden(golden_dir):
+    g = _golden(golden_dir, "encoder_default")
+    sd = W.make_encoder_state_dict(W.ENC_DEFAULT, 1)
+    enc = S.FullMaterialsVAE.from_state_dict(sd, device=DEV)
+    idx, frac, mask, magpie, tc = W.make_compositions(g["meta"]["B"], g["meta"]["seed_in"])
+    out = enc(idx.to(DEV), frac.to(DEV), mask.to(DEV), magpie.to(DEV), tc.to(DEV))
+    fused = enc.encode(idx.to(DEV), frac.to(DEV), mask.to(DEV), magpie.to(DEV), tc.to(DEV))["fused_repr"]
+    for k, v in g.items():
+        if k == "meta":
+            continue
+        got = fused if k == "fused_repr" else out[k]
+        torch.testing.assert_close(got.cpu(), v, rtol=5e-4, atol=5e-5, msg=lambda m, k=k: f"{k}: {m}")
+    stoich, heads = enc.conditioning(out["z"])
+    ref = EO.forward(sd, idx, frac, mask, magpie, tc)
+    rs, rh = EO.conditioning(ref)
+    torch.testing.assert_close(stoich.cpu(), rs, rtol=5e-4, atol=5e-5)
+    hin = enc.heads_from_latent(out["z"])["heads_input"].cpu()
+    torch.testing.assert_close(hin, DO.heads_input_matrix(rh, rs.shape[0]), rtol=5e-4, atol=5e-5)
+
+
+def test_encoder_52k_rows_relative_l2(golden_dir):
+    """BASELINE config 5 at full size: rel-L2 <= 2e-3 on z and memory vs the fp32 oracle on a 512-row sample,
+    and full-size run is finite and deterministic."""
+    sd_e = W.make_encoder_state_dict(W.ENC_DEFAULT, 1)
+    sd_d = W.make_decoder_state_dict(W.C512, 0)
+    enc = S.FullMaterialsVAE.from_state_dict(sd_e, device=DEV)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd_d, nhead=8, device=DEV)
+    n = 52800
+    idx, frac, mask, magpie, tc = W.make_compositions(n, 7)
+    z = enc.encode(idx.to(DEV), frac.to(DEV), mask.to(DEV), magpie.to(DEV), tc.to(DEV))["z"]
+    stoich, heads = enc.conditioning(z)
+    mem = dec.precompute_memory(z, None, stoich, heads)
+    assert tuple(mem.shape) == (n, 24, 512) and bool(torch.isfinite(mem).all())
+    s = slice(0, 512)
+    ref = EO.forward(sd_e, idx[s], frac[s], mask[s], magpie[s], tc[s])
+    rs, rh = EO.conditioning(ref)
+    rmem = DO.build_memory(sd_d, ref["z"], None, rs, rh)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(z[s].cpu(), ref["z"]) <= 2e-3
+    assert rel(mem[s].cpu(), rmem) <= 2e-3
+    z2 = enc.encode(idx.to(DEV), frac.to(DEV), mask.to(DEV), magpie.to(DEV), tc.to(DEV))["z"]
+    assert torch.equal(z, z2)
+
+
+# ------------------------------------------------------------------------------------------ latent walks
+def test_slerp_matches_reference(golden_dir):
+    g = _golden(golden_dir, "slerp")
+    out = S.latent.slerp(g["z1"].to(DEV), g["z2"].to(DEV), g["t"].to(DEV))
+    torch.testing.assert_close(out.cpu(), g["slerp"], rtol=1e-5, atol=1e-5)
+    out = S.latent.slerp(g["z1"].to(DEV), (g["z1"] * 2.0).to(DEV), 0.25)     # near-parallel -> lerp fallback
+    torch.testing.assert_close(out.cpu(), g["slerp_parallel"], rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_config2_4096_latents_properties(golden_dir):
+    """BASELINE config 2 at full size (4096 latents, masks + stop head, greedy): bit-exact vs the oracle on the
+    first 48 rows (positions up to each row's first END), run-to-run determinism, and batch invariance
+    (rows decoded alone equal the same rows inside the 4096 batch)."""
+    shape = W.C512
+    sd = W.make_decoder_state_dict(shape, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    B = 4096
+    z = W.make_latents(B, shape.latent_dim, 1234)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, 1234)
+    masks = OV.type_masks()
+    kw = dict(temperature=0.001, max_len=64, type_masks=_cuda(masks), stop_boost=10.0, hard_stop_threshold=0.8)
+    t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+    t2, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+    assert torch.equal(t, t2)
+    n = 48
+    sub = {k: v[:n] for k, v in heads.items()}
+    ts, _, _ = dec.generate_with_kv_cache(_cuda(z[:n]), stoich_pred=_cuda(stoich[:n]), heads_pred=_cuda(sub), **kw)
+    rt, _, _ = DO.generate_with_kv_cache(sd, 8, z[:n], stoich_pred=stoich[:n], temperature=0.001, max_len=64,
+                                         heads_pred=sub, type_masks=masks, stop_boost=10.0, hard_stop_threshold=0.8)
+    assert torch.equal(ts.cpu(), rt)
+    lens = DO.first_end_lengths(rt)
+    tc = t.cpu()
+    for r in range(n):
+        k = int(lens[r])
+        assert torch.equal(tc[r, :k], rt[r, :k]), f"row {r} differs inside the 4096 batch"
+    assert tc.shape[1] >= rt.shape[1]
+    # every row that finished ends with END exactly once up to its length
+    fl = DO.first_end_lengths(tc)
+    assert int((tc == 2).any(dim=1).sum()) >= 1 and int(fl.max()) <= tc.shape[1]
