@@ -155,10 +155,14 @@ int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const i
 
 /* ---------------------------------------------------------------- kernel-level taps (tests) */
 /* y[M,N] = act(x[M,K] * w[N,K]^T + bias) (+ residual); w is bf16 with row stride ldw (elements).
- * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 0 auto, 1 SIMT fp32, 2 tcgen05 hi/lo bf16. */
+ * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 1 SIMT fp32 (w_bf16 row-major), 2 tcgen05 hi/lo bf16
+ * (w_bf16 in the tile layout of scv_op_pack_tiled; ldw ignored). */
 int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t ldw, const float* bias,
                   const float* residual, int32_t ldr, float* y, int32_t ldy, int32_t M, int32_t N, int32_t K,
                   int32_t act, int32_t impl, void* stream);
+/* impl 2 takes its weights in the tcgen05 tile layout: [ceil(N/128)][ceil(K/64)][128 x 64 bf16, 128-byte swizzle] */
+int64_t scv_op_tiled_elems(int32_t N, int32_t K);
+int scv_op_pack_tiled(const float* src, uint16_t* dst, int32_t N, int32_t K, void* stream);
 int scv_op_pack_bf16(const float* src, uint16_t* dst, int32_t rows, int32_t cols, int32_t ld_dst, void* stream);
 int scv_op_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, float* y, int32_t ldy,
                      int32_t M, int32_t N, int32_t act, void* stream);

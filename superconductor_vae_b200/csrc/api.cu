@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/scvae_b200.h"
@@ -81,10 +82,31 @@ float* WeightStore::add_vector(const std::string& name, int64_t numel) {
   return static_cast<float*>(p);
 }
 
-int WeightStore::add_linear(const std::string& prefix, int N, int K, Lin* out, bool bias) {
+__nv_bfloat16* WeightStore::add_tiled_view(const std::string& name, int row0, int rows) {
+  auto it = slots_.find(name);
+  if (it == slots_.end() || !it->second.is_matrix) {
+    set_error("add_tiled_view: %s is not a registered matrix", name.c_str());
+    return nullptr;
+  }
+  void* p = nullptr;
+  const size_t bytes = tc_packed_elems(rows, it->second.cols) * sizeof(__nv_bfloat16);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed for the tiled copy of %s", bytes, name.c_str());
+    return nullptr;
+  }
+  allocs_.push_back(p);
+  it->second.tiled.push_back({static_cast<__nv_bfloat16*>(p), row0, rows});
+  return static_cast<__nv_bfloat16*>(p);
+}
+
+int WeightStore::add_linear(const std::string& prefix, int N, int K, Lin* out, bool bias, bool tiled) {
   out->N = N; out->K = K;
   out->w = add_matrix(prefix + ".weight", N, K, &out->ldw);
   if (!out->w) return 2;
+  if (tiled) {
+    out->wt = add_tiled_view(prefix + ".weight", 0, N);
+    if (!out->wt) return 2;
+  }
   if (bias) {
     out->b = add_vector(prefix + ".bias", N);
     if (!out->b) return 2;
@@ -112,6 +134,8 @@ int WeightStore::load(const char* name, const float* src, int64_t numel, cudaStr
               (long long)sl.numel, (long long)numel);
   if (sl.is_matrix) {
     SCV_TRY(launch_pack_bf16(src, static_cast<__nv_bfloat16*>(sl.dst), sl.rows, sl.cols, sl.ld, s));
+    for (const TiledView& tv : sl.tiled)
+      SCV_TRY(launch_pack_tiled(src + (size_t)tv.row0 * sl.cols, tv.dst, tv.rows, sl.cols, s));
   } else {
     SCV_TRY(launch_copy_f32(src, static_cast<float*>(sl.dst), numel, s));
   }
@@ -131,8 +155,13 @@ int WeightStore::missing(std::string* first) const {
   return n;
 }
 
+// impl 0: tensor cores whenever the shape allows (M >= 64, K >= 64, 16-byte aligned rows), else CUDA cores.
+// SCV_LINEAR_IMPL=1 in the environment forces the CUDA-core path everywhere (A/B testing of the two paths).
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s) {
-  (void)impl;   // the tcgen05 path is selected here once it is wired in
+  static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
+  if (impl == 0) impl = forced;
+  if (impl == 2) return launch_linear_tcgen05(a, s);
+  if (impl == 0 && tc_shape_ok(a)) return launch_linear_tcgen05(a, s);
   return launch_linear_simt(a, s);
 }
 
@@ -178,9 +207,17 @@ int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t l
                   const float* residual, int32_t ldr, float* y, int32_t ldy, int32_t M, int32_t N, int32_t K,
                   int32_t act, int32_t impl, void* stream) {
   LinearArgs a;
-  a.x = x; a.ldx = ldx; a.w = reinterpret_cast<const __nv_bfloat16*>(w_bf16); a.ldw = ldw; a.bias = bias;
+  a.x = x; a.ldx = ldx; a.bias = bias;
+  if (impl == 2) a.wt = reinterpret_cast<const __nv_bfloat16*>(w_bf16);   // tiled layout (scv_op_pack_tiled)
+  else { a.w = reinterpret_cast<const __nv_bfloat16*>(w_bf16); a.ldw = ldw; }
   a.residual = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K; a.act = act;
   return launch_linear(a, impl, static_cast<cudaStream_t>(stream));
+}
+
+int64_t scv_op_tiled_elems(int32_t N, int32_t K) { return (int64_t)tc_packed_elems(N, K); }
+
+int scv_op_pack_tiled(const float* src, uint16_t* dst, int32_t N, int32_t K, void* stream) {
+  return launch_pack_tiled(src, reinterpret_cast<__nv_bfloat16*>(dst), N, K, static_cast<cudaStream_t>(stream));
 }
 
 int scv_op_pack_bf16(const float* src, uint16_t* dst, int32_t rows, int32_t cols, int32_t ld_dst, void* stream) {

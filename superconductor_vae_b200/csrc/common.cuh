@@ -119,6 +119,7 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 struct LinearArgs {
   const float* x = nullptr; int ldx = 0;
   const __nv_bfloat16* w = nullptr; int ldw = 0;   // [N, ldw] bf16, zero padded beyond K
+  const __nv_bfloat16* wt = nullptr;               // same weights, tiled + swizzled for tcgen05 (or null)
   const float* bias = nullptr;
   const float* residual = nullptr; int ldr = 0;    // may alias y
   float* y = nullptr; int ldy = 0;
@@ -127,6 +128,10 @@ struct LinearArgs {
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
 };
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
+int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
+bool tc_shape_ok(const LinearArgs& a);
+size_t tc_packed_elems(int N, int K);
+int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s);
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s);   // impl 0 auto, 1 simt, 2 tcgen05
 
 int launch_pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int ld_dst, cudaStream_t s);

@@ -16,6 +16,8 @@ namespace {
 struct DecLayer {
   LNp n1, n2, n3;
   __nv_bfloat16* sa_in_w = nullptr; float* sa_in_b = nullptr; int sa_in_ld = 0;   // [3d, d]
+  __nv_bfloat16* sa_in_wt = nullptr;                      // tcgen05 tiles of the whole [3d, d]
+  __nv_bfloat16* ca_q_wt = nullptr; __nv_bfloat16* ca_kv_wt = nullptr;   // tiles of rows [0,d) and [d,3d)
   Lin sa_out;
   __nv_bfloat16* ca_in_w = nullptr; float* ca_in_b = nullptr; int ca_in_ld = 0;   // [3d, d] rows q;k;v
   Lin ca_out;
@@ -76,12 +78,12 @@ static int dec_register(scv_decoder* D) {
   if (!D->emb || !D->pe) return 2;
   const int n_lat = d * c.n_memory_tokens;
   if (c.memory_bottleneck_dim > 0) {
-    SCV_TRY(W.add_linear("latent_to_memory.0", c.memory_bottleneck_dim, c.latent_dim, &D->l2m_a));
+    SCV_TRY(W.add_linear("latent_to_memory.0", c.memory_bottleneck_dim, c.latent_dim, &D->l2m_a, true, true));
     SCV_TRY(W.add_layernorm("latent_to_memory.1", c.memory_bottleneck_dim, &D->l2m_ln));
-    SCV_TRY(W.add_linear("latent_to_memory.3", n_lat, c.memory_bottleneck_dim, &D->l2m_b));
+    SCV_TRY(W.add_linear("latent_to_memory.3", n_lat, c.memory_bottleneck_dim, &D->l2m_b, true, true));
   } else {
-    SCV_TRY(W.add_linear("latent_to_memory.0", n_lat / 2, c.latent_dim, &D->l2m_a));
-    SCV_TRY(W.add_linear("latent_to_memory.2", n_lat, n_lat / 2, &D->l2m_b));
+    SCV_TRY(W.add_linear("latent_to_memory.0", n_lat / 2, c.latent_dim, &D->l2m_a, true, true));
+    SCV_TRY(W.add_linear("latent_to_memory.2", n_lat, n_lat / 2, &D->l2m_b, true, true));
   }
   if (c.skip_n_tokens > 0) {
     const int n_skip = d * c.skip_n_tokens;
@@ -108,26 +110,30 @@ static int dec_register(scv_decoder* D) {
     L.ca_in_w = W.add_matrix(p + "multihead_attn.in_proj_weight", 3 * d, d, &L.ca_in_ld);
     L.ca_in_b = W.add_vector(p + "multihead_attn.in_proj_bias", 3 * d);
     if (!L.sa_in_w || !L.sa_in_b || !L.ca_in_w || !L.ca_in_b) return 2;
-    SCV_TRY(W.add_linear(p + "self_attn.out_proj", d, d, &L.sa_out));
-    SCV_TRY(W.add_linear(p + "multihead_attn.out_proj", d, d, &L.ca_out));
-    SCV_TRY(W.add_linear(p + "linear1", c.dim_feedforward, d, &L.ff1));
-    SCV_TRY(W.add_linear(p + "linear2", d, c.dim_feedforward, &L.ff2));
+    L.sa_in_wt = W.add_tiled_view(p + "self_attn.in_proj_weight", 0, 3 * d);
+    L.ca_q_wt = W.add_tiled_view(p + "multihead_attn.in_proj_weight", 0, d);
+    L.ca_kv_wt = W.add_tiled_view(p + "multihead_attn.in_proj_weight", d, 2 * d);
+    if (!L.sa_in_wt || !L.ca_q_wt || !L.ca_kv_wt) return 2;
+    SCV_TRY(W.add_linear(p + "self_attn.out_proj", d, d, &L.sa_out, true, true));
+    SCV_TRY(W.add_linear(p + "multihead_attn.out_proj", d, d, &L.ca_out, true, true));
+    SCV_TRY(W.add_linear(p + "linear1", c.dim_feedforward, d, &L.ff1, true, true));
+    SCV_TRY(W.add_linear(p + "linear2", d, c.dim_feedforward, &L.ff2, true, true));
     SCV_TRY(W.add_layernorm(p + "norm1", d, &L.n1));
     SCV_TRY(W.add_layernorm(p + "norm2", d, &L.n2));
     SCV_TRY(W.add_layernorm(p + "norm3", d, &L.n3));
   }
   SCV_TRY(W.add_layernorm("output_proj.0", d, &D->out_ln));
-  SCV_TRY(W.add_linear("output_proj.1", d, d, &D->out_a));
-  SCV_TRY(W.add_linear("output_proj.4", c.vocab_size, d, &D->out_b));
-  SCV_TRY(W.add_linear("stop_head.0", d / 4, d, &D->stop_a));
+  SCV_TRY(W.add_linear("output_proj.1", d, d, &D->out_a, true, true));
+  SCV_TRY(W.add_linear("output_proj.4", c.vocab_size, d, &D->out_b, true, true));
+  SCV_TRY(W.add_linear("stop_head.0", d / 4, d, &D->stop_a, true, true));
   SCV_TRY(W.add_linear("stop_head.2", 1, d / 4, &D->stop_b));
   SCV_TRY(W.add_linear("site_dup_head.0", d / 4, d, &D->dup_a));
   SCV_TRY(W.add_linear("site_dup_head.2", 1, d / 4, &D->dup_b));
   for (const char* n : {"site_dup_head.0.weight", "site_dup_head.0.bias", "site_dup_head.2.weight", "site_dup_head.2.bias"})
     W.mark_optional(n);   // older checkpoints lack it; only used when site_dup_threshold > 0
   SCV_TRY(W.add_layernorm("token_type_head.0", d, &D->tt_ln));
-  SCV_TRY(W.add_linear("token_type_head.1", d, d, &D->tt_a));
-  SCV_TRY(W.add_linear("token_type_head.4", d / 4, d, &D->tt_b));
+  SCV_TRY(W.add_linear("token_type_head.1", d, d, &D->tt_a, true, true));
+  SCV_TRY(W.add_linear("token_type_head.4", d / 4, d, &D->tt_b, true, true));
   SCV_TRY(W.add_linear("token_type_head.7", 5, d / 4, &D->tt_c));
   return 0;
 }
@@ -135,7 +141,7 @@ static int dec_register(scv_decoder* D) {
 static LinearArgs lin_args(const float* x, int ldx, const Lin& L, float* y, int ldy, int M, int act,
                            const int* done = nullptr) {
   LinearArgs a;
-  a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.bias = L.b; a.y = y; a.ldy = ldy;
+  a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.wt = L.wt; a.bias = L.b; a.y = y; a.ldy = ldy;
   a.M = M; a.N = L.N; a.K = L.K; a.act = act; a.done_flag = done;
   return a;
 }
@@ -281,7 +287,7 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     // ---- self attention (:1244-1296)
     SCV_TRY(launch_layernorm(x, d, L.n1.g, L.n1.b, xn, d, B, d, ACT_NONE, done, s));
     LinearArgs a;
-    a.x = xn; a.ldx = d; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
+    a.x = xn; a.ldx = d; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.wt = L.sa_in_wt; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
     a.M = B; a.N = 3 * d; a.K = d; a.done_flag = done;
     SCV_TRY(launch_linear(a, 0, s));
     AttnArgs sa;
@@ -298,7 +304,7 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     // ---- cross attention to the memory tokens (:1299-1308)
     SCV_TRY(launch_layernorm(x, d, L.n2.g, L.n2.b, xn, d, B, d, ACT_NONE, done, s));
     LinearArgs q;
-    q.x = xn; q.ldx = d; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
+    q.x = xn; q.ldx = d; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.wt = L.ca_q_wt; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
     q.M = B; q.N = d; q.K = d; q.done_flag = done;
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
@@ -372,7 +378,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   for (int li = 0; li < c.num_layers; ++li) {
     const DecLayer& L = D->layers[li];
     LinearArgs a;
-    a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld;
+    a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld; a.wt = L.ca_kv_wt;
     a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
     a.M = B * M; a.N = 2 * d; a.K = d;
     SCV_TRY(launch_linear(a, 0, s));

@@ -1,0 +1,296 @@
+// y = act(x * W^T + bias) (+ residual) on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Exactness: the decode path must reproduce the fp32 reference's greedy decisions while streaming bf16
+// weights (precision-sensitivity table).  Plain bf16 activations flip ~1 % of the
+// decisions; splitting every fp32 activation into hi = bf16(x) and lo = bf16(x - hi) and issuing two MMAs per
+// weight tile keeps 16 mantissa bits of x, every product bf16 x bf16 is exact in fp32, and the probe in the
+// survey shows 100 % agreement.  So per 64-wide k-block this kernel issues 4 x {A_hi, A_lo} x W UMMAs of
+// shape 128 x 128 x 16 (kind::f16, bf16 inputs, fp32 accumulate in TMEM).
+//
+// Structure (one 128 x 128 output tile per CTA, 192 threads):
+//   warps 0-3  producers: wait empty[s]; thread 0 posts expect_tx and one cp.async.bulk (UBLKCP) that brings
+//              the pre-swizzled 16 KB weight tile; all 128 threads read the fp32 activation tile (coalesced
+//              float4), split it, and st.shared it in the 128-byte-swizzled K-major layout the UMMA
+//              descriptor expects; fence.proxy.async; arrive on full[s].
+//              Afterwards the same warps run the epilogue: tcgen05.ld 32 lanes x 32 columns, bias /
+//              activation / residual, fp32 stores.
+//   warp 4     allocates TMEM (128 columns), then its lane 0 waits full[s], issues the UMMAs and commits to
+//              empty[s]; a final commit signals the epilogue.
+// Weights are packed once at load time into [n_tile][k_block][128 rows x 64 bf16, SW128] so a tile is one
+// contiguous 16 KB bulk copy (no tensor map needed).
+#include "common.cuh"
+
+namespace scv {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = 128 * 128;                       // 128 rows x 64 bf16 = 16 KB
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;                 // A_hi, A_lo, W
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_PRODUCERS = 128;
+constexpr uint32_t TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle: 8-row atoms of 1024 B (SBO = 1024), LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);     // .x = a (low half), .y = b
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TcArgs {
+  const float* x; int ldx;
+  const __nv_bfloat16* wt;          // tiled + swizzled weights
+  int kblocks;                      // K padded / 64
+  const float* bias;
+  const float* residual; int ldr;
+  float* y; int ldy;
+  int M, N, K, act;
+  const int* done_flag;
+};
+
+__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(TcArgs a) {
+  if (a.done_flag != nullptr && *a.done_flag != 0) return;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SW128 tiles need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;            // full[STAGES], empty[STAGES], accum, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x, m0 = blockIdx.y * BM, n0 = n_tile * BN;
+  const int KB = a.kblocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * KB * (TILE_BYTES / 2);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(empty_bar(s), phase ^ 1u);
+      const uint32_t st_base = base + s * STAGE_BYTES;
+      if (tid == 0) {
+        mbar_expect_tx(full_bar(s), TILE_BYTES);
+        bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+      }
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * NUM_PRODUCERS + tid;
+        const int row = idx >> 4, c4 = idx & 15;
+        const int gm = m0 + row, gk = kb * BK + c4 * 4;
+        v[it] = (gm < a.M && gk < a.K) ? *reinterpret_cast<const float4*>(a.x + (size_t)gm * a.ldx + gk)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * NUM_PRODUCERS + tid;
+        const int row = idx >> 4, c4 = idx & 15;
+        const float4 f = v[it];
+        const float hx = __bfloat162float(__float2bfloat16_rn(f.x)), hy = __bfloat162float(__float2bfloat16_rn(f.y));
+        const float hz = __bfloat162float(__float2bfloat16_rn(f.z)), hw = __bfloat162float(__float2bfloat16_rn(f.w));
+        const uint32_t hi0 = pack_bf16x2(hx, hy), hi1 = pack_bf16x2(hz, hw);
+        const uint32_t lo0 = pack_bf16x2(f.x - hx, f.y - hy), lo1 = pack_bf16x2(f.z - hz, f.w - hw);
+        const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)c4 & 1u) * 8u;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + off), "r"(hi0), "r"(hi1) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + TILE_BYTES + off), "r"(lo0), "r"(lo1) : "memory");
+      }
+      fence_proxy_async();                // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(full_bar(s));
+    }
+    // ===================== epilogue =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int gm = m0 + warp * 32 + lane;
+    const bool row_ok = gm < a.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();                        // tcgen05.ld is .sync.aligned: the whole warp issues it together
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      const int gn0 = n0 + c0;
+      if (row_ok && gn0 < a.N) {
+        float* yrow = a.y + (size_t)gm * a.ldy + gn0;
+        const float* rrow = a.residual != nullptr ? a.residual + (size_t)gm * a.ldr + gn0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (gn0 + j < a.N) {             // N is a multiple of 4 on this path
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float t = __uint_as_float(r[j + q]);
+              if (a.bias != nullptr) t += a.bias[gn0 + j + q];
+              o[q] = apply_act(t, a.act);
+            }
+            if (rrow != nullptr) {
+              const float4 rv = *reinterpret_cast<const float4*>(rrow + j);
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+            }
+            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(full_bar(s), phase);
+        tc_fence_after();
+        const uint32_t st_base = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t bd = umma_desc_sw128(st_base + 2 * TILE_BYTES + kk * 32);
+          umma_bf16(tmem_base, umma_desc_sw128(st_base + kk * 32), bd, (kb | kk) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, umma_desc_sw128(st_base + TILE_BYTES + kk * 32), bd, 1u);
+        }
+        umma_commit(empty_bar(s));       // frees the stage once the MMAs that read it have finished
+      }
+      umma_commit(accum_bar);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// fp32 [N, K] row-major -> bf16 tiles [ceil(N/128)][ceil(K/64)][128 x 64, SW128], zero padded.
+__global__ void pack_tiled_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K,
+                                  int n_tiles, int kblocks) {
+  const int64_t total = (int64_t)n_tiles * kblocks * 8192;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = i >> 13;
+    const int within = (int)(i & 8191);
+    const int r = within >> 6, pos = within & 63;           // physical position inside the row
+    const int chunk_phys = pos >> 3, e = pos & 7;
+    const int chunk = chunk_phys ^ (r & 7);                 // logical 16-byte chunk stored at this position
+    const int nt = (int)(tile / kblocks), kb = (int)(tile % kblocks);
+    const int n = nt * 128 + r, k = kb * 64 + chunk * 8 + e;
+    dst[i] = __float2bfloat16_rn((n < N && k < K) ? src[(int64_t)n * K + k] : 0.f);
+  }
+}
+
+}  // namespace
+
+size_t tc_packed_elems(int N, int K) { return (size_t)ceil_div(N, 128) * ceil_div(K, 64) * 8192; }
+
+int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s) {
+  const int nt = ceil_div(N, 128), kb = ceil_div(K, 64);
+  const int64_t total = (int64_t)nt * kb * 8192;
+  pack_tiled_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, s>>>(src, dst, N, K, nt, kb);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+bool tc_shape_ok(const LinearArgs& a) {
+  return a.wt != nullptr && a.M >= 64 && a.K >= 64 && a.K % 4 == 0 && a.N % 4 == 0 && a.ldx % 4 == 0 && a.ldy % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0 &&
+         (a.residual == nullptr || (a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15u) == 0));
+}
+
+int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
+  SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  TcArgs t;
+  t.x = a.x; t.ldx = a.ldx; t.wt = a.wt; t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual;
+  t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
+  // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
+  ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
+                 2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
+  dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM));
+  gemm_tcgen05_kernel<<<grid, 192, SMEM_BYTES, s>>>(t);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace scv

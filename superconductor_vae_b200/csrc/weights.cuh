@@ -10,6 +10,7 @@ namespace scv {
 
 struct Lin {               // nn.Linear: weight [N, K] bf16 (row stride ldw, zero padded), bias [N] fp32
   __nv_bfloat16* w = nullptr;
+  __nv_bfloat16* wt = nullptr;   // tiled + swizzled copy for the tcgen05 GEMM (null when the shape never uses it)
   float* b = nullptr;
   int N = 0, K = 0, ldw = 0;
 };
@@ -24,8 +25,10 @@ class WeightStore {
   ~WeightStore();
   // registration (allocates device memory); returns nullptr and sets the error on failure
   __nv_bfloat16* add_matrix(const std::string& name, int rows, int cols, int* ld_out);
+  // extra tcgen05-tiled copy of rows [row0, row0 + rows) of an already registered matrix
+  __nv_bfloat16* add_tiled_view(const std::string& name, int row0, int rows);
   float* add_vector(const std::string& name, int64_t numel);
-  int add_linear(const std::string& prefix, int N, int K, Lin* out, bool bias = true);
+  int add_linear(const std::string& prefix, int N, int K, Lin* out, bool bias = true, bool tiled = false);
   int add_layernorm(const std::string& prefix, int N, LNp* out);
   // optional entries are accepted by load() but not required by missing()
   void mark_optional(const std::string& name);
@@ -33,12 +36,14 @@ class WeightStore {
   int missing(std::string* first) const;
 
  private:
+  struct TiledView { __nv_bfloat16* dst; int row0, rows; };
   struct Slot {
     void* dst = nullptr;
     bool is_matrix = false;
     int rows = 0, cols = 0, ld = 0;
     int64_t numel = 0;
     bool loaded = false, optional = false;
+    std::vector<TiledView> tiled;
   };
   std::unordered_map<std::string, Slot> slots_;
   std::vector<std::string> order_;

@@ -82,14 +82,38 @@ def test_op_linear_matches_fp32(M, N, K, act):
     torch.testing.assert_close(y.cpu(), ref, rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 512), (4096, 1536, 512), (4096, 512, 2048),
+                                   (200, 132, 72), (64, 4752, 512), (1000, 2048, 576)])
+@pytest.mark.parametrize("act,residual", [(0, True), (1, False)])
+def test_op_linear_tcgen05_matches_fp64(M, N, K, act, residual):
+    """Tensor-core path (bf16 weights, activations split into bf16 hi + lo, fp32 accumulate in TMEM):
+    |diff| <= 5e-5 abs against fp64 math on O(1) outputs, i.e. fp32-accumulation noise only."""
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    x = torch.randn((M, K), generator=g)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(torch.bfloat16).float()
+    b, r = torch.randn((N,), generator=g), torch.randn((M, N), generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref = torch.nn.functional.gelu(ref) if act == 1 else ref
+    ref = ref + r.double() if residual else ref
+    L = _lib.lib()
+    xd, wd, bd, rd = x.to(DEV), w.to(DEV).contiguous(), b.to(DEV), r.to(DEV)
+    wt = torch.zeros(int(L.scv_op_tiled_elems(N, K)), dtype=torch.bfloat16, device=DEV)
+    _lib.check(L.scv_op_pack_tiled(_lib.ptr(wd), _lib.ptr(wt), N, K, _lib.current_stream()))
+    y = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(L.scv_op_linear(_lib.ptr(xd), K, _lib.ptr(wt), 0, _lib.ptr(bd), _lib.ptr(rd) if residual else None, N,
+                               _lib.ptr(y), N, M, N, K, act, 2, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert float((y.cpu().double() - ref).abs().max()) <= 5e-5
+
+
 def test_op_layernorm_matches_fp32():
     g = torch.Generator().manual_seed(3)
     for M, N in ((1, 64), (37, 512), (130, 576), (9, 1024)):
         x = torch.randn((M, N), generator=g) * 3 + 1
         ga, be = torch.randn((N,), generator=g), torch.randn((N,), generator=g)
         ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (N,), ga, be, 1e-5))
-        xd, y = x.to(DEV), torch.empty((M, N), device=DEV)
-        _lib.check(_lib.lib().scv_op_layernorm(_lib.ptr(xd), N, _lib.ptr(ga.to(DEV)), _lib.ptr(be.to(DEV)),
+        xd, gd, bd, y = x.to(DEV), ga.to(DEV), be.to(DEV), torch.empty((M, N), device=DEV)
+        _lib.check(_lib.lib().scv_op_layernorm(_lib.ptr(xd), N, _lib.ptr(gd), _lib.ptr(bd),
                                                _lib.ptr(y), N, M, N, 1, _lib.current_stream()))
         torch.cuda.synchronize()
         torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
