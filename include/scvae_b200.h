@@ -163,6 +163,16 @@ int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t l
 /* impl 2 takes its weights in the tcgen05 tile layout: [ceil(N/128)][ceil(K/64)][128 x 64 bf16, 128-byte swizzle] */
 int64_t scv_op_tiled_elems(int32_t N, int32_t K);
 int scv_op_pack_tiled(const float* src, uint16_t* dst, int32_t N, int32_t K, void* stream);
+/* SplitTile activations (bf16 hi/lo, [m_tile][k_block][hi 16 KB | lo 16 KB], 128-byte swizzle): the form in which
+ * LayerNorm / attention / GEMM epilogues hand activations to the next tcgen05 projection. */
+int64_t scv_op_split_tile_bytes(int32_t M, int32_t K);
+/* LayerNorm (normalize = 1) or plain split (normalize = 0) of fp32 rows into a zero-initialised SplitTile buffer */
+int scv_op_split_rows(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_split, int32_t M,
+                      int32_t N, int32_t normalize, void* stream);
+/* tcgen05 projection with SplitTile input; output fp32 rows (y) or, when y_split != NULL, SplitTile */
+int scv_op_linear_split(const void* a_split, const uint16_t* w_tiled, const float* bias, const float* residual,
+                        int32_t ldr, float* y, int32_t ldy, void* y_split, int32_t M, int32_t N, int32_t K, int32_t act,
+                        void* stream);
 int scv_op_pack_bf16(const float* src, uint16_t* dst, int32_t rows, int32_t cols, int32_t ld_dst, void* stream);
 int scv_op_layernorm(const float* x, int32_t ldx, const float* gamma, const float* beta, float* y, int32_t ldy,
                      int32_t M, int32_t N, int32_t act, void* stream);

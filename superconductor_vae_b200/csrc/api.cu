@@ -159,6 +159,7 @@ int WeightStore::missing(std::string* first) const {
 // SCV_LINEAR_IMPL=1 in the environment forces the CUDA-core path everywhere (A/B testing of the two paths).
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s) {
   static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
+  if (a.a_split != nullptr || a.y_split != nullptr) return launch_linear_tcgen05(a, s);   // no fp32 copy exists
   if (impl == 0) impl = forced;
   if (impl == 2) return launch_linear_tcgen05(a, s);
   if (impl == 0 && tc_shape_ok(a)) return launch_linear_tcgen05(a, s);
@@ -212,6 +213,22 @@ int scv_op_linear(const float* x, int32_t ldx, const uint16_t* w_bf16, int32_t l
   else { a.w = reinterpret_cast<const __nv_bfloat16*>(w_bf16); a.ldw = ldw; }
   a.residual = residual; a.ldr = ldr; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K; a.act = act;
   return launch_linear(a, impl, static_cast<cudaStream_t>(stream));
+}
+
+int64_t scv_op_split_tile_bytes(int32_t M, int32_t K) { return (int64_t)split_tile_bytes(M, K); }
+
+int scv_op_split_rows(const float* x, int32_t ldx, const float* gamma, const float* beta, void* out_split, int32_t M,
+                      int32_t N, int32_t normalize, void* stream) {
+  return launch_layernorm_split(x, ldx, gamma, beta, out_split, M, N, normalize, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int scv_op_linear_split(const void* a_split, const uint16_t* w_tiled, const float* bias, const float* residual,
+                        int32_t ldr, float* y, int32_t ldy, void* y_split, int32_t M, int32_t N, int32_t K, int32_t act,
+                        void* stream) {
+  LinearArgs a;
+  a.a_split = a_split; a.wt = reinterpret_cast<const __nv_bfloat16*>(w_tiled); a.bias = bias; a.residual = residual;
+  a.ldr = ldr; a.y = y; a.ldy = ldy; a.y_split = y_split; a.M = M; a.N = N; a.K = K; a.act = act;
+  return launch_linear_tcgen05(a, static_cast<cudaStream_t>(stream));
 }
 
 int64_t scv_op_tiled_elems(int32_t N, int32_t K) { return (int64_t)tc_packed_elems(N, K); }

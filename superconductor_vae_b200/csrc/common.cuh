@@ -86,6 +86,16 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
 
+// Two fp32 values -> packed bf16 pairs hi = bf16(x) and lo = bf16(x - hi) (element 0 in the low half).
+// hi + lo carries 16 mantissa bits of x; both MMAs against exact-bf16 weights are exact products.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  const __nv_bfloat162 h = __halves2bfloat162(ha, hb);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ha), b - __bfloat162float(hb));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the multinomial sampler ----
 struct Philox {
   __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -118,11 +128,13 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 // ---------------- kernel launchers shared between translation units ----------------
 struct LinearArgs {
   const float* x = nullptr; int ldx = 0;
+  const void* a_split = nullptr;                   // activations already in SplitTile form (tcgen05 path only)
   const __nv_bfloat16* w = nullptr; int ldw = 0;   // [N, ldw] bf16, zero padded beyond K
   const __nv_bfloat16* wt = nullptr;               // same weights, tiled + swizzled for tcgen05 (or null)
   const float* bias = nullptr;
   const float* residual = nullptr; int ldr = 0;    // may alias y
   float* y = nullptr; int ldy = 0;
+  void* y_split = nullptr;                         // write the output in SplitTile form instead of fp32 rows
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
@@ -131,6 +143,10 @@ int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
 bool tc_shape_ok(const LinearArgs& a);
 size_t tc_packed_elems(int N, int K);
+size_t split_tile_bytes(int M, int K);             // bytes of a SplitTile buffer for an [M, K] activation
+// LayerNorm (or, with normalize = 0, a plain copy) of fp32 rows straight into SplitTile form
+int launch_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, void* out_split, int M,
+                           int N, int normalize, const int* done_flag, cudaStream_t s);
 int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s);
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s);   // impl 0 auto, 1 simt, 2 tcgen05
 

@@ -149,16 +149,40 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs a) {
       if (e < hd) acc[j] = fmaf(w, vp[e], acc[j]);
     }
   }
+  if (a.out_split == nullptr) {
 #pragma unroll
-  for (int j = 0; j < EPL; ++j) {
-    const int e = lane + 32 * j;
-    if (e < hd) a.out[(size_t)b * a.ldo + h * hd + e] = acc[j];
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + 32 * j;
+      if (e < hd) a.out[(size_t)b * a.ldo + h * hd + e] = acc[j];
+    }
+  } else {
+    // the only consumer is the tensor-core out-projection: emit bf16 hi/lo chunks in SplitTile form
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = lane + 32 * j;
+      if (e < hd) sc[e] = acc[j];
+    }
+    __syncwarp();
+    if (lane * 8 < hd) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) split_pair(sc[lane * 8 + 2 * p], sc[lane * 8 + 2 * p + 1], hi[p], lo[p]);
+      const int col = h * hd + lane * 8;           // head_dim is a multiple of 8 on this path
+      const int mt = b >> 7, ri = b & 127, kb = col >> 6, cj = (col & 63) >> 3;
+      uint8_t* dst = a.out_split + ((size_t)mt * a.kb_out + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
-int launch_attention(const AttnArgs& a, cudaStream_t s) {
-  SCV_REQUIRE(a.hd >= 1 && a.hd <= 128, "attention: head_dim %d not in 1..128", a.hd);
-  SCV_REQUIRE(a.max_n >= 1, "attention: max_n must be positive");
+int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
+  SCV_REQUIRE(a_in.hd >= 1 && a_in.hd <= 128, "attention: head_dim %d not in 1..128", a_in.hd);
+  SCV_REQUIRE(a_in.max_n >= 1, "attention: max_n must be positive");
+  SCV_REQUIRE(a_in.out_split == nullptr || a_in.hd % 8 == 0, "attention: SplitTile output needs head_dim %% 8 == 0");
+  AttnArgs a = a_in;
+  a.max_n = std::max(a_in.max_n, a_in.hd);     // the score buffer doubles as the staging row of the split output
   const int warps = 8;
   const int blocks = ceil_div(a.B * a.nhead, warps);
   const size_t smem = (size_t)warps * a.max_n * sizeof(float);

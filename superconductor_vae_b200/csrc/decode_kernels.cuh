@@ -37,6 +37,7 @@ struct AttnArgs {
   const int* page_table = nullptr; int pages_per_seq = 0; long long page_stride = 0;   // paged (self)
   long long seq_stride = 0; int row_stride = 0;          // contiguous (cross): b*seq_stride + p*row_stride
   float* out = nullptr; int ldo = 0;
+  unsigned char* out_split = nullptr; int kb_out = 0;     // SplitTile output (bf16 hi/lo) for the tcgen05 out-projection
   int B = 0, nhead = 0, hd = 0; float scale = 1.f;
   int fixed_len = -1;                                    // cross: memory tokens; self: -1 -> step + 1
   int max_n = 0;                                         // smem scores per warp

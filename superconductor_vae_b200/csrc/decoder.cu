@@ -56,13 +56,14 @@ struct scv_decoder {
   LNp tt_ln; Lin tt_a, tt_b, tt_c;
   // workspaces (engine-owned, grown on demand)
   DevBuf x, xn, qkv, attn, q2, ff, h1, h2, t3, logits, tlog, slog, ckv, kvpool, cur, fin, ptab, state, mtmp;
+  DevBuf xn_s, attn_s, ff_s, h2_s;   // SplitTile (bf16 hi/lo) activations feeding the tcgen05 projections
   int* pinned = nullptr;              // host-pinned: [0..1] done polls, [2..9] StepState copy
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int last_B = 0;
 
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
-                      &fin, &ptab, &state, &mtmp})
+                      &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s})
       b->release();
     if (pinned) cudaFreeHost(pinned);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -241,6 +242,14 @@ int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const fl
   return 0;
 }
 
+// The tensor-core step (activations handed from kernel to kernel as bf16 hi/lo SplitTiles) needs a batch that
+// fills UMMA tiles and feature dims that are whole 64-wide k-blocks; smaller shapes use the CUDA-core kernels.
+static bool use_tensor_cores(const scv_decoder_config& c, int B) {
+  static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
+  return forced != 1 && B >= 64 && c.d_model % 64 == 0 && c.dim_feedforward % 64 == 0 && (c.d_model / c.nhead) % 8 == 0 &&
+         c.vocab_size % 4 == 0 && c.d_model <= 1024;
+}
+
 static int ensure_workspace(scv_decoder* D, int B, int M) {
   const scv_decoder_config& c = D->cfg;
   const size_t d = c.d_model, f = sizeof(float);
@@ -263,6 +272,15 @@ static int ensure_workspace(scv_decoder* D, int B, int M) {
   SCV_TRY(D->fin.ensure((size_t)B));
   SCV_TRY(D->ptab.ensure((size_t)B * pps * sizeof(int)));
   SCV_TRY(D->state.ensure(sizeof(StepState)));
+  if (use_tensor_cores(c, B)) {
+    // zero-filled once: k-block padding columns (d/4 = 144 -> 192 for C576) must read as zeros forever
+    for (DevBuf* b : {&D->xn_s, &D->attn_s, &D->h2_s}) {
+      const size_t need = split_tile_bytes(B, c.d_model);
+      if (need > b->cap) { SCV_TRY(b->ensure(need)); SCV_CUDA(cudaMemset(b->p, 0, need)); }
+    }
+    const size_t need = split_tile_bytes(B, c.dim_feedforward);
+    if (need > D->ff_s.cap) { SCV_TRY(D->ff_s.ensure(need)); SCV_CUDA(cudaMemset(D->ff_s.p, 0, need)); }
+  }
   return 0;
 }
 
@@ -275,6 +293,15 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
   const float scale = (float)(1.0 / std::sqrt((double)hd));
   float* x = D->x.as<float>(); float* xn = D->xn.as<float>(); float* qkv = D->qkv.as<float>();
   float* attn = D->attn.as<float>(); float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>();
+  // Tensor-core step: every projection input is handed over as a bf16 hi/lo SplitTile written by its producer
+  // (LayerNorm, attention, previous GEMM epilogue); nullptr selects the fp32 CUDA-core path.
+  const bool tc = use_tensor_cores(c, B);
+  void* xn_s = tc ? D->xn_s.p : nullptr; void* attn_s = tc ? D->attn_s.p : nullptr;
+  void* ff_s = tc ? D->ff_s.p : nullptr; void* h2_s = tc ? D->h2_s.p : nullptr;
+  auto norm = [&](const LNp& P, float* fp32_out) -> int {
+    return tc ? launch_layernorm_split(x, d, P.g, P.b, xn_s, B, d, 1, done, s)
+              : launch_layernorm(x, d, P.g, P.b, fp32_out, d, B, d, ACT_NONE, done, s);
+  };
 
   EmbedArgs e;
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>(); e.x = x; e.B = B;
@@ -285,9 +312,9 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
   for (int li = 0; li < c.num_layers; ++li) {
     const DecLayer& L = D->layers[li];
     // ---- self attention (:1244-1296)
-    SCV_TRY(launch_layernorm(x, d, L.n1.g, L.n1.b, xn, d, B, d, ACT_NONE, done, s));
+    SCV_TRY(norm(L.n1, xn));
     LinearArgs a;
-    a.x = xn; a.ldx = d; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.wt = L.sa_in_wt; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
+    a.x = xn; a.ldx = d; a.a_split = xn_s; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.wt = L.sa_in_wt; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
     a.M = B; a.N = 3 * d; a.K = d; a.done_flag = done;
     SCV_TRY(launch_linear(a, 0, s));
     AttnArgs sa;
@@ -297,14 +324,15 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     sa.page_table = D->ptab.as<int>(); sa.pages_per_seq = pps; sa.page_stride = page_stride; sa.row_stride = d;
     sa.out = attn; sa.ldo = d; sa.B = B; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale; sa.fixed_len = -1;
     sa.max_n = std::max(c.pe_len, M); sa.st = st; sa.host_len_hint = host_step + 1;
+    sa.out_split = static_cast<unsigned char*>(attn_s); sa.kb_out = d / 64;
     SCV_TRY(launch_attention(sa, s));
     LinearArgs o = lin_args(attn, d, L.sa_out, x, d, B, ACT_NONE, done);
-    o.residual = x; o.ldr = d;
+    o.residual = x; o.ldr = d; o.a_split = attn_s;
     SCV_TRY(launch_linear(o, 0, s));
     // ---- cross attention to the memory tokens (:1299-1308)
-    SCV_TRY(launch_layernorm(x, d, L.n2.g, L.n2.b, xn, d, B, d, ACT_NONE, done, s));
+    SCV_TRY(norm(L.n2, xn));
     LinearArgs q;
-    q.x = xn; q.ldx = d; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.wt = L.ca_q_wt; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
+    q.x = xn; q.ldx = d; q.a_split = xn_s; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.wt = L.ca_q_wt; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
     q.M = B; q.N = d; q.K = d; q.done_flag = done;
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
@@ -312,26 +340,37 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     ca.q = q2; ca.ldq = d; ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d;
     ca.row_stride = 2 * d; ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
     ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
+    ca.out_split = static_cast<unsigned char*>(attn_s); ca.kb_out = d / 64;
     SCV_TRY(launch_attention(ca, s));
     LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
-    co.residual = x; co.ldr = d;
+    co.residual = x; co.ldr = d; co.a_split = attn_s;
     SCV_TRY(launch_linear(co, 0, s));
     // ---- feed forward (:1311-1313)
-    SCV_TRY(launch_layernorm(x, d, L.n3.g, L.n3.b, xn, d, B, d, ACT_NONE, done, s));
-    SCV_TRY(launch_linear(lin_args(xn, d, L.ff1, ff, c.dim_feedforward, B, ACT_GELU, done), 0, s));
+    SCV_TRY(norm(L.n3, xn));
+    LinearArgs f1 = lin_args(xn, d, L.ff1, ff, c.dim_feedforward, B, ACT_GELU, done);
+    f1.a_split = xn_s; f1.y_split = ff_s;
+    SCV_TRY(launch_linear(f1, 0, s));
     LinearArgs f2 = lin_args(ff, c.dim_feedforward, L.ff2, x, d, B, ACT_NONE, done);
-    f2.residual = x; f2.ldr = d;
+    f2.residual = x; f2.ldr = d; f2.a_split = ff_s;
     SCV_TRY(launch_linear(f2, 0, s));
   }
   // ---- heads (:1413, 1417, 1439)
   float* h1 = D->h1.as<float>(); float* h2 = D->h2.as<float>(); float* t3 = D->t3.as<float>();
-  SCV_TRY(launch_layernorm(x, d, D->out_ln.g, D->out_ln.b, h1, d, B, d, ACT_NONE, done, s));
-  SCV_TRY(launch_linear(lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done), 0, s));
-  SCV_TRY(launch_linear(lin_args(h2, d, D->out_b, D->logits.as<float>(), c.vocab_size, B, ACT_NONE, done), 0, s));
+  SCV_TRY(norm(D->out_ln, h1));
+  LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done);
+  oa.a_split = xn_s; oa.y_split = h2_s;
+  SCV_TRY(launch_linear(oa, 0, s));
+  LinearArgs ob = lin_args(h2, d, D->out_b, D->logits.as<float>(), c.vocab_size, B, ACT_NONE, done);
+  ob.a_split = h2_s;
+  SCV_TRY(launch_linear(ob, 0, s));
   if (A->type_masks != nullptr) {
-    SCV_TRY(launch_layernorm(x, d, D->tt_ln.g, D->tt_ln.b, h1, d, B, d, ACT_NONE, done, s));
-    SCV_TRY(launch_linear(lin_args(h1, d, D->tt_a, h2, d, B, ACT_GELU, done), 0, s));
-    SCV_TRY(launch_linear(lin_args(h2, d, D->tt_b, t3, d / 4, B, ACT_GELU, done), 0, s));
+    SCV_TRY(norm(D->tt_ln, h1));
+    LinearArgs ta = lin_args(h1, d, D->tt_a, h2, d, B, ACT_GELU, done);
+    ta.a_split = xn_s; ta.y_split = h2_s;
+    SCV_TRY(launch_linear(ta, 0, s));
+    LinearArgs tb = lin_args(h2, d, D->tt_b, t3, d / 4, B, ACT_GELU, done);
+    tb.a_split = h2_s;
+    SCV_TRY(launch_linear(tb, 0, s));
     SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, D->tlog.as<float>(), 8, B, ACT_NONE, done), 0, s));
   }
   if (A->stop_boost > 0.f) {

@@ -7,28 +7,28 @@
 // survey shows 100 % agreement.  So per 64-wide k-block this kernel issues 4 x {A_hi, A_lo} x W UMMAs of
 // shape 128 x 128 x 16 (kind::f16, bf16 inputs, fp32 accumulate in TMEM).
 //
-// Structure (one 128 x 128 output tile per CTA, 192 threads):
-//   warps 0-3  producers: wait empty[s]; thread 0 posts expect_tx and one cp.async.bulk (UBLKCP) that brings
-//              the pre-swizzled 16 KB weight tile; all 128 threads read the fp32 activation tile (coalesced
-//              float4), split it, and st.shared it in the 128-byte-swizzled K-major layout the UMMA
-//              descriptor expects; fence.proxy.async; arrive on full[s].
-//              Afterwards the same warps run the epilogue: tcgen05.ld 32 lanes x 32 columns, bias /
-//              activation / residual, fp32 stores.
-//   warp 4     allocates TMEM (128 columns), then its lane 0 waits full[s], issues the UMMAs and commits to
-//              empty[s]; a final commit signals the epilogue.
-// Weights are packed once at load time into [n_tile][k_block][128 rows x 64 bf16, SW128] so a tile is one
-// contiguous 16 KB bulk copy (no tensor map needed).
+// Operand formats
+//   W        packed once at load time: [n_tile][k_block][128 rows x 64 bf16, 128-byte swizzle] (16 KB tiles)
+//   A split  "SplitTile": [m_tile][k_block][hi 16 KB | lo 16 KB], same swizzle; written by the producing
+//            kernel (LayerNorm, attention, a previous GEMM's epilogue), so one 32 KB + one 16 KB bulk copy
+//            (cp.async.bulk -> UBLKCP) per k-block feeds the tensor core with no ALU work in this kernel;
+//   A fp32   row-major activations are split inside the kernel by eight producer warps (two groups that
+//            alternate k-blocks so one group's global-load latency overlaps the other's conversion work).
+// One 128 x 128 output tile per CTA, 2 CTAs per SM (2 stages x 48 KB each) so one CTA's epilogue overlaps the
+// other's main loop; 9 warps: 0-7 producers/epilogue (warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4)..),
+// warp 8 allocates TMEM and its lane 0 issues the UMMAs.
 #include "common.cuh"
 
 namespace scv {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2;
 constexpr int TILE_BYTES = 128 * 128;                       // 128 rows x 64 bf16 = 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;                 // A_hi, A_lo, W
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_PRODUCERS = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int GROUP_THREADS = 128;
+constexpr int NUM_THREADS = 288;
 constexpr uint32_t TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -92,23 +95,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);     // .x = a (low half), .y = b
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 struct TcArgs {
-  const float* x; int ldx;
+  const float* x; int ldx;          // fp32 activations (A_SPLIT = false)
+  const uint8_t* a_split;           // SplitTile activations (A_SPLIT = true)
   const __nv_bfloat16* wt;          // tiled + swizzled weights
-  int kblocks;                      // K padded / 64
+  int kblocks;                      // ceil(K / 64)
   const float* bias;
   const float* residual; int ldr;
-  float* y; int ldy;
+  float* y; int ldy;                // fp32 output (OUT_SPLIT = false)
+  uint8_t* y_split; int kb_out;     // SplitTile output with kb_out = ceil(N / 64) k-blocks per row tile
   int M, N, K, act;
   const int* done_flag;
 };
 
-__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(TcArgs a) {
+template <bool A_SPLIT, bool OUT_SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tcgen05_kernel(TcArgs a) {
   if (a.done_flag != nullptr && *a.done_flag != 0) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -119,18 +120,22 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(TcArgs a) {
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   const uint32_t accum_bar = bars + 8u * (2 * STAGES);
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tile = blockIdx.x, m0 = blockIdx.y * BM, n0 = n_tile * BN;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, m0 = m_tile * BM, n0 = n_tile * BN;
   const int KB = a.kblocks;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), NUM_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), A_SPLIT ? 1 : GROUP_THREADS);
+      mbar_init(empty_bar(s), 1);
+    }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -138,81 +143,127 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(TcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * KB * (TILE_BYTES / 2);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== producers =====================
-    const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * KB * (TILE_BYTES / 2);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
-      mbar_wait(empty_bar(s), phase ^ 1u);
-      const uint32_t st_base = base + s * STAGE_BYTES;
+    if constexpr (A_SPLIT) {
       if (tid == 0) {
-        mbar_expect_tx(full_bar(s), TILE_BYTES);
-        bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+        const uint8_t* atile0 = a.a_split + (size_t)m_tile * KB * (2 * TILE_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(empty_bar(s), phase ^ 1u);
+          const uint32_t st_base = base + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), 3 * TILE_BYTES);
+          bulk_copy_g2s(st_base, atile0 + (size_t)kb * (2 * TILE_BYTES), 2 * TILE_BYTES, full_bar(s));
+          bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+        }
       }
-      float4 v[16];
+    } else {
+      const int grp = warp >> 2, gtid = tid & (GROUP_THREADS - 1);
+      for (int kb = grp; kb < KB; kb += 2) {
+        const int s = kb % STAGES;                  // == grp: each group owns one stage
+        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar(s), phase ^ 1u);
+        const uint32_t st_base = base + s * STAGE_BYTES;
+        if (gtid == 0) {
+          mbar_expect_tx(full_bar(s), TILE_BYTES);
+          bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+        }
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * NUM_PRODUCERS + tid;
-        const int row = idx >> 4, c4 = idx & 15;
-        const int gm = m0 + row, gk = kb * BK + c4 * 4;
-        v[it] = (gm < a.M && gk < a.K) ? *reinterpret_cast<const float4*>(a.x + (size_t)gm * a.ldx + gk)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int half = 0; half < 2; ++half) {
+          float4 v[8];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * NUM_PRODUCERS + tid;
-        const int row = idx >> 4, c4 = idx & 15;
-        const float4 f = v[it];
-        const float hx = __bfloat162float(__float2bfloat16_rn(f.x)), hy = __bfloat162float(__float2bfloat16_rn(f.y));
-        const float hz = __bfloat162float(__float2bfloat16_rn(f.z)), hw = __bfloat162float(__float2bfloat16_rn(f.w));
-        const uint32_t hi0 = pack_bf16x2(hx, hy), hi1 = pack_bf16x2(hz, hw);
-        const uint32_t lo0 = pack_bf16x2(f.x - hx, f.y - hy), lo1 = pack_bf16x2(f.z - hz, f.w - hw);
-        const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)c4 & 1u) * 8u;
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + off), "r"(hi0), "r"(hi1) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + TILE_BYTES + off), "r"(lo0), "r"(lo1) : "memory");
+          for (int it = 0; it < 8; ++it) {
+            const int idx = (half * 8 + it) * GROUP_THREADS + gtid;
+            const int row = idx >> 4, c4 = idx & 15;
+            const int gm = m0 + row, gk = kb * BK + c4 * 4;
+            v[it] = (gm < a.M && gk < a.K) ? *reinterpret_cast<const float4*>(a.x + (size_t)gm * a.ldx + gk)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int idx = (half * 8 + it) * GROUP_THREADS + gtid;
+            const int row = idx >> 4, c4 = idx & 15;
+            const float4 f = v[it];
+            uint32_t hi0, hi1, lo0, lo1;
+            split_pair(f.x, f.y, hi0, lo0);
+            split_pair(f.z, f.w, hi1, lo1);
+            const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)c4 & 1u) * 8u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + off), "r"(hi0), "r"(hi1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_base + TILE_BYTES + off), "r"(lo0), "r"(lo1) : "memory");
+          }
+        }
+        fence_proxy_async();              // generic-proxy stores -> visible to the tensor core's async proxy
+        mbar_arrive(full_bar(s));
       }
-      fence_proxy_async();                // generic-proxy stores -> visible to the tensor core's async proxy
-      mbar_arrive(full_bar(s));
     }
     // ===================== epilogue =====================
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int gm = m0 + warp * 32 + lane;
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int ri = quad * 32 + lane, gm = m0 + ri;
     const bool row_ok = gm < a.M;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = chalf * 64 + cc * 32;
       uint32_t r[32];
       __syncwarp();                        // tcgen05.ld is .sync.aligned: the whole warp issues it together
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
       const int gn0 = n0 + c0;
-      if (row_ok && gn0 < a.N) {
-        float* yrow = a.y + (size_t)gm * a.ldy + gn0;
-        const float* rrow = a.residual != nullptr ? a.residual + (size_t)gm * a.ldr + gn0 : nullptr;
+      if constexpr (!OUT_SPLIT) {
+        if (row_ok && gn0 < a.N) {
+          float* yrow = a.y + (size_t)gm * a.ldy + gn0;
+          const float* rrow = a.residual != nullptr ? a.residual + (size_t)gm * a.ldr + gn0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (gn0 + j < a.N) {             // N is a multiple of 4 on this path
-            float o[4];
+          for (int j = 0; j < 32; j += 4) {
+            if (gn0 + j < a.N) {           // N is a multiple of 4 on this path
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (a.bias != nullptr) bv = *reinterpret_cast<const float4*>(a.bias + gn0 + j);
+              float o0 = apply_act(__uint_as_float(r[j + 0]) + bv.x, a.act);
+              float o1 = apply_act(__uint_as_float(r[j + 1]) + bv.y, a.act);
+              float o2 = apply_act(__uint_as_float(r[j + 2]) + bv.z, a.act);
+              float o3 = apply_act(__uint_as_float(r[j + 3]) + bv.w, a.act);
+              if (rrow != nullptr) {
+                const float4 rv = *reinterpret_cast<const float4*>(rrow + j);
+                o0 += rv.x; o1 += rv.y; o2 += rv.z; o3 += rv.w;
+              }
+              *reinterpret_cast<float4*>(yrow + j) = make_float4(o0, o1, o2, o3);
+            }
+          }
+        }
+      } else {
+        // SplitTile output: this thread's 32 columns are 4 chunks of 8 inside output k-block gn0 / 64
+        const int kb2 = gn0 >> 6;
+        if (row_ok && kb2 < a.kb_out) {
+          uint8_t* tile = a.y_split + ((size_t)m_tile * a.kb_out + kb2) * (2 * TILE_BYTES) + (size_t)ri * 128;
+          const int chunk0 = (gn0 & 63) >> 3;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float t = __uint_as_float(r[j + q]);
-              if (a.bias != nullptr) t += a.bias[gn0 + j + q];
-              o[q] = apply_act(t, a.act);
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const int j = ch * 8 + p * 2, gn = gn0 + j;
+              float o0 = 0.f, o1 = 0.f;
+              if (gn < a.N) {              // N is even; columns >= N are the zero padding of the next K
+                o0 = __uint_as_float(r[j]); o1 = __uint_as_float(r[j + 1]);
+                if (a.bias != nullptr) { o0 += a.bias[gn]; o1 += a.bias[gn + 1]; }
+                o0 = apply_act(o0, a.act); o1 = apply_act(o1, a.act);
+              }
+              split_pair(o0, o1, hi[p], lo[p]);
             }
-            if (rrow != nullptr) {
-              const float4 rv = *reinterpret_cast<const float4*>(rrow + j);
-              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-            }
-            *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            const uint32_t off = (uint32_t)(((chunk0 + ch) ^ (ri & 7)) << 4);
+            *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(tile + TILE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
     }
     __syncwarp();
     tc_fence_before();
-  } else if (warp == 4) {
-    // ===================== MMA issuer =====================
+  } else {
+    // ===================== MMA issuer (warp 8) =====================
     if (lane == 0) {
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
@@ -234,7 +285,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(TcArgs a) {
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -259,6 +310,7 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, __nv_bfloat16* 
 }  // namespace
 
 size_t tc_packed_elems(int N, int K) { return (size_t)ceil_div(N, 128) * ceil_div(K, 64) * 8192; }
+size_t split_tile_bytes(int M, int K) { return (size_t)ceil_div(M, 128) * ceil_div(K, 64) * (2 * TILE_BYTES); }
 
 int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s) {
   const int nt = ceil_div(N, 128), kb = ceil_div(K, 64);
@@ -269,26 +321,44 @@ int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaSt
 }
 
 bool tc_shape_ok(const LinearArgs& a) {
-  return a.wt != nullptr && a.M >= 64 && a.K >= 64 && a.K % 4 == 0 && a.N % 4 == 0 && a.ldx % 4 == 0 && a.ldy % 4 == 0 &&
-         (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0 &&
-         (a.residual == nullptr || (a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15u) == 0));
+  if (a.wt == nullptr || a.M < 64 || a.K < 64 || a.N % 4 != 0) return false;
+  if (a.a_split == nullptr) {
+    if (a.x == nullptr || a.K % 4 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15u) != 0) return false;
+  }
+  if (a.y_split == nullptr) {
+    if (a.y == nullptr || a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) return false;
+    if (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15u) != 0) return false;
+    if (a.residual != nullptr && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15u) != 0)) return false;
+  } else if (a.residual != nullptr) {
+    return false;
+  }
+  return true;
 }
 
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
   static bool attr_set = false;
   if (!attr_set) {
-    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   TcArgs t;
-  t.x = a.x; t.ldx = a.ldx; t.wt = a.wt; t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual;
-  t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
+  t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;
+  t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
+  t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
+  t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM));
-  gemm_tcgen05_kernel<<<grid, 192, SMEM_BYTES, s>>>(t);
+  const bool as = a.a_split != nullptr, os = a.y_split != nullptr;
+  if (as && os) gemm_tcgen05_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
+  else if (as) gemm_tcgen05_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
+  else if (os) gemm_tcgen05_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
+  else gemm_tcgen05_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
   SCV_LAUNCH_CHECK();
   return 0;
 }

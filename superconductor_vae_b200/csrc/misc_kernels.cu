@@ -53,6 +53,94 @@ layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma,
   }
 }
 
+// LayerNorm whose only consumer is a tensor-core projection: one warp per row, the row held in registers
+// (single global read), output written as bf16 hi/lo chunks straight into the SplitTile layout of
+// gemm_tcgen05.cu ([m_tile][k_block][hi 16 KB | lo 16 KB], 128-byte swizzle).  normalize = 0 only splits.
+constexpr int kLnMaxChunks = 4;      // 8-element chunks per lane -> rows up to 1024 wide
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, uint8_t* __restrict__ out, int M, int N, int normalize,
+                       const int* done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int n_chunks = N >> 3, KB = (N + 63) >> 6;
+  const float* xr = x + (size_t)row * ldx;
+  float v[kLnMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < n_chunks) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + ch * 8);
+      const float4 b = *reinterpret_cast<const float4*>(xr + ch * 8 + 4);
+      v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+      v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+    }
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (normalize) {
+    mean = warp_sum(s) / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxChunks; ++j) {
+      if (lane + 32 * j < n_chunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+      }
+    }
+    rstd = 1.0f / sqrtf(warp_sum(q) / (float)N + 1e-5f);
+  }
+  const int mt = row >> 7, ri = row & 127;
+#pragma unroll
+  for (int j = 0; j < kLnMaxChunks; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < KB * 8) {                      // chunks in [n_chunks, KB*8) are the zero padding of the last k-block
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      if (ch < n_chunks) {
+        if (normalize) {
+          const float4 g0 = *reinterpret_cast<const float4*>(gamma + ch * 8), g1 = *reinterpret_cast<const float4*>(gamma + ch * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(beta + ch * 8), b1 = *reinterpret_cast<const float4*>(beta + ch * 8 + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = v[j][e];
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) split_pair(o[2 * p], o[2 * p + 1], hi[p], lo[p]);
+      const int kb = ch >> 3, cj = ch & 7;
+      uint8_t* dst = out + ((size_t)mt * KB + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+int launch_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, void* out_split, int M,
+                           int N, int normalize, const int* done_flag, cudaStream_t s) {
+  SCV_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= kLnMaxChunks * 256, "layernorm_split: N=%d must be a multiple of 8, <= %d",
+              N, kLnMaxChunks * 256);
+  SCV_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "layernorm_split: unaligned input");
+  ProfScope prof(PC_LAYERNORM, s, 8.0 * M * N, 8.0 * M * N);
+  layernorm_split_kernel<<<ceil_div(M, 8), 256, 0, s>>>(x, ldx, gamma, beta, static_cast<uint8_t*>(out_split), M, N,
+                                                         normalize, done_flag);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy, int M,
                      int N, int act, const int* done_flag, cudaStream_t s) {
   SCV_REQUIRE(M > 0 && N > 0, "layernorm: empty shape");
