@@ -430,9 +430,9 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     if (sync_each) {
       SCV_CUDA(cudaStreamSynchronize(s));
     }
-    if ((step & 7) == 7 && step + 1 < steps_max) {
-      // bound the host's run-ahead to <= 16 steps and stop enqueueing once every row has finished
-      const int k = (step >> 3) & 1;
+    if ((step & 3) == 3 && step + 1 < steps_max) {
+      // bound the host's run-ahead to <= 8 steps and stop enqueueing once every row has finished
+      const int k = (step >> 2) & 1;
       if (used[k]) {
         SCV_CUDA(cudaEventSynchronize(D->ev[k]));
         if (D->pinned[k] != 0) break;

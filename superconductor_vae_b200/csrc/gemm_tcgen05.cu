@@ -23,10 +23,11 @@ namespace scv {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2;
+constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int TILE_BYTES = 128 * 128;                       // 128 rows x 64 bf16 = 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;                 // A_hi, A_lo, W
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/; }
+constexpr int STG_PITCH = 36;                               // floats per staged epilogue row (32 + pad, 16-byte aligned)
 constexpr int GROUP_THREADS = 128;
 constexpr int NUM_THREADS = 288;
 constexpr uint32_t TMEM_COLS = 128;
@@ -108,8 +109,8 @@ struct TcArgs {
   const int* done_flag;
 };
 
-template <bool A_SPLIT, bool OUT_SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tcgen05_kernel(TcArgs a) {
+template <bool A_SPLIT, bool OUT_SPLIT, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
   if (a.done_flag != nullptr && *a.done_flag != 0) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -200,62 +201,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tcgen05_kernel(TcArgs a) 
       }
     }
     // ===================== epilogue =====================
+    // TMEM -> registers (thread = one row, 32 columns) -> shared staging (the pipeline stages are free once the
+    // accumulator barrier fires) -> row-contiguous global accesses: each warp instruction touches whole 128-byte
+    // (fp32 output / residual) or 64-byte (SplitTile) row segments instead of 32 scattered 16-byte pieces.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int quad = warp & 3, chalf = warp >> 2;
-    const int ri = quad * 32 + lane, gm = m0 + ri;
-    const bool row_ok = gm < a.M;
+    float* stg = reinterpret_cast<float*>(base_ptr) + warp * (32 * STG_PITCH);
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c0 = chalf * 64 + cc * 32;
       uint32_t r[32];
-      __syncwarp();                        // tcgen05.ld is .sync.aligned: the whole warp issues it together
+      __syncwarp();                        // tcgen05.ld is .sync.aligned; also fences the previous staging pass
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
       const int gn0 = n0 + c0;
       if constexpr (!OUT_SPLIT) {
-        if (row_ok && gn0 < a.N) {
-          float* yrow = a.y + (size_t)gm * a.ldy + gn0;
-          const float* rrow = a.residual != nullptr ? a.residual + (size_t)gm * a.ldr + gn0 : nullptr;
+        const int c4 = lane & 7, rr = lane >> 3;
+        const int gn = gn0 + 4 * c4;
+        if (gn < a.N) {                    // N is a multiple of 4 on this path
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias != nullptr) bv = *reinterpret_cast<const float4*>(a.bias + gn);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (gn0 + j < a.N) {           // N is a multiple of 4 on this path
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (a.bias != nullptr) bv = *reinterpret_cast<const float4*>(a.bias + gn0 + j);
-              float o0 = apply_act(__uint_as_float(r[j + 0]) + bv.x, a.act);
-              float o1 = apply_act(__uint_as_float(r[j + 1]) + bv.y, a.act);
-              float o2 = apply_act(__uint_as_float(r[j + 2]) + bv.z, a.act);
-              float o3 = apply_act(__uint_as_float(r[j + 3]) + bv.w, a.act);
-              if (rrow != nullptr) {
-                const float4 rv = *reinterpret_cast<const float4*>(rrow + j);
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rr, gm = m0 + quad * 32 + row;
+            if (gm < a.M) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 4 * c4);
+              float o0 = apply_act(v.x + bv.x, a.act), o1 = apply_act(v.y + bv.y, a.act);
+              float o2 = apply_act(v.z + bv.z, a.act), o3 = apply_act(v.w + bv.w, a.act);
+              if (a.residual != nullptr) {
+                const float4 rv = *reinterpret_cast<const float4*>(a.residual + (size_t)gm * a.ldr + gn);
                 o0 += rv.x; o1 += rv.y; o2 += rv.z; o3 += rv.w;
               }
-              *reinterpret_cast<float4*>(yrow + j) = make_float4(o0, o1, o2, o3);
+              *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
             }
           }
         }
       } else {
-        // SplitTile output: this thread's 32 columns are 4 chunks of 8 inside output k-block gn0 / 64
-        const int kb2 = gn0 >> 6;
-        if (row_ok && kb2 < a.kb_out) {
-          uint8_t* tile = a.y_split + ((size_t)m_tile * a.kb_out + kb2) * (2 * TILE_BYTES) + (size_t)ri * 128;
-          const int chunk0 = (gn0 & 63) >> 3;
+        // SplitTile output: these 32 columns are chunks chunk0..chunk0+3 of output k-block gn0 / 64
+        const int kb2 = gn0 >> 6, chunk0 = (gn0 & 63) >> 3;
+        const int ch = lane & 3, rr = lane >> 2;
+        const int gn = gn0 + 8 * ch;
+        if (kb2 < a.kb_out) {
+          float bb[8];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t hi[4], lo[4];
+          for (int e = 0; e < 8; ++e) bb[e] = (a.bias != nullptr && gn + e < a.N) ? a.bias[gn + e] : 0.f;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int j = ch * 8 + p * 2, gn = gn0 + j;
-              float o0 = 0.f, o1 = 0.f;
-              if (gn < a.N) {              // N is even; columns >= N are the zero padding of the next K
-                o0 = __uint_as_float(r[j]); o1 = __uint_as_float(r[j + 1]);
-                if (a.bias != nullptr) { o0 += a.bias[gn]; o1 += a.bias[gn + 1]; }
-                o0 = apply_act(o0, a.act); o1 = apply_act(o1, a.act);
+          for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + rr, ri = quad * 32 + row, gm = m0 + ri;
+            if (gm < a.M) {
+              const float4 v0 = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 8 * ch);
+              const float4 v1 = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 8 * ch + 4);
+              const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int p2 = 0; p2 < 4; ++p2) {
+                // columns >= N are the zero padding of the next projection's K
+                const float o0 = gn + 2 * p2 < a.N ? apply_act(vv[2 * p2] + bb[2 * p2], a.act) : 0.f;
+                const float o1 = gn + 2 * p2 + 1 < a.N ? apply_act(vv[2 * p2 + 1] + bb[2 * p2 + 1], a.act) : 0.f;
+                split_pair(o0, o1, hi[p2], lo[p2]);
               }
-              split_pair(o0, o1, hi[p], lo[p]);
+              uint8_t* dst = a.y_split + ((size_t)m_tile * a.kb_out + kb2) * (2 * TILE_BYTES) + (size_t)ri * 128 +
+                             (size_t)(((chunk0 + ch) ^ (ri & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dst + TILE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            const uint32_t off = (uint32_t)(((chunk0 + ch) ^ (ri & 7)) << 4);
-            *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(tile + TILE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
@@ -339,10 +352,11 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
   static bool attr_set = false;
   if (!attr_set) {
-    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define SCV_SET_SMEM(A, O, S) \
+  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S)))
+    SCV_SET_SMEM(false, false, 2); SCV_SET_SMEM(false, true, 2); SCV_SET_SMEM(true, false, 2); SCV_SET_SMEM(true, true, 2);
+    SCV_SET_SMEM(false, false, 4); SCV_SET_SMEM(false, true, 4); SCV_SET_SMEM(true, false, 4); SCV_SET_SMEM(true, true, 4);
+#undef SCV_SET_SMEM
     attr_set = true;
   }
   TcArgs t;
@@ -355,10 +369,18 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM));
   const bool as = a.a_split != nullptr, os = a.y_split != nullptr;
-  if (as && os) gemm_tcgen05_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
-  else if (as) gemm_tcgen05_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
-  else if (os) gemm_tcgen05_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
-  else gemm_tcgen05_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(t);
+  // <= one CTA per SM: a deeper (4-stage, 192 KB) pipeline hides the bulk-copy round trip; larger grids run two
+  // 2-stage CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+  const bool deep = (int)(grid.x * grid.y) <= 148;
+#define SCV_LAUNCH(A, O, S) gemm_tcgen05_kernel<A, O, S><<<grid, NUM_THREADS, smem_bytes(S), s>>>(t)
+  if (deep) {
+    if (as && os) SCV_LAUNCH(true, true, 4); else if (as) SCV_LAUNCH(true, false, 4);
+    else if (os) SCV_LAUNCH(false, true, 4); else SCV_LAUNCH(false, false, 4);
+  } else {
+    if (as && os) SCV_LAUNCH(true, true, 2); else if (as) SCV_LAUNCH(true, false, 2);
+    else if (os) SCV_LAUNCH(false, true, 2); else SCV_LAUNCH(false, false, 2);
+  }
+#undef SCV_LAUNCH
   SCV_LAUNCH_CHECK();
   return 0;
 }
