@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_total() { return g_launches.load(); }
 
 // ------------------------------------------------------------------ profiling
 struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };

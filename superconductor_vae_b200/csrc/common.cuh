@@ -9,6 +9,7 @@ namespace scv {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+long long launch_total();
 
 #define SCV_CUDA(call)                                                                          \
   do {                                                                                          \

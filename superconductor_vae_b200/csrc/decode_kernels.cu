@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
     return;
   }
   // probs = softmax(logits) (:1511); uniform when degenerate (:1512-1513)
-  const float u = Philox::uniform(a.seed, a.offset, (uint32_t)b, (uint32_t)step);
+  const float u = Philox::uniform(a.st->seed, a.st->offset, (uint32_t)(b + a.row_base), (uint32_t)step);
   if (degenerate) {
     if (tid == 0) {
       int tok = min((int)(u * (float)V), V - 1);
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
   }
 }
 
-int launch_sampler(const SamplerArgs& a, cudaStream_t s) {
+int launch_sampler(const SamplerArgs& a, int which, cudaStream_t s) {
   SCV_REQUIRE(a.top_k <= 0 && !(a.top_p < 1.0f), "sampler: top_k/top_p filtering is not implemented in this build");
   const size_t smem = (size_t)a.V * sizeof(float);
   const bool two_phase = !(a.temperature < 0.01f) || a.want_entropy;
@@ -459,9 +459,10 @@ int launch_sampler(const SamplerArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   SCV_REQUIRE(smem <= 200 * 1024, "sampler: vocabulary of %d tokens does not fit in shared memory", a.V);
-  sampler_phase1_kernel<<<a.B, kSamplerThreads, smem, s>>>(a, two_phase ? 0 : 1);
-  SCV_LAUNCH_CHECK();
-  if (two_phase) {
+  if (which == 1) {
+    sampler_phase1_kernel<<<a.B, kSamplerThreads, smem, s>>>(a, two_phase ? 0 : 1);
+    SCV_LAUNCH_CHECK();
+  } else if (two_phase) {
     sampler_phase2_kernel<<<a.B, kSamplerThreads, smem, s>>>(a);
     SCV_LAUNCH_CHECK();
   }
@@ -485,7 +486,8 @@ int launch_step_end(StepState* st, int max_steps, cudaStream_t s) {
   return 0;
 }
 
-__global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B, StepState* st) {
+__global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B, StepState* st,
+                                 unsigned long long seed, unsigned long long offset) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     cur_tokens[i] = kStartIdx;     // (:1392)
@@ -493,11 +495,13 @@ __global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B
   }
   if (i == 0) {
     st->step = 0; st->done = 0; st->n_unfinished = B; st->out_len = 0; st->degenerate = 0; st->next_free_page = 0;
+    st->seed = seed; st->offset = offset;
   }
 }
 
-int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, cudaStream_t s) {
-  init_rows_kernel<<<ceil_div(B, 256), 256, 0, s>>>(cur_tokens, finished, B, st);
+int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
+                     unsigned long long offset, cudaStream_t s) {
+  init_rows_kernel<<<ceil_div(B, 256), 256, 0, s>>>(cur_tokens, finished, B, st, seed, offset);
   SCV_LAUNCH_CHECK();
   return 0;
 }

@@ -18,6 +18,7 @@ struct StepState {
   int degenerate;      // batch-global "logits contain nan/inf" flag of the current step (:1464-1466)
   int next_free_page;  // bump allocator over the KV page pool
   int pad[2];
+  unsigned long long seed, offset;   // Philox key / counter offset of this call (kept out of the kernel arguments)
 };
 
 struct EmbedArgs {
@@ -55,15 +56,17 @@ struct SamplerArgs {
   float temperature = 1.f; int top_k = 0; float top_p = 1.f;
   float stop_boost = 0.f, hard_stop = 0.f;
   int want_logprobs = 0, want_entropy = 0; unsigned flags = 0;
-  unsigned long long seed = 0, offset = 0;
+  int row_base = 0;                                      // first row of this sub-batch (Philox counter)
   long long* out_tokens = nullptr; float* out_logprobs = nullptr; float* out_entropy = nullptr; int out_ld = 0;
   int* cur_tokens = nullptr; unsigned char* finished = nullptr;
   const long long* forced = nullptr;
   StepState* st = nullptr;
 };
-// one or two kernels (the second only when sampling or entropy is requested)
-int launch_sampler(const SamplerArgs& a, cudaStream_t s);
+// which = 1: first kernel (stages logits, publishes the H2 flag, picks the token when the call is plain greedy);
+// which = 2: second kernel (entropy / temperature sampling / log-prob), only when sampling or entropy is requested
+int launch_sampler(const SamplerArgs& a, int which, cudaStream_t s);
 int launch_step_end(StepState* st, int max_steps, cudaStream_t s);
-int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, cudaStream_t s);
+int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
+                     unsigned long long offset, cudaStream_t s);
 
 }  // namespace scv

@@ -39,6 +39,22 @@ struct DevBuf {
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
+constexpr int kMaxSub = 4;
+
+// Everything that is baked into the kernel arguments of one decode step.
+struct GraphKey {
+  int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced;
+  unsigned flags;
+  float temperature, top_p, stop_boost, hard_stop;
+  bool operator==(const GraphKey& o) const {
+    return B == o.B && M == o.M && steps_max == o.steps_max && n_sub == o.n_sub && top_k == o.top_k &&
+           has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced &&
+           flags == o.flags && temperature == o.temperature && top_p == o.top_p && stop_boost == o.stop_boost &&
+           hard_stop == o.hard_stop;
+  }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; };
+
 }  // namespace
 
 struct scv_decoder {
@@ -57,16 +73,46 @@ struct scv_decoder {
   // workspaces (engine-owned, grown on demand)
   DevBuf x, xn, qkv, attn, q2, ff, h1, h2, t3, logits, tlog, slog, ckv, kvpool, cur, fin, ptab, state, mtmp;
   DevBuf xn_s, attn_s, ff_s, h2_s;   // SplitTile (bf16 hi/lo) activations feeding the tcgen05 projections
+  DevBuf o_tok, o_lp, o_ent, masks_buf, forced_buf;   // engine-owned I/O so that a captured step never bakes caller pointers
+  std::vector<GraphEntry> graphs;    // one instantiated CUDA graph of a decode step per call configuration
+  size_t ws_signature = 0;
   int* pinned = nullptr;              // host-pinned: [0..1] done polls, [2..9] StepState copy
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t main = nullptr;             // the decode loop's own stream
+  cudaStream_t sub[kMaxSub] = {};          // sub-batch streams (created on first use)
+  cudaEvent_t ev_sub[kMaxSub] = {};
+  cudaEvent_t ev_fork = nullptr;
   int last_B = 0;
+  int launches_per_step = 0;               // kernels in one step (what a replayed graph launches)
+
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+
+  int ensure_streams() {
+    if (ev_fork != nullptr) return 0;
+    for (int i = 0; i < kMaxSub; ++i) {
+      SCV_CUDA(cudaStreamCreateWithFlags(&sub[i], cudaStreamNonBlocking));
+      SCV_CUDA(cudaEventCreateWithFlags(&ev_sub[i], cudaEventDisableTiming));
+    }
+    SCV_CUDA(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
+    SCV_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    return 0;
+  }
 
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
-                      &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s})
+                      &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
+                      &forced_buf})
       b->release();
+    drop_graphs();
     if (pinned) cudaFreeHost(pinned);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_sub) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto& st_ : sub) if (st_) cudaStreamDestroy(st_);
+    if (main) cudaStreamDestroy(main);
   }
 };
 
@@ -281,31 +327,68 @@ static int ensure_workspace(scv_decoder* D, int B, int M) {
     const size_t need = split_tile_bytes(B, c.dim_feedforward);
     if (need > D->ff_s.cap) { SCV_TRY(D->ff_s.ensure(need)); SCV_CUDA(cudaMemset(D->ff_s.p, 0, need)); }
   }
+  const size_t io = (size_t)B * (c.pe_len - 1);
+  SCV_TRY(D->o_tok.ensure(io * sizeof(long long)));
+  SCV_TRY(D->o_lp.ensure(io * f));
+  SCV_TRY(D->o_ent.ensure(io * f));
+  SCV_TRY(D->forced_buf.ensure(io * sizeof(long long)));
+  SCV_TRY(D->masks_buf.ensure((size_t)5 * c.vocab_size));
+  // captured steps hold raw workspace pointers: drop them whenever any buffer was reallocated
+  size_t sig = 0;
+  for (const DevBuf* b : {&D->x, &D->xn, &D->qkv, &D->attn, &D->q2, &D->ff, &D->h1, &D->h2, &D->t3, &D->logits, &D->tlog,
+                          &D->slog, &D->ckv, &D->kvpool, &D->cur, &D->fin, &D->ptab, &D->state, &D->xn_s, &D->attn_s,
+                          &D->ff_s, &D->h2_s, &D->o_tok, &D->o_lp, &D->o_ent, &D->masks_buf, &D->forced_buf})
+    sig = sig * 1000003u + reinterpret_cast<size_t>(b->p);
+  if (sig != D->ws_signature) { D->drop_graphs(); D->ws_signature = sig; }
   return 0;
 }
 
-static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max, int host_step, cudaStream_t s) {
+// One decode step for rows [r0, r0 + B) of the call's batch (a sub-batch; every buffer is row-major by batch row and
+// the SplitTile buffers are tiled by 128 rows, so a sub-batch is a pointer offset).  phase 1 = everything up to and
+// including the first sampler kernel, phase 2 = the second sampler kernel (sampling / entropy only).
+static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max, int host_step, int r0, int B,
+                       int phase, cudaStream_t s) {
   const scv_decoder_config& c = D->cfg;
-  const int B = A->batch, M = A->n_memory, d = c.d_model, hd = d / c.nhead;
+  const int Bfull = A->batch, M = A->n_memory, d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward;
   StepState* st = D->state.as<StepState>();
   const int* done = &st->done;
   const int pps = ceil_div(c.pe_len, kPagePos);
   const float scale = (float)(1.0 / std::sqrt((double)hd));
-  float* x = D->x.as<float>(); float* xn = D->xn.as<float>(); float* qkv = D->qkv.as<float>();
-  float* attn = D->attn.as<float>(); float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>();
+  float* x = D->x.as<float>() + (size_t)r0 * d; float* xn = D->xn.as<float>() + (size_t)r0 * d;
+  float* qkv = D->qkv.as<float>() + (size_t)r0 * 3 * d; float* attn = D->attn.as<float>() + (size_t)r0 * d;
+  float* q2 = D->q2.as<float>() + (size_t)r0 * d; float* ff = D->ff.as<float>() + (size_t)r0 * dff;
+  int* page_table = D->ptab.as<int>() + (size_t)r0 * pps;
   // Tensor-core step: every projection input is handed over as a bf16 hi/lo SplitTile written by its producer
   // (LayerNorm, attention, previous GEMM epilogue); nullptr selects the fp32 CUDA-core path.
-  const bool tc = use_tensor_cores(c, B);
-  void* xn_s = tc ? D->xn_s.p : nullptr; void* attn_s = tc ? D->attn_s.p : nullptr;
-  void* ff_s = tc ? D->ff_s.p : nullptr; void* h2_s = tc ? D->h2_s.p : nullptr;
+  const bool tc = use_tensor_cores(c, Bfull);
+  auto tile_off = [&](const DevBuf& b, int K) -> void* {
+    return static_cast<unsigned char*>(b.p) + (size_t)(r0 / 128) * ceil_div(K, 64) * 32768;
+  };
+  void* xn_s = tc ? tile_off(D->xn_s, d) : nullptr; void* attn_s = tc ? tile_off(D->attn_s, d) : nullptr;
+  void* ff_s = tc ? tile_off(D->ff_s, dff) : nullptr; void* h2_s = tc ? tile_off(D->h2_s, d) : nullptr;
+  SamplerArgs sp;
+  sp.logits = D->logits.as<float>() + (size_t)r0 * c.vocab_size; sp.ldl = c.vocab_size;
+  sp.type_logits = D->tlog.as<float>() + (size_t)r0 * 8; sp.ldt = 8; sp.stop_logits = D->slog.as<float>() + r0;
+  sp.type_masks = A->type_masks; sp.B = B; sp.V = c.vocab_size; sp.max_len = steps_max + 1;
+  sp.temperature = A->temperature; sp.top_k = A->top_k; sp.top_p = A->top_p;
+  sp.stop_boost = A->stop_boost; sp.hard_stop = A->hard_stop_threshold;
+  sp.want_logprobs = A->want_log_probs; sp.want_entropy = A->want_entropy; sp.flags = A->flags;
+  sp.row_base = r0;
+  sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens) + (size_t)r0 * steps_max;
+  sp.out_logprobs = A->want_log_probs ? A->out_log_probs + (size_t)r0 * steps_max : nullptr;
+  sp.out_entropy = A->want_entropy ? A->out_entropy + (size_t)r0 * steps_max : nullptr;
+  sp.out_ld = steps_max; sp.cur_tokens = D->cur.as<int>() + r0; sp.finished = D->fin.as<unsigned char>() + r0;
+  sp.forced = A->forced_tokens ? reinterpret_cast<const long long*>(A->forced_tokens) + (size_t)r0 * steps_max : nullptr;
+  sp.st = st;
+  if (phase == 2) return launch_sampler(sp, 2, s);
   auto norm = [&](const LNp& P, float* fp32_out) -> int {
     return tc ? launch_layernorm_split(x, d, P.g, P.b, xn_s, B, d, 1, done, s)
               : launch_layernorm(x, d, P.g, P.b, fp32_out, d, B, d, ACT_NONE, done, s);
   };
 
   EmbedArgs e;
-  e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>(); e.x = x; e.B = B;
-  e.page_table = D->ptab.as<int>(); e.pages_per_seq = pps; e.st = st;
+  e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
+  e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
   SCV_TRY(launch_embed(e, s));
 
   const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
@@ -321,7 +404,7 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     sa.q = qkv; sa.ldq = 3 * d; sa.knew = qkv + d; sa.vnew = qkv + 2 * d; sa.ldn = 3 * d;
     sa.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
     sa.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d;
-    sa.page_table = D->ptab.as<int>(); sa.pages_per_seq = pps; sa.page_stride = page_stride; sa.row_stride = d;
+    sa.page_table = page_table; sa.pages_per_seq = pps; sa.page_stride = page_stride; sa.row_stride = d;
     sa.out = attn; sa.ldo = d; sa.B = B; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale; sa.fixed_len = -1;
     sa.max_n = std::max(c.pe_len, M); sa.st = st; sa.host_len_hint = host_step + 1;
     sa.out_split = static_cast<unsigned char*>(attn_s); sa.kb_out = d / 64;
@@ -336,7 +419,7 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     q.M = B; q.N = d; q.K = d; q.done_flag = done;
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
-    float* ckv = D->ckv.as<float>() + (size_t)li * B * M * 2 * d;
+    float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + r0) * M * 2 * d;
     ca.q = q2; ca.ldq = d; ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d;
     ca.row_stride = 2 * d; ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
     ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
@@ -347,20 +430,23 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(co, 0, s));
     // ---- feed forward (:1311-1313)
     SCV_TRY(norm(L.n3, xn));
-    LinearArgs f1 = lin_args(xn, d, L.ff1, ff, c.dim_feedforward, B, ACT_GELU, done);
+    LinearArgs f1 = lin_args(xn, d, L.ff1, ff, dff, B, ACT_GELU, done);
     f1.a_split = xn_s; f1.y_split = ff_s;
     SCV_TRY(launch_linear(f1, 0, s));
-    LinearArgs f2 = lin_args(ff, c.dim_feedforward, L.ff2, x, d, B, ACT_NONE, done);
+    LinearArgs f2 = lin_args(ff, dff, L.ff2, x, d, B, ACT_NONE, done);
     f2.residual = x; f2.ldr = d; f2.a_split = ff_s;
     SCV_TRY(launch_linear(f2, 0, s));
   }
   // ---- heads (:1413, 1417, 1439)
-  float* h1 = D->h1.as<float>(); float* h2 = D->h2.as<float>(); float* t3 = D->t3.as<float>();
+  float* h1 = D->h1.as<float>() + (size_t)r0 * d; float* h2 = D->h2.as<float>() + (size_t)r0 * d;
+  float* t3 = D->t3.as<float>() + (size_t)r0 * (d / 4);
+  float* logits = D->logits.as<float>() + (size_t)r0 * c.vocab_size;
+  float* tlog = D->tlog.as<float>() + (size_t)r0 * 8; float* slog = D->slog.as<float>() + r0;
   SCV_TRY(norm(D->out_ln, h1));
   LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done);
   oa.a_split = xn_s; oa.y_split = h2_s;
   SCV_TRY(launch_linear(oa, 0, s));
-  LinearArgs ob = lin_args(h2, d, D->out_b, D->logits.as<float>(), c.vocab_size, B, ACT_NONE, done);
+  LinearArgs ob = lin_args(h2, d, D->out_b, logits, c.vocab_size, B, ACT_NONE, done);
   ob.a_split = h2_s;
   SCV_TRY(launch_linear(ob, 0, s));
   if (A->type_masks != nullptr) {
@@ -371,39 +457,31 @@ static int decode_step(scv_decoder* D, const scv_generate_args* A, int steps_max
     LinearArgs tb = lin_args(h2, d, D->tt_b, t3, d / 4, B, ACT_GELU, done);
     tb.a_split = h2_s;
     SCV_TRY(launch_linear(tb, 0, s));
-    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, D->tlog.as<float>(), 8, B, ACT_NONE, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, tlog, 8, B, ACT_NONE, done), 0, s));
   }
   if (A->stop_boost > 0.f) {
     SCV_TRY(launch_linear(lin_args(x, d, D->stop_a, t3, d / 4, B, ACT_GELU, done), 0, s));
-    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, D->slog.as<float>(), 1, B, ACT_NONE, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, slog, 1, B, ACT_NONE, done), 0, s));
   }
-  SamplerArgs sp;
-  sp.logits = D->logits.as<float>(); sp.ldl = c.vocab_size;
-  sp.type_logits = D->tlog.as<float>(); sp.ldt = 8; sp.stop_logits = D->slog.as<float>();
-  sp.type_masks = A->type_masks; sp.B = B; sp.V = c.vocab_size; sp.max_len = steps_max + 1;
-  sp.temperature = A->temperature; sp.top_k = A->top_k; sp.top_p = A->top_p;
-  sp.stop_boost = A->stop_boost; sp.hard_stop = A->hard_stop_threshold;
-  sp.want_logprobs = A->want_log_probs; sp.want_entropy = A->want_entropy; sp.flags = A->flags;
-  sp.seed = A->seed; sp.offset = A->offset;
-  sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens);
-  sp.out_logprobs = A->want_log_probs ? A->out_log_probs : nullptr;
-  sp.out_entropy = A->want_entropy ? A->out_entropy : nullptr;
-  sp.out_ld = steps_max; sp.cur_tokens = D->cur.as<int>(); sp.finished = D->fin.as<unsigned char>();
-  sp.forced = reinterpret_cast<const long long*>(A->forced_tokens); sp.st = st;
-  SCV_TRY(launch_sampler(sp, s));
-  SCV_TRY(launch_step_end(st, steps_max, s));
-  return 0;
+  return launch_sampler(sp, 1, s);
 }
 
 int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* stream) {
   SCV_REQUIRE(D && A, "generate: null argument");
+  const scv_generate_args* A_user = A;
   SCV_REQUIRE(A->batch > 0 && A->memory && A->out_tokens && A->out_steps, "generate: bad arguments");
   SCV_REQUIRE(A->n_memory > 0, "generate: n_memory must be positive");
   SCV_REQUIRE(!(A->site_dup_threshold > 0.f), "generate: site_dup gating is not implemented in this build");
   SCV_REQUIRE(!A->want_log_probs || A->out_log_probs, "generate: out_log_probs is NULL");
   SCV_REQUIRE(!A->want_entropy || A->out_entropy, "generate: out_entropy is NULL");
   SCV_REQUIRE(scv_decoder_missing_weights(D) == 0, "generate: weights missing");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // The decode runs on an engine-owned stream (the caller's may be the legacy default stream, which cannot be
+  // captured into a CUDA graph); it is ordered after the caller's stream here and synchronised before returning.
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  SCV_TRY(D->ensure_streams());
+  cudaStream_t s = D->main;
+  SCV_CUDA(cudaEventRecord(D->ev_fork, caller));
+  SCV_CUDA(cudaStreamWaitEvent(s, D->ev_fork, 0));
   const scv_decoder_config& c = D->cfg;
   const int max_len = std::min(A->max_len, c.pe_len);        // silent clamp (:1372-1375)
   const int steps_max = max_len - 1;
@@ -411,7 +489,24 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const int B = A->batch, M = A->n_memory, d = c.d_model;
   SCV_TRY(ensure_workspace(D, B, M));
   StepState* st = D->state.as<StepState>();
-  SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, s));
+  SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s));
+  // the step kernels read / write engine-owned buffers only (so a captured step can be replayed for any call);
+  // caller tensors are copied in here and out after the loop
+  const size_t io = (size_t)B * steps_max;
+  scv_generate_args G = *A;
+  G.out_tokens = D->o_tok.as<int64_t>(); G.out_log_probs = D->o_lp.as<float>(); G.out_entropy = D->o_ent.as<float>();
+  if (A->type_masks != nullptr) {
+    SCV_CUDA(cudaMemcpyAsync(D->masks_buf.p, A->type_masks, (size_t)5 * c.vocab_size, cudaMemcpyDeviceToDevice, s));
+    G.type_masks = D->masks_buf.as<uint8_t>();
+  }
+  if (A->forced_tokens != nullptr) {
+    SCV_CUDA(cudaMemcpyAsync(D->forced_buf.p, A->forced_tokens, io * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    G.forced_tokens = D->forced_buf.as<int64_t>();
+  }
+  SCV_CUDA(cudaMemsetAsync(D->o_tok.p, 0, io * sizeof(long long), s));
+  if (A->want_log_probs) SCV_CUDA(cudaMemsetAsync(D->o_lp.p, 0, io * sizeof(float), s));
+  if (A->want_entropy) SCV_CUDA(cudaMemsetAsync(D->o_ent.p, 0, io * sizeof(float), s));
+  A = &G;
   // per-layer K/V projection of the memory tokens, once per call instead of once per step and layer
   // (the reference re-projects them inside nn.MultiheadAttention at every step, :1302-1307)
   for (int li = 0; li < c.num_layers; ++li) {
@@ -425,14 +520,85 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   D->pinned[0] = D->pinned[1] = 0;
   bool used[2] = {false, false};
   const bool sync_each = (A->flags & SCV_FLAG_SYNC_EVERY_STEP) != 0;
+  const bool two_phase = !(A->temperature < 0.01f) || A->want_entropy;
+  // Sub-batches: the ~150 dependent kernels of a step are short at these sizes (a few microseconds of tensor work
+  // behind fixed launch / prologue / tail costs), so the batch is decoded as independent row ranges on separate
+  // streams whose kernels overlap on the GPU.  Semantics stay batch-global: one shared StepState (step counter,
+  // unfinished-row count, H2 flag), sub-batches re-join before the second sampler kernel and before step_end.
+  int n_sub = 1;
+  {
+    static const int forced = [] { const char* e = getenv("SCV_SUBBATCHES"); return e ? atoi(e) : 0; }();
+    n_sub = forced > 0 ? forced : (B >= 2048 ? 2 : 1);
+    n_sub = std::max(1, std::min(n_sub, kMaxSub));
+    while (n_sub > 1 && round_up(ceil_div(B, n_sub), 128) * (n_sub - 1) >= B) --n_sub;
+  }
+  const int sub_rows = n_sub > 1 ? round_up(ceil_div(B, n_sub), 128) : B;
+  auto enqueue_step = [&](int step) -> int {
+    if (n_sub == 1) {
+      SCV_TRY(decode_rows(D, A, steps_max, step, 0, B, 1, s));
+      if (two_phase) SCV_TRY(decode_rows(D, A, steps_max, step, 0, B, 2, s));
+    } else {
+      SCV_CUDA(cudaEventRecord(D->ev_fork, s));
+      for (int i = 0; i < n_sub; ++i) {
+        const int r0 = i * sub_rows, nb = std::min(sub_rows, B - r0);
+        SCV_CUDA(cudaStreamWaitEvent(D->sub[i], D->ev_fork, 0));
+        SCV_TRY(decode_rows(D, A, steps_max, step, r0, nb, 1, D->sub[i]));
+        SCV_CUDA(cudaEventRecord(D->ev_sub[i], D->sub[i]));
+      }
+      for (int i = 0; i < n_sub; ++i) SCV_CUDA(cudaStreamWaitEvent(s, D->ev_sub[i], 0));
+      if (two_phase) {       // the H2 flag is batch-global: every row's first sampler kernel precedes any second one
+        SCV_CUDA(cudaEventRecord(D->ev_fork, s));
+        for (int i = 0; i < n_sub; ++i) {
+          const int r0 = i * sub_rows, nb = std::min(sub_rows, B - r0);
+          SCV_CUDA(cudaStreamWaitEvent(D->sub[i], D->ev_fork, 0));
+          SCV_TRY(decode_rows(D, A, steps_max, step, r0, nb, 2, D->sub[i]));
+          SCV_CUDA(cudaEventRecord(D->ev_sub[i], D->sub[i]));
+        }
+        for (int i = 0; i < n_sub; ++i) SCV_CUDA(cudaStreamWaitEvent(s, D->ev_sub[i], 0));
+      }
+    }
+    SCV_TRY(launch_step_end(st, steps_max, s));
+    return 0;
+  };
+  // CUDA graph of one step: the launch sequence is identical for every step (position, done flag, RNG seed all live
+  // in device memory), so step 0 runs eagerly and steps >= 1 replay one instantiated graph (one launch per step
+  // instead of ~150-300); cached per call configuration.
+  static const int graph_env = [] { const char* e = getenv("SCV_GRAPH"); return e ? atoi(e) : 1; }();
+  const bool use_graph = graph_env != 0 && !prof_enabled() && !sync_each && steps_max >= 3;
+  const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
+                     A->forced_tokens != nullptr, A->flags, A->temperature, A->top_p, A->stop_boost,
+                     A->hard_stop_threshold};
+  cudaGraphExec_t exec = nullptr;
+  if (use_graph)
+    for (auto& g : D->graphs) if (g.key == key) exec = g.exec;
   for (int step = 0; step < steps_max; ++step) {
-    SCV_TRY(decode_step(D, A, steps_max, step, s));
+    if (use_graph && step >= 1) {
+      if (exec == nullptr) {
+        cudaGraph_t graph = nullptr;
+        SCV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(step);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        SCV_CUDA(ce);
+        SCV_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (D->graphs.size() >= 8) D->drop_graphs();
+        D->graphs.push_back({key, exec});
+      }
+      SCV_CUDA(cudaGraphLaunch(exec, s));
+      count_launch(D->launches_per_step);
+    } else {
+      const long long before = launch_total();
+      SCV_TRY(enqueue_step(step));
+      D->launches_per_step = (int)(launch_total() - before);
+    }
     if (sync_each) {
       SCV_CUDA(cudaStreamSynchronize(s));
     }
-    if ((step & 3) == 3 && step + 1 < steps_max) {
-      // bound the host's run-ahead to <= 8 steps and stop enqueueing once every row has finished
-      const int k = (step >> 2) & 1;
+    const int poll = use_graph ? 2 : 4;
+    if ((step % poll) == poll - 1 && step + 1 < steps_max) {
+      // bound the host's run-ahead to <= 2 * poll steps and stop enqueueing once every row has finished
+      const int k = (step / poll) & 1;
       if (used[k]) {
         SCV_CUDA(cudaEventSynchronize(D->ev[k]));
         if (D->pinned[k] != 0) break;
@@ -442,10 +608,13 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
       used[k] = true;
     }
   }
+  SCV_CUDA(cudaMemcpyAsync(A_user->out_tokens, D->o_tok.p, io * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  if (A->want_log_probs) SCV_CUDA(cudaMemcpyAsync(A_user->out_log_probs, D->o_lp.p, io * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (A->want_entropy) SCV_CUDA(cudaMemcpyAsync(A_user->out_entropy, D->o_ent.p, io * sizeof(float), cudaMemcpyDeviceToDevice, s));
   SCV_CUDA(cudaMemcpyAsync(&D->pinned[2], st, sizeof(StepState), cudaMemcpyDeviceToHost, s));
   SCV_CUDA(cudaStreamSynchronize(s));
   const StepState* hs = reinterpret_cast<const StepState*>(&D->pinned[2]);
-  *A->out_steps = hs->done ? hs->out_len : hs->step;
+  *A_user->out_steps = hs->done ? hs->out_len : hs->step;
   D->last_B = B;
   return 0;
 }

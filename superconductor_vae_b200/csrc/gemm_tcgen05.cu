@@ -17,20 +17,21 @@
 // One 128 x 128 output tile per CTA, 2 CTAs per SM (2 stages x 48 KB each) so one CTA's epilogue overlaps the
 // other's main loop; 9 warps: 0-7 producers/epilogue (warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4)..),
 // warp 8 allocates TMEM and its lane 0 issues the UMMAs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scv {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int TILE_BYTES = 128 * 128;                       // 128 rows x 64 bf16 = 16 KB
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;                 // A_hi, A_lo, W
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/; }
+__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * TILE_BYTES + bn * 128; }       // A_hi, A_lo, W (bn rows x 128 B)
+__host__ __device__ constexpr int smem_bytes(int stages, int bn) { return stages * stage_bytes(bn) + 1024 /*align*/ + 128 /*barriers*/; }
 constexpr int STG_PITCH = 36;                               // floats per staged epilogue row (32 + pad, 16-byte aligned)
 constexpr int GROUP_THREADS = 128;
 constexpr int NUM_THREADS = 288;
-constexpr uint32_t TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,10 +70,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn.
+__host__ __device__ constexpr uint32_t idesc_for(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t kIdesc) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -109,9 +112,13 @@ struct TcArgs {
   const int* done_flag;
 };
 
-template <bool A_SPLIT, bool OUT_SPLIT, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
+template <bool A_SPLIT, bool OUT_SPLIT, int STAGES, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
   if (a.done_flag != nullptr && *a.done_flag != 0) return;
+  constexpr int STAGE_BYTES = stage_bytes(BN);
+  constexpr uint32_t TMEM_COLS = BN;
+  constexpr uint32_t W_BYTES = BN * 128;
+  constexpr uint32_t kIdesc = idesc_for(BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SW128 tiles need 1024-byte alignment
@@ -144,7 +151,8 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * KB * (TILE_BYTES / 2);
+  // weight tiles are packed per 128 output rows: a 256-wide CTA tile is two of them (same k-block, KB tiles apart)
+  const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * (BN / 128) * KB * (TILE_BYTES / 2);
 
   if (warp < 8) {
     // ===================== producers =====================
@@ -156,9 +164,11 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05
           const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
           mbar_wait(empty_bar(s), phase ^ 1u);
           const uint32_t st_base = base + s * STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(s), 3 * TILE_BYTES);
+          mbar_arrive_expect_tx(full_bar(s), 2 * TILE_BYTES + W_BYTES);
           bulk_copy_g2s(st_base, atile0 + (size_t)kb * (2 * TILE_BYTES), 2 * TILE_BYTES, full_bar(s));
-          bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h)
+            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
         }
       }
     } else {
@@ -169,8 +179,10 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05
         mbar_wait(empty_bar(s), phase ^ 1u);
         const uint32_t st_base = base + s * STAGE_BYTES;
         if (gtid == 0) {
-          mbar_expect_tx(full_bar(s), TILE_BYTES);
-          bulk_copy_g2s(st_base + 2 * TILE_BYTES, wtile0 + (size_t)kb * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+          mbar_expect_tx(full_bar(s), W_BYTES);
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h)
+            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -209,8 +221,8 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(base_ptr) + warp * (32 * STG_PITCH);
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c0 = chalf * 64 + cc * 32;
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int c0 = chalf * (BN / 2) + cc * 32;
       uint32_t r[32];
       __syncwarp();                        // tcgen05.ld is .sync.aligned; also fences the previous staging pass
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
@@ -287,8 +299,8 @@ __global__ void __launch_bounds__(NUM_THREADS, STAGES == 2 ? 2 : 1) gemm_tcgen05
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t bd = umma_desc_sw128(st_base + 2 * TILE_BYTES + kk * 32);
-          umma_bf16(tmem_base, umma_desc_sw128(st_base + kk * 32), bd, (kb | kk) != 0 ? 1u : 0u);
-          umma_bf16(tmem_base, umma_desc_sw128(st_base + TILE_BYTES + kk * 32), bd, 1u);
+          umma_bf16(tmem_base, umma_desc_sw128(st_base + kk * 32), bd, (kb | kk) != 0 ? 1u : 0u, kIdesc);
+          umma_bf16(tmem_base, umma_desc_sw128(st_base + TILE_BYTES + kk * 32), bd, 1u, kIdesc);
         }
         umma_commit(empty_bar(s));       // frees the stage once the MMAs that read it have finished
       }
@@ -352,10 +364,12 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
   static bool attr_set = false;
   if (!attr_set) {
-#define SCV_SET_SMEM(A, O, S) \
-  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S)))
-    SCV_SET_SMEM(false, false, 2); SCV_SET_SMEM(false, true, 2); SCV_SET_SMEM(true, false, 2); SCV_SET_SMEM(true, true, 2);
-    SCV_SET_SMEM(false, false, 4); SCV_SET_SMEM(false, true, 4); SCV_SET_SMEM(true, false, 4); SCV_SET_SMEM(true, true, 4);
+#define SCV_SET_SMEM(A, O, S, N) \
+  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, N)))
+#define SCV_SET_ALL(S, N) \
+  SCV_SET_SMEM(false, false, S, N); SCV_SET_SMEM(false, true, S, N); SCV_SET_SMEM(true, false, S, N); SCV_SET_SMEM(true, true, S, N)
+    SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256);
+#undef SCV_SET_ALL
 #undef SCV_SET_SMEM
     attr_set = true;
   }
@@ -367,19 +381,29 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
-  dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM));
   const bool as = a.a_split != nullptr, os = a.y_split != nullptr;
-  // <= one CTA per SM: a deeper (4-stage, 192 KB) pipeline hides the bulk-copy round trip; larger grids run two
-  // 2-stage CTAs per SM so one CTA's epilogue overlaps the other's main loop.
-  const bool deep = (int)(grid.x * grid.y) <= 148;
-#define SCV_LAUNCH(A, O, S) gemm_tcgen05_kernel<A, O, S><<<grid, NUM_THREADS, smem_bytes(S), s>>>(t)
-  if (deep) {
-    if (as && os) SCV_LAUNCH(true, true, 4); else if (as) SCV_LAUNCH(true, false, 4);
-    else if (os) SCV_LAUNCH(false, true, 4); else SCV_LAUNCH(false, false, 4);
+  // Tile choice: 128 x 128 with a deep 4-stage pipeline when the grid is at most one CTA per SM, else two 2-stage
+  // CTAs per SM so that one CTA's epilogue overlaps the other's main loop; 128 x 256 (SCV_GEMM_BN=256) halves the
+  // A re-reads but runs one CTA per SM.
+  static const int force_bn = [] { const char* e = getenv("SCV_GEMM_BN"); return e ? atoi(e) : 0; }();
+  const int n128 = ceil_div(a.N, 128), mt = ceil_div(a.M, BM);
+  // measured on B200 (profiles/README.md, r01e): the 256-wide tile is slower at these K (8-32 k-blocks, one CTA per
+  // SM so no epilogue overlap), so it stays opt-in
+  const bool wide = force_bn == 256 && n128 % 2 == 0;
+#define SCV_LAUNCH(A, O, S, N) gemm_tcgen05_kernel<A, O, S, N><<<grid, NUM_THREADS, smem_bytes(S, N), s>>>(t)
+#define SCV_LAUNCH_MODE(S, N)                                                            \
+  do {                                                                                   \
+    if (as && os) SCV_LAUNCH(true, true, S, N); else if (as) SCV_LAUNCH(true, false, S, N); \
+    else if (os) SCV_LAUNCH(false, true, S, N); else SCV_LAUNCH(false, false, S, N);         \
+  } while (0)
+  if (wide) {
+    dim3 grid(n128 / 2, mt);
+    SCV_LAUNCH_MODE(3, 256);
   } else {
-    if (as && os) SCV_LAUNCH(true, true, 2); else if (as) SCV_LAUNCH(true, false, 2);
-    else if (os) SCV_LAUNCH(false, true, 2); else SCV_LAUNCH(false, false, 2);
+    dim3 grid(n128, mt);
+    if (n128 * mt <= 148) SCV_LAUNCH_MODE(4, 128); else SCV_LAUNCH_MODE(2, 128);
   }
+#undef SCV_LAUNCH_MODE
 #undef SCV_LAUNCH
   SCV_LAUNCH_CHECK();
   return 0;
