@@ -54,6 +54,7 @@ struct SamplerArgs {
   const uint8_t* type_masks = nullptr;
   int B = 0, V = 0, max_len = 0;
   float temperature = 1.f; int top_k = 0; float top_p = 1.f;
+  int sort_n = 0;                                        // set by the launcher: padded vocabulary for top-k/top-p
   float stop_boost = 0.f, hard_stop = 0.f;
   int want_logprobs = 0, want_entropy = 0; unsigned flags = 0;
   int row_base = 0;                                      // first row of this sub-batch (Philox counter)

@@ -292,7 +292,8 @@ int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const fl
 // fills UMMA tiles and feature dims that are whole 64-wide k-blocks; smaller shapes use the CUDA-core kernels.
 static bool use_tensor_cores(const scv_decoder_config& c, int B) {
   static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
-  return forced != 1 && B >= 64 && c.d_model % 64 == 0 && c.dim_feedforward % 64 == 0 && (c.d_model / c.nhead) % 8 == 0 &&
+  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 64; }();
+  return forced != 1 && B >= min_rows && c.d_model % 64 == 0 && c.dim_feedforward % 64 == 0 && (c.d_model / c.nhead) % 8 == 0 &&
          c.vocab_size % 4 == 0 && c.d_model <= 1024;
 }
 
@@ -529,6 +530,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   {
     static const int forced = [] { const char* e = getenv("SCV_SUBBATCHES"); return e ? atoi(e) : 0; }();
     n_sub = forced > 0 ? forced : (B >= 2048 ? 2 : 1);
+    if (prof_enabled()) n_sub = 1;       // per-kernel timing wants one kernel at a time
     n_sub = std::max(1, std::min(n_sub, kMaxSub));
     while (n_sub > 1 && round_up(ceil_div(B, n_sub), 128) * (n_sub - 1) >= B) --n_sub;
   }

@@ -182,6 +182,12 @@ struct scv_encoder {
   ~scv_encoder() { for (DevBuf* b : {&t0, &t1, &t2, &fused_in, &cond, &sc_in, &small}) b->release(); }
 };
 
+// nn.Linear with an extra tcgen05-tiled weight copy whenever the tensor-core path can take the projection
+static int add_lin(WeightStore& W, const std::string& prefix, int N, int K, Lin* out) {
+  const bool tiled = K >= 64 && K % 4 == 0 && N % 4 == 0;
+  return W.add_linear(prefix, N, K, out, true, tiled);
+}
+
 static int enc_register(scv_encoder* E) {
   const scv_encoder_config& c = E->cfg;
   WeightStore& W = E->ws;
@@ -189,91 +195,91 @@ static int enc_register(scv_encoder* E) {
   std::string p = "element_encoder.element_embedding.";
   E->elem_table = W.add_matrix(p + "element_embed.weight", c.n_element_rows, e, &E->ld_table);
   if (!E->elem_table) return 2;
-  SCV_TRY(W.add_linear(p + "property_encoder.0", e, 11, &E->prop_enc));
+  SCV_TRY(add_lin(W, p + "property_encoder.0", e, 11, &E->prop_enc));
   SCV_TRY(W.add_layernorm(p + "property_encoder.1", e, &E->prop_ln));
-  SCV_TRY(W.add_linear(p + "combiner", e, 2 * e, &E->combiner));
+  SCV_TRY(add_lin(W, p + "combiner", e, 2 * e, &E->combiner));
   for (const char* n : {"property_encoder.0.weight", "property_encoder.0.bias", "property_encoder.1.weight",
                         "property_encoder.1.bias", "combiner.weight", "combiner.bias"})
     W.mark_optional(p + n);
   p = "element_encoder.element_attention.";
   E->query = W.add_matrix(p + "query", c.n_attention_heads, e / c.n_attention_heads, &E->ld_query);
   if (!E->query) return 2;
-  SCV_TRY(W.add_linear(p + "key_proj", e, e, &E->key_proj));
-  SCV_TRY(W.add_linear(p + "value_proj", e, e, &E->value_proj));
-  SCV_TRY(W.add_linear(p + "output_proj", e, e, &E->att_out));
+  SCV_TRY(add_lin(W, p + "key_proj", e, e, &E->key_proj));
+  SCV_TRY(add_lin(W, p + "value_proj", e, e, &E->value_proj));
+  SCV_TRY(add_lin(W, p + "output_proj", e, e, &E->att_out));
   SCV_TRY(W.add_layernorm(p + "layer_norm", e, &E->att_ln));
-  SCV_TRY(W.add_linear("element_encoder.output_projection.0", f, e, &E->elem_out));
+  SCV_TRY(add_lin(W, "element_encoder.output_projection.0", f, e, &E->elem_out));
   SCV_TRY(W.add_layernorm("element_encoder.output_projection.1", f, &E->elem_out_ln));
-  SCV_TRY(W.add_linear("magpie_encoder.0", 2 * f, c.magpie_dim, &E->mag_a));
+  SCV_TRY(add_lin(W, "magpie_encoder.0", 2 * f, c.magpie_dim, &E->mag_a));
   SCV_TRY(W.add_layernorm("magpie_encoder.1", 2 * f, &E->mag_ln_a));
-  SCV_TRY(W.add_linear("magpie_encoder.4", f, 2 * f, &E->mag_b));
+  SCV_TRY(add_lin(W, "magpie_encoder.4", f, 2 * f, &E->mag_b));
   SCV_TRY(W.add_layernorm("magpie_encoder.5", f, &E->mag_ln_b));
-  SCV_TRY(W.add_linear("tc_encoder.0", f / 2, 1, &E->tc_a));
-  SCV_TRY(W.add_linear("tc_encoder.2", f, f / 2, &E->tc_b));
+  SCV_TRY(add_lin(W, "tc_encoder.0", f / 2, 1, &E->tc_a));
+  SCV_TRY(add_lin(W, "tc_encoder.2", f, f / 2, &E->tc_b));
   SCV_TRY(W.add_layernorm("tc_encoder.3", f, &E->tc_ln));
-  SCV_TRY(W.add_linear("fusion.0", 3 * f, 3 * f, &E->fusion));
+  SCV_TRY(add_lin(W, "fusion.0", 3 * f, 3 * f, &E->fusion));
   SCV_TRY(W.add_layernorm("fusion.1", 3 * f, &E->fusion_ln));
   int prev = 3 * f;
   E->enc_lin.resize(c.n_encoder_hidden); E->enc_ln.resize(c.n_encoder_hidden);
   for (int j = 0; j < c.n_encoder_hidden; ++j) {
-    SCV_TRY(W.add_linear("vae_encoder.encoder." + std::to_string(3 * j), c.encoder_hidden[j], prev, &E->enc_lin[j]));
+    SCV_TRY(add_lin(W, "vae_encoder.encoder." + std::to_string(3 * j), c.encoder_hidden[j], prev, &E->enc_lin[j]));
     SCV_TRY(W.add_layernorm("vae_encoder.encoder." + std::to_string(3 * j + 1), c.encoder_hidden[j], &E->enc_ln[j]));
     prev = c.encoder_hidden[j];
   }
-  SCV_TRY(W.add_linear("vae_encoder.fc_mean", c.latent_dim, prev, &E->fc_mean));
+  SCV_TRY(add_lin(W, "vae_encoder.fc_mean", c.latent_dim, prev, &E->fc_mean));
   prev = c.latent_dim;
   E->bb_lin.resize(c.n_decoder_hidden); E->bb_ln.resize(c.n_decoder_hidden);
   for (int j = 0; j < c.n_decoder_hidden; ++j) {
-    SCV_TRY(W.add_linear("decoder_backbone." + std::to_string(4 * j), c.decoder_hidden[j], prev, &E->bb_lin[j]));
+    SCV_TRY(add_lin(W, "decoder_backbone." + std::to_string(4 * j), c.decoder_hidden[j], prev, &E->bb_lin[j]));
     SCV_TRY(W.add_layernorm("decoder_backbone." + std::to_string(4 * j + 1), c.decoder_hidden[j], &E->bb_ln[j]));
     prev = c.decoder_hidden[j];
   }
   const int bb = prev, L = c.latent_dim;
-  SCV_TRY(W.add_linear("tc_proj", 256, bb, &E->tc_proj));
-  SCV_TRY(W.add_linear("tc_res_block.0", 256, 256, &E->res_a));
+  SCV_TRY(add_lin(W, "tc_proj", 256, bb, &E->tc_proj));
+  SCV_TRY(add_lin(W, "tc_res_block.0", 256, 256, &E->res_a));
   SCV_TRY(W.add_layernorm("tc_res_block.1", 256, &E->res_ln));
-  SCV_TRY(W.add_linear("tc_res_block.4", 256, 256, &E->res_b));
+  SCV_TRY(add_lin(W, "tc_res_block.4", 256, 256, &E->res_b));
   SCV_TRY(W.add_layernorm("tc_out.0", 256, &E->tc_out_ln));
-  SCV_TRY(W.add_linear("tc_out.2", 128, 256, &E->tc_out_a));
-  SCV_TRY(W.add_linear("tc_out.4", 1, 128, &E->tc_out_b));
-  SCV_TRY(W.add_linear("magpie_head.0", bb, bb, &E->mag_head_a));
-  SCV_TRY(W.add_linear("magpie_head.2", c.magpie_dim, bb, &E->mag_head_b));
-  SCV_TRY(W.add_linear("attended_head.0", f, bb, &E->att_head));
+  SCV_TRY(add_lin(W, "tc_out.2", 128, 256, &E->tc_out_a));
+  SCV_TRY(add_lin(W, "tc_out.4", 1, 128, &E->tc_out_b));
+  SCV_TRY(add_lin(W, "magpie_head.0", bb, bb, &E->mag_head_a));
+  SCV_TRY(add_lin(W, "magpie_head.2", c.magpie_dim, bb, &E->mag_head_b));
+  SCV_TRY(add_lin(W, "attended_head.0", f, bb, &E->att_head));
   SCV_TRY(W.add_layernorm("attended_head.1", f, &E->att_head_ln));
-  SCV_TRY(W.add_linear("competence_head.0", L / 4, L, &E->comp_a));
-  SCV_TRY(W.add_linear("competence_head.2", 1, L / 4, &E->comp_b));
-  SCV_TRY(W.add_linear("fraction_head.0", 256, L, &E->frac_a));
+  SCV_TRY(add_lin(W, "competence_head.0", L / 4, L, &E->comp_a));
+  SCV_TRY(add_lin(W, "competence_head.2", 1, L / 4, &E->comp_b));
+  SCV_TRY(add_lin(W, "fraction_head.0", 256, L, &E->frac_a));
   SCV_TRY(W.add_layernorm("fraction_head.1", 256, &E->frac_ln));
-  SCV_TRY(W.add_linear("fraction_head.4", 128, 256, &E->frac_b));
-  SCV_TRY(W.add_linear("fraction_head.6", c.max_elements + 1, 128, &E->frac_c));
-  SCV_TRY(W.add_linear("hp_head.0", 256, L, &E->hp_a));
-  SCV_TRY(W.add_linear("hp_head.2", 1, 256, &E->hp_b));
-  SCV_TRY(W.add_linear("tc_class_head.0", 256, bb, &E->cls_a));
-  SCV_TRY(W.add_linear("tc_class_head.3", 5, 256, &E->cls_b));
+  SCV_TRY(add_lin(W, "fraction_head.4", 128, 256, &E->frac_b));
+  SCV_TRY(add_lin(W, "fraction_head.6", c.max_elements + 1, 128, &E->frac_c));
+  SCV_TRY(add_lin(W, "hp_head.0", 256, L, &E->hp_a));
+  SCV_TRY(add_lin(W, "hp_head.2", 1, 256, &E->hp_b));
+  SCV_TRY(add_lin(W, "tc_class_head.0", 256, bb, &E->cls_a));
+  SCV_TRY(add_lin(W, "tc_class_head.3", 5, 256, &E->cls_b));
   const int sc_in = L + 1 + c.magpie_dim + 1 + c.max_elements + 1 + 1 + 5;
-  SCV_TRY(W.add_linear("sc_head.0", 512, sc_in, &E->sc_a));
+  SCV_TRY(add_lin(W, "sc_head.0", 512, sc_in, &E->sc_a));
   SCV_TRY(W.add_layernorm("sc_head.2", 512, &E->sc_ln));
-  SCV_TRY(W.add_linear("sc_head.4", 128, 512, &E->sc_b));
-  SCV_TRY(W.add_linear("sc_head.6", 1, 128, &E->sc_c));
+  SCV_TRY(add_lin(W, "sc_head.4", 128, 512, &E->sc_b));
+  SCV_TRY(add_lin(W, "sc_head.6", 1, 128, &E->sc_c));
   p = "hierarchical_family_head.";
-  SCV_TRY(W.add_linear(p + "coarse_head.0", 256, bb + 1, &E->co_a));
+  SCV_TRY(add_lin(W, p + "coarse_head.0", 256, bb + 1, &E->co_a));
   SCV_TRY(W.add_layernorm(p + "coarse_head.1", 256, &E->co_ln));
-  SCV_TRY(W.add_linear(p + "coarse_head.4", 128, 256, &E->co_b));
-  SCV_TRY(W.add_linear(p + "coarse_head.6", 7, 128, &E->co_c));
-  SCV_TRY(W.add_linear(p + "cuprate_sub_head.0", 128, bb + 1, &E->cu_a));
+  SCV_TRY(add_lin(W, p + "coarse_head.4", 128, 256, &E->co_b));
+  SCV_TRY(add_lin(W, p + "coarse_head.6", 7, 128, &E->co_c));
+  SCV_TRY(add_lin(W, p + "cuprate_sub_head.0", 128, bb + 1, &E->cu_a));
   SCV_TRY(W.add_layernorm(p + "cuprate_sub_head.1", 128, &E->cu_ln));
-  SCV_TRY(W.add_linear(p + "cuprate_sub_head.4", 64, 128, &E->cu_b));
-  SCV_TRY(W.add_linear(p + "cuprate_sub_head.6", 6, 64, &E->cu_c));
-  SCV_TRY(W.add_linear(p + "iron_sub_head.0", 64, bb + 1, &E->ir_a));
+  SCV_TRY(add_lin(W, p + "cuprate_sub_head.4", 64, 128, &E->cu_b));
+  SCV_TRY(add_lin(W, p + "cuprate_sub_head.6", 6, 64, &E->cu_c));
+  SCV_TRY(add_lin(W, p + "iron_sub_head.0", 64, bb + 1, &E->ir_a));
   SCV_TRY(W.add_layernorm(p + "iron_sub_head.1", 64, &E->ir_ln));
-  SCV_TRY(W.add_linear(p + "iron_sub_head.4", 2, 64, &E->ir_b));
+  SCV_TRY(add_lin(W, p + "iron_sub_head.4", 2, 64, &E->ir_b));
   return 0;
 }
 
 static int lin(const float* x, int ldx, const Lin& L, float* y, int ldy, int M, int act, cudaStream_t s,
                const float* residual = nullptr, int ldr = 0) {
   LinearArgs a;
-  a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.bias = L.b; a.y = y; a.ldy = ldy; a.M = M; a.N = L.N; a.K = L.K;
+  a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.wt = L.wt; a.bias = L.b; a.y = y; a.ldy = ldy; a.M = M; a.N = L.N; a.K = L.K;
   a.act = act; a.residual = residual; a.ldr = ldr;
   return launch_linear(a, 0, s);
 }

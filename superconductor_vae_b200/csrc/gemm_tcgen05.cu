@@ -346,7 +346,8 @@ int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaSt
 }
 
 bool tc_shape_ok(const LinearArgs& a) {
-  if (a.wt == nullptr || a.M < 64 || a.K < 64 || a.N % 4 != 0) return false;
+  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 64; }();
+  if (a.wt == nullptr || a.M < min_rows || a.K < 64 || a.N % 4 != 0) return false;
   if (a.a_split == nullptr) {
     if (a.x == nullptr || a.K % 4 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15u) != 0) return false;
   }

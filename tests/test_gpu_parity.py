@@ -256,6 +256,41 @@ def test_sampled_logprobs_and_entropy_match_oracle_replay(golden_dir, name):
     assert not torch.equal(t3.cpu()[:, :min(t3.shape[1], t.shape[1])], t[:, :min(t3.shape[1], t.shape[1])])
 
 
+@pytest.mark.parametrize("name,kw", [("tiny", dict(top_k=7)), ("tiny", dict(top_p=0.8)), ("tiny", dict(top_k=20, top_p=0.6)),
+                                     ("c512b_b4", dict(top_k=50)), ("c512b_b4", dict(top_p=0.9))])
+def test_topk_topp_filtering_matches_oracle_replay(golden_dir, name, kw):
+    """top-k / nucleus filtering (reference :1489-1503): every sampled token must lie inside the oracle's filtered set
+    and carry the oracle's log-prob of the filtered, temperature-scaled distribution (1e-3 abs)."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    t, lp, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), temperature=0.9, heads_pred=_cuda(heads),
+                                          max_len=min(shape.max_len, 16), return_log_probs=True, _seed=3, **kw)
+    t, lp = t.cpu(), lp.cpu()
+    rt, rlp, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.9, heads_pred=heads,
+                                           max_len=min(shape.max_len, 16), return_log_probs=True, forced_tokens=t, **kw)
+    assert rt.shape == t.shape
+    assert float(rlp.min()) > math.log(1e-8) + 1e-3, "a sampled token fell outside the oracle's top-k / top-p set"
+    torch.testing.assert_close(lp, rlp, rtol=1e-3, atol=1e-3)
+
+
+def test_topk_histogram_stays_inside_the_top_k(golden_dir):
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    n, k = 20000, 5
+    trace = {}
+    DO.generate_with_kv_cache(sd, shape.nhead, z[:1], stoich_pred=stoich[:1], temperature=1.0, max_len=2,
+                              heads_pred={kk: v[:1] for kk, v in heads.items()}, trace=trace)
+    top = set(trace["final_logits"][0][0].topk(k).indices.tolist())
+    mem = dec.precompute_memory(_cuda(z[:1]), None, _cuda(stoich[:1]), _cuda({kk: v[:1] for kk, v in heads.items()}))
+    old = dec.max_rows_per_call
+    dec.max_rows_per_call = n
+    try:
+        t, _, _ = dec.generate_with_kv_cache(None, temperature=1.0, top_k=k, max_len=2, _seed=9,
+                                             cached_memory=mem.expand(n, -1, -1).contiguous())
+    finally:
+        dec.max_rows_per_call = old
+    seen = set(t[:, 0].cpu().tolist())
+    assert seen == top, (seen, top)
+
+
 def test_sampling_distribution_matches_reference_softmax(golden_dir):
     """First-step token histogram over 200k draws of one latent vs softmax(logits/T) of the oracle:
     chi-square over bins with expected count >= 20 must stay below the 99.9% quantile."""
