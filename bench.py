@@ -26,6 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
 
 METRIC = "formulas/sec (KV-cache decode, bf16)"
 UNIT = "formulas/s"
@@ -97,7 +98,7 @@ def algorithmic_flops(B, executed_steps):
 # synthetic weights / inputs; measured on the B200 by the engine arm and asserted there).  The CPU sample is run
 # for the same number of steps so that its cost per formula is that of the full batch, not of a small batch
 # that happens to finish early.
-FULL_BATCH_STEPS = 63
+FULL_BATCH_STEPS = 22      # measured on B200 (profiles/bench_r01*.json: "executed_decode_steps": 22)
 
 
 def cpu_oracle_run(rows, threads, max_len=64, repeats=1, steps=FULL_BATCH_STEPS):

@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Throughput of the other BASELINE.json configurations (3: RLOO rollouts, 4: 1M SLERP latents, 5: fused encoder).
+Not the driver's contract bench (that is bench.py = config 2); prints one JSON line per configuration.
+
+    python bench_configs.py [--configs 3,4,5] [--latents 1000000]
+    torchrun --nproc-per-node N bench_configs.py --configs 4        # config 4 sharded, NCCL gather of sequences
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+
+import torch
+import torch.distributed as dist
+
+import superconductor_vae_b200 as S
+from superconductor_vae_b200 import latent, parallel, synthetic as Sy
+from superconductor_vae_b200.tokenizer import FractionAwareTokenizer
+
+
+def timed(fn, warmup=1, iters=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        out = fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / iters, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--latents", type=int, default=1_000_000)
+    args = ap.parse_args()
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(Sy.make_decoder_state_dict(Sy.C512, 0), nhead=8, device=dev)
+    enc = S.FullMaterialsVAE.from_state_dict(Sy.make_encoder_state_dict(Sy.ENC_DEFAULT, 1), device=dev)
+    tok = FractionAwareTokenizer(max_len=64, fractions=[f"{i + 1}/100003" for i in range(4317)],
+                                 isotopes=[f"{300 + i}Og" for i in range(291)])
+    masks = tok.get_type_masks(dev)
+    todo = [int(c) for c in args.configs.split(",")]
+
+    if 3 in todo and rank == 0:
+        # RLOO: 2048 latents x k = 4 samples (sample-major repeat), temperature 1.2, log-probs + entropy + mask
+        B, k = 2048, 4
+        z = Sy.make_latents(B, 2048, 1234).to(dev).repeat(k, 1)
+        st, hp = Sy.make_conditioning(B, 13, 1234)
+        st, hp = st.to(dev).repeat(k, 1), {n: v.to(dev).repeat(k, *([1] * (v.dim() - 1))) for n, v in hp.items()}
+        fn = lambda: dec.sample_for_reinforce(z, stoich_pred=st, temperature=1.2, max_len=64, stop_boost=10.0,
+                                              heads_pred=hp, _seed=7)
+        ms, (t, lp, en, mk) = timed(fn)
+        print(json.dumps({"config": 3, "what": "RLOO rollouts: 2048 latents x 4 samples, temperature 1.2, per-token log-probs, "
+                          "entropy and mask (stop_boost 10, no hard masks so the reference's H2 fallback cannot trip)",
+                          "rows": B * k, "executed_decode_steps": int(t.shape[1]), "ms": ms,
+                          "formulas_per_s": B * k / (ms / 1e3), "mean_len": float(mk.sum(1).mean())}))
+
+    if 5 in todo and rank == 0:
+        n = 52800
+        idx, frac, mask, magpie, tc = (t.to(dev) for t in Sy.make_compositions(n, 7))
+
+        def fn():
+            z = enc.encode(idx, frac, mask, magpie, tc)["z"]
+            st, hp = enc.conditioning(z)
+            return dec.precompute_memory(z, None, st, hp)
+        ms, mem = timed(fn)
+        print(json.dumps({"config": 5, "what": "three-branch encoder + all heads + memory tokens on 52,800 synthetic compositions",
+                          "rows": n, "ms": ms, "rows_per_s": n / (ms / 1e3), "memory_shape": list(mem.shape),
+                          "algorithmic_tflops": n * 103.4e6 / (ms * 1e9)}))
+
+    if 4 in todo:
+        # 1M SLERP-interpolated latents between 1024 anchors, conditioning from z alone (notebook pipeline),
+        # greedy decode with masks + stop head, rows sharded over the ranks, NCCL gather of token ids only
+        N = args.latents
+        lo, hi = parallel.shard_bounds(N, world, rank)
+        anchors = Sy.make_latents(1024, 2048, 1234).to(dev)
+        g = torch.Generator().manual_seed(99)
+        i1 = torch.randint(0, 1024, (N,), generator=g)
+        i2 = (i1 + torch.randint(1, 1024, (N,), generator=g)) % 1024
+        tt = torch.rand((N,), generator=g) * 0.9 + 0.05
+        i1, i2, tt = i1[lo:hi].to(dev), i2[lo:hi].to(dev), tt[lo:hi].to(dev)
+        chunk = 65536
+        out = torch.zeros((hi - lo, 63), dtype=torch.int16, device=dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        L = 0
+        for c0 in range(0, hi - lo, chunk):
+            c1 = min(hi - lo, c0 + chunk)
+            z = latent.slerp_rows(anchors, i1[c0:c1], i2[c0:c1], tt[c0:c1])
+            toks = latent.decode_z_batch(enc, dec, z, temperature=0.001, type_masks=masks, max_len=64)
+            out[c0:c1, :toks.shape[1]] = toks.to(torch.int16)
+            L = max(L, toks.shape[1])
+        if world > 1:
+            gathered = parallel.gather_rows(out[:, :L].contiguous(), N, 0)
+        else:
+            gathered = out[:, :L]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax)
+        if rank == 0:
+            lens = (gathered == 2).int().argmax(dim=1) + 1
+            print(json.dumps({"config": 4, "what": "SLERP latents -> heads_from_latent -> greedy decode (masks + stop head), "
+                              "sharded over ranks, gather of int16 token ids", "latents": N, "n_gpus": world,
+                              "seconds": dt, "formulas_per_s": N / dt, "max_len_gathered": int(gathered.shape[1]),
+                              "mean_formula_len": float(lens.float().mean()), "sample": tok.decode_batch(gathered[:2])}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,15 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_total() { return g_launches.load(); }
+// PDL pays off when the kernels are latency-bound (small batches: ~8 % per step on B200); at thousands of rows the
+// early-launched CTAs only compete for shared memory / TMEM with the kernel that is still running (measured 3 %
+// slower), so the decoder switches it per call.  SCV_PDL=0/1 forces it.
+static bool g_pdl_call = true;
+void set_pdl_for_call(bool on) { g_pdl_call = on; }
+bool pdl_enabled() {
+  static const int forced = [] { const char* e = getenv("SCV_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  return forced >= 0 ? forced == 1 : g_pdl_call;
+}
 
 // ------------------------------------------------------------------ profiling
 struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };

@@ -55,6 +55,27 @@ struct ProfScope {
   cudaStream_t s_;
 };
 
+// Programmatic dependent launch (PDL): every per-step kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel of the stream may be scheduled while this one
+// is still running; griddepcontrol.wait blocks until all prerequisite grids have completed and flushed their
+// memory, so everything that reads a predecessor's output comes after pdl_wait().  What runs before it (barrier
+// init, TMEM allocation, index math) overlaps the predecessor's tail.  SCV_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+void set_pdl_for_call(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
 
 constexpr int kEndIdx = 2;    // END_IDX (models/autoregressive_decoder.py:97)

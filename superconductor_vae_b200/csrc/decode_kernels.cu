@@ -13,7 +13,9 @@ namespace scv {
 // Also grows the row's KV page list when the step crosses a page boundary.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
+  pdl_wait();
   if (a.st->done) return;
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const int step = a.st->step;
   if (threadIdx.x == 0 && (step & (kPagePos - 1)) == 0) {
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
 
 int launch_embed(const EmbedArgs& a, cudaStream_t s) {
   ProfScope prof(PC_EMBED, s, 1.0 * a.B * a.d, 6.0 * a.B * a.d);
-  embed_kernel<<<a.B, 128, 0, s>>>(a);
+  SCV_CUDA(launch_k(embed_kernel, dim3(a.B), dim3(128), 0, s, a));
   SCV_LAUNCH_CHECK();
   return 0;
 }
@@ -44,7 +46,9 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
 template <int EPL>
 __global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs a) {
   extern __shared__ float sc_all[];
+  pdl_wait();
   if (a.st->done) return;
+  pdl_launch_dependents();
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   if (gw >= a.B * a.nhead) return;
@@ -184,7 +188,9 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs a) {
 template <int LPP>
 __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   extern __shared__ float sc_all[];
+  pdl_wait();
   if (a.st->done) return;
+  pdl_launch_dependents();
   constexpr int PPI = 32 / LPP;
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -305,18 +311,18 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
                  4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
   if (v4) {
     const int lanes = a.hd / 4;
-    if (lanes <= 4) attention_decode_v4_kernel<4><<<blocks, warps * 32, smem, s>>>(a);
-    else if (lanes <= 8) attention_decode_v4_kernel<8><<<blocks, warps * 32, smem, s>>>(a);
-    else if (lanes <= 16) attention_decode_v4_kernel<16><<<blocks, warps * 32, smem, s>>>(a);
-    else attention_decode_v4_kernel<32><<<blocks, warps * 32, smem, s>>>(a);
+    if (lanes <= 4) SCV_CUDA(launch_k(attention_decode_v4_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a));
+    else if (lanes <= 8) SCV_CUDA(launch_k(attention_decode_v4_kernel<8>, dim3(blocks), dim3(warps * 32), smem, s, a));
+    else if (lanes <= 16) SCV_CUDA(launch_k(attention_decode_v4_kernel<16>, dim3(blocks), dim3(warps * 32), smem, s, a));
+    else SCV_CUDA(launch_k(attention_decode_v4_kernel<32>, dim3(blocks), dim3(warps * 32), smem, s, a));
     SCV_LAUNCH_CHECK();
     return 0;
   }
   switch (epl) {
-    case 1: attention_decode_kernel<1><<<blocks, warps * 32, smem, s>>>(a); break;
-    case 2: attention_decode_kernel<2><<<blocks, warps * 32, smem, s>>>(a); break;
-    case 3: attention_decode_kernel<3><<<blocks, warps * 32, smem, s>>>(a); break;
-    default: attention_decode_kernel<4><<<blocks, warps * 32, smem, s>>>(a); break;
+    case 1: SCV_CUDA(launch_k(attention_decode_kernel<1>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
+    case 2: SCV_CUDA(launch_k(attention_decode_kernel<2>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
+    case 3: SCV_CUDA(launch_k(attention_decode_kernel<3>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
+    default: SCV_CUDA(launch_k(attention_decode_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
   }
   SCV_LAUNCH_CHECK();
   return 0;
@@ -431,7 +437,9 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
   extern __shared__ float sl[];
   __shared__ float redv[kSamplerThreads / 32];
   __shared__ int redi[kSamplerThreads / 32];
+  pdl_wait();
   if (a.st->done) return;
+  pdl_launch_dependents();
   const int b = blockIdx.x, step = a.st->step;
   const int bad = stage_logits(a, b, step, sl);
   const int row_bad = __syncthreads_or(bad & 1);
@@ -452,7 +460,9 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
   __shared__ int redi[kSamplerThreads / 32];
   __shared__ float scan[kSamplerThreads];
   __shared__ int pick;
+  pdl_wait();
   if (a.st->done) return;
+  pdl_launch_dependents();
   const int b = blockIdx.x, step = a.st->step, V = a.V, tid = threadIdx.x;
   const int bad = stage_logits(a, b, step, sl);
   const int row_real_bad = __syncthreads_or(bad & 2);
@@ -645,16 +655,17 @@ int launch_sampler(const SamplerArgs& a_in, int which, cudaStream_t s) {
   }
   SCV_REQUIRE(smem <= 200 * 1024, "sampler: vocabulary of %d tokens does not fit in shared memory", a.V);
   if (which == 1) {
-    sampler_phase1_kernel<<<a.B, kSamplerThreads, smem, s>>>(a, two_phase ? 0 : 1);
+    SCV_CUDA(launch_k(sampler_phase1_kernel, dim3(a.B), dim3(kSamplerThreads), smem, s, a, two_phase ? 0 : 1));
     SCV_LAUNCH_CHECK();
   } else if (two_phase) {
-    sampler_phase2_kernel<<<a.B, kSamplerThreads, smem, s>>>(a);
+    SCV_CUDA(launch_k(sampler_phase2_kernel, dim3(a.B), dim3(kSamplerThreads), smem, s, a));
     SCV_LAUNCH_CHECK();
   }
   return 0;
 }
 
 __global__ void step_end_kernel(StepState* st, int max_steps) {
+  pdl_wait();
   if (st->done) return;
   const int s = st->step + 1;
   st->step = s;
@@ -666,7 +677,7 @@ __global__ void step_end_kernel(StepState* st, int max_steps) {
 }
 
 int launch_step_end(StepState* st, int max_steps, cudaStream_t s) {
-  step_end_kernel<<<1, 1, 0, s>>>(st, max_steps);
+  SCV_CUDA(launch_k(step_end_kernel, dim3(1), dim3(1), 0, s, st, max_steps));
   SCV_LAUNCH_CHECK();
   return 0;
 }

@@ -292,7 +292,7 @@ int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const fl
 // fills UMMA tiles and feature dims that are whole 64-wide k-blocks; smaller shapes use the CUDA-core kernels.
 static bool use_tensor_cores(const scv_decoder_config& c, int B) {
   static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
-  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 64; }();
+  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 1; }();
   return forced != 1 && B >= min_rows && c.d_model % 64 == 0 && c.dim_feedforward % 64 == 0 && (c.d_model / c.nhead) % 8 == 0 &&
          c.vocab_size % 4 == 0 && c.d_model <= 1024;
 }
@@ -488,6 +488,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const int steps_max = max_len - 1;
   SCV_REQUIRE(steps_max >= 1, "generate: max_len %d leaves no step to run", A->max_len);
   const int B = A->batch, M = A->n_memory, d = c.d_model;
+  set_pdl_for_call(B < 1024);
   SCV_TRY(ensure_workspace(D, B, M));
   StepState* st = D->state.as<StepState>();
   SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s));

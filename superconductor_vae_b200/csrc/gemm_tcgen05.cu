@@ -114,7 +114,6 @@ struct TcArgs {
 
 template <bool A_SPLIT, bool OUT_SPLIT, int STAGES, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
-  if (a.done_flag != nullptr && *a.done_flag != 0) return;
   constexpr int STAGE_BYTES = stage_bytes(BN);
   constexpr uint32_t TMEM_COLS = BN;
   constexpr uint32_t W_BYTES = BN * 128;
@@ -151,10 +150,17 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above (barrier init, TMEM allocation) touched no global memory and overlapped the previous kernel's
+  // tail; from here on this kernel reads what its predecessors wrote.
+  pdl_wait();
+  const bool skip = a.done_flag != nullptr && *a.done_flag != 0;     // every row finished: nothing left to compute
+  pdl_launch_dependents();
   // weight tiles are packed per 128 output rows: a 256-wide CTA tile is two of them (same k-block, KB tiles apart)
   const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * (BN / 128) * KB * (TILE_BYTES / 2);
 
-  if (warp < 8) {
+  if (skip) {
+    // fall through to the teardown
+  } else if (warp < 8) {
     // ===================== producers =====================
     if constexpr (A_SPLIT) {
       if (tid == 0) {
@@ -346,7 +352,7 @@ int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaSt
 }
 
 bool tc_shape_ok(const LinearArgs& a) {
-  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 64; }();
+  static const int min_rows = [] { const char* e = getenv("SCV_TC_MIN_ROWS"); return e ? atoi(e) : 1; }();
   if (a.wt == nullptr || a.M < min_rows || a.K < 64 || a.N % 4 != 0) return false;
   if (a.a_split == nullptr) {
     if (a.x == nullptr || a.K % 4 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15u) != 0) return false;
@@ -391,7 +397,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // measured on B200 (profiles/README.md, r01e): the 256-wide tile is slower at these K (8-32 k-blocks, one CTA per
   // SM so no epilogue overlap), so it stays opt-in
   const bool wide = force_bn == 256 && n128 % 2 == 0;
-#define SCV_LAUNCH(A, O, S, N) gemm_tcgen05_kernel<A, O, S, N><<<grid, NUM_THREADS, smem_bytes(S, N), s>>>(t)
+#define SCV_LAUNCH(A, O, S, N) SCV_CUDA(launch_k(gemm_tcgen05_kernel<A, O, S, N>, grid, dim3(NUM_THREADS), (size_t)smem_bytes(S, N), s, t))
 #define SCV_LAUNCH_MODE(S, N)                                                            \
   do {                                                                                   \
     if (as && os) SCV_LAUNCH(true, true, S, N); else if (as) SCV_LAUNCH(true, false, S, N); \

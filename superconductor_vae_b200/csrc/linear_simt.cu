@@ -13,7 +13,9 @@ namespace scv {
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 linear_simt_kernel(LinearArgs a, int x_vec_ok) {
+  pdl_wait();
   if (a.done_flag != nullptr && *a.done_flag != 0) return;
+  pdl_launch_dependents();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TMH = TM / 2, TNH = TN / 2;
   constexpr int PADM = BM + 4, PADN = BN + 4;
@@ -156,10 +158,10 @@ int launch_linear_simt(const LinearArgs& a, cudaStream_t s) {
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
   if (a.M > 48) {
     dim3 grid(ceil_div(a.N, 128), ceil_div(a.M, 128));
-    linear_simt_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, s>>>(a, vec_ok);
+    SCV_CUDA(launch_k(linear_simt_kernel<128, 128, 16, 8, 8>, grid, dim3(256), 0, s, a, vec_ok));
   } else {
     dim3 grid(ceil_div(a.N, 32), ceil_div(a.M, 32));
-    linear_simt_kernel<32, 32, 16, 2, 2><<<grid, 256, 0, s>>>(a, vec_ok);
+    SCV_CUDA(launch_k(linear_simt_kernel<32, 32, 16, 2, 2>, grid, dim3(256), 0, s, a, vec_ok));
   }
   SCV_LAUNCH_CHECK();
   return 0;

@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* y, int ldy, int M, int N, int act,
                  const int* done_flag) {
+  pdl_wait();
   if (done_flag != nullptr && *done_flag != 0) return;
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                        const float* __restrict__ beta, uint8_t* __restrict__ out, int M, int N, int normalize,
                        const int* done_flag) {
+  pdl_wait();
   if (done_flag != nullptr && *done_flag != 0) return;
+  pdl_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -135,8 +139,8 @@ int launch_layernorm_split(const float* x, int ldx, const float* gamma, const fl
               N, kLnMaxChunks * 256);
   SCV_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "layernorm_split: unaligned input");
   ProfScope prof(PC_LAYERNORM, s, 8.0 * M * N, 8.0 * M * N);
-  layernorm_split_kernel<<<ceil_div(M, 8), 256, 0, s>>>(x, ldx, gamma, beta, static_cast<uint8_t*>(out_split), M, N,
-                                                         normalize, done_flag);
+  SCV_CUDA(launch_k(layernorm_split_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, s, x, ldx, gamma, beta,
+                    static_cast<uint8_t*>(out_split), M, N, normalize, done_flag));
   SCV_LAUNCH_CHECK();
   return 0;
 }
@@ -145,7 +149,7 @@ int launch_layernorm(const float* x, int ldx, const float* gamma, const float* b
                      int N, int act, const int* done_flag, cudaStream_t s) {
   SCV_REQUIRE(M > 0 && N > 0, "layernorm: empty shape");
   ProfScope prof(PC_LAYERNORM, s, 8.0 * M * N, 8.0 * M * N);
-  layernorm_kernel<<<ceil_div(M, 8), 256, 0, s>>>(x, ldx, gamma, beta, y, ldy, M, N, act, done_flag);
+  SCV_CUDA(launch_k(layernorm_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, s, x, ldx, gamma, beta, y, ldy, M, N, act, done_flag));
   SCV_LAUNCH_CHECK();
   return 0;
 }
