@@ -26,7 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/scvae_nccl_debug.%h.%p")   # NCCL prints its version banner to stdout otherwise; stdout must stay one JSON line
 
 METRIC = "formulas/sec (KV-cache decode, bf16)"
 UNIT = "formulas/s"

@@ -13,7 +13,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/scvae_nccl_debug.%h.%p")   # NCCL prints its version banner to stdout otherwise; stdout must stay one JSON line
 
 import torch
 import torch.distributed as dist
