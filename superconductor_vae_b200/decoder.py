@@ -29,6 +29,18 @@ N_TOKEN_TYPES = 5
 HEADS_ORDER = ("tc_pred", "sc_pred", "hp_pred", "tc_class_logits", "competence", "element_count_pred")
 
 
+def _legacy_vocab() -> List[str]:
+    """id -> string of the reference's pre-V13 character vocabulary (autoregressive_decoder.py:52-97):
+    20 special tokens, the 118 element symbols, digits 0-9."""
+    from .tokenizer import ELEMENTS
+    special = ["<PAD>", "<START>", "<END>", ".", "(", ")", "[", "]", "{", "}", "·", "•", "+", "-", "_", "^", "/",
+               "'", '"', "*"]
+    return special + ELEMENTS[1:] + [str(i) for i in range(10)]
+
+
+_LEGACY_VOCAB = _legacy_vocab()
+
+
 class _PositionalEncoding(nn.Module):
     """Holds the sinusoidal ``pe`` buffer [1, max_len, d_model] (reference :392-413)."""
 
@@ -337,6 +349,28 @@ class EnhancedTransformerDecoder(nn.Module):
         end_pos = torch.where(is_end.any(dim=1), end_pos, torch.full_like(end_pos, Lq))
         mask = (torch.arange(Lq, device=tokens.device).unsqueeze(0) <= end_pos.unsqueeze(1)).float()
         return tokens, lp, ent, mask
+
+    def generate_formulas_fast(self, z, encoder_skip=None, stoich_pred=None, temperature: float = 1.0,
+                               max_len: Optional[int] = None, cached_memory: Optional[torch.Tensor] = None,
+                               tokenizer=None) -> List[str]:
+        """Reference :1998-2032: KV-cache generation, then ids -> strings.  Like the reference it uses the legacy
+        148-token character vocabulary (20 specials, 118 elements, digits 0-9; ids outside it map to '') unless a
+        `FractionAwareTokenizer` is passed, in which case its `decode` is used."""
+        tokens, _, _ = self.generate_with_kv_cache(z=z, encoder_skip=encoder_skip, stoich_pred=stoich_pred,
+                                                   temperature=temperature, max_len=max_len, cached_memory=cached_memory)
+        rows = tokens.cpu().tolist()
+        if tokenizer is not None:
+            return [tokenizer.decode(r) for r in rows]
+        out = []
+        for r in rows:
+            parts = []
+            for i in r:
+                if i == END_IDX:
+                    break
+                if i not in (PAD_IDX, START_IDX):
+                    parts.append(_LEGACY_VOCAB[i] if 0 <= i < len(_LEGACY_VOCAB) else "")
+            out.append("".join(parts))
+        return out
 
     def debug_tap(self, what: int) -> torch.Tensor:
         """Engine-internal fp32 state of the last executed step of the last engine call (tests only):

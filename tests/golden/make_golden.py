@@ -192,6 +192,9 @@ def tokenizer_case():
            "mask_row_sums": m.sum(dim=1), "ids": ids, "decoded": [tok.decode(i) for i in ids],
            "names": {i: tok.get_token_name(i) for i in (0, 1, 2, 3, 4, 5, 122, 123, 142, 143, 4459, 4460, 4461, 4751)},
            "encoded_YBCO": tok.encode("YBa2Cu3O7"), "meta": META}
+    from superconductor.models import autoregressive_decoder as AD      # legacy 148-token vocabulary (generate_formulas_fast)
+    out["legacy_vocab"] = list(AD.VOCAB)
+    out["legacy_decoded"] = AD.indices_to_formula(torch.tensor([1, 58, 141, 48, 140, 2, 5]))
     torch.save(out, os.path.join(HERE, "tokenizer.pt"))
     print("tokenizer", out["vocab_size"], out["mask_row_sums"].tolist(), out["decoded"], out["encoded_YBCO"][:12])
     return m

@@ -167,3 +167,26 @@ def test_gather_rows_world_size_2():
     assert (out[:lo1, 3:] == 0).all()                  # shorter shard padded to the global L
     assert out[lo1:].tolist() == [[r * 100 + c for c in range(5)] for r in range(lo1, 11)]
     assert torch.equal(lp, out.float() * 0.5)
+
+
+def test_legacy_vocab_of_generate_formulas_fast(golden_dir):
+    from superconductor_vae_b200.decoder import _LEGACY_VOCAB
+    g = torch.load(os.path.join(golden_dir, "tokenizer.pt"), weights_only=False)
+    assert _LEGACY_VOCAB == g["legacy_vocab"] and len(_LEGACY_VOCAB) == 148
+    ids = [1, 58, 141, 48, 140, 2, 5]
+    assert "".join(_LEGACY_VOCAB[i] for i in ids[1:5]) == g["legacy_decoded"]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-rows", "2", "--max-len", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
