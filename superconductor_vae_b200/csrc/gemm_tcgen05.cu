@@ -222,11 +222,28 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
     // TMEM -> registers (thread = one row, 32 columns) -> shared staging (the pipeline stages are free once the
     // accumulator barrier fires) -> row-contiguous global accesses: each warp instruction touches whole 128-byte
     // (fp32 output / residual) or 64-byte (SplitTile) row segments instead of 32 scattered 16-byte pieces.
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(base_ptr) + warp * (32 * STG_PITCH);
-#pragma unroll 1
+    // The residual is an input of the kernel: fetch this thread's share while the tensor core is still working
+    // (it may alias the output, x += f(x), so the compiler could not hoist these loads above earlier stores).
+    constexpr int NCC = BN / 64;
+    float4 rv[OUT_SPLIT ? 1 : NCC][OUT_SPLIT ? 1 : 8];
+    if constexpr (!OUT_SPLIT) {
+#pragma unroll
+      for (int cc = 0; cc < NCC; ++cc) {
+        const int gn = n0 + chalf * (BN / 2) + cc * 32 + 4 * (lane & 7);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int gm = m0 + quad * 32 + it * 4 + (lane >> 3);
+          rv[cc][it] = (a.residual != nullptr && gm < a.M && gn < a.N)
+                           ? *reinterpret_cast<const float4*>(a.residual + (size_t)gm * a.ldr + gn)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll
     for (int cc = 0; cc < BN / 64; ++cc) {
       const int c0 = chalf * (BN / 2) + cc * 32;
       uint32_t r[32];
@@ -248,12 +265,8 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
             const int row = it * 4 + rr, gm = m0 + quad * 32 + row;
             if (gm < a.M) {
               const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 4 * c4);
-              float o0 = apply_act(v.x + bv.x, a.act), o1 = apply_act(v.y + bv.y, a.act);
-              float o2 = apply_act(v.z + bv.z, a.act), o3 = apply_act(v.w + bv.w, a.act);
-              if (a.residual != nullptr) {
-                const float4 rv = *reinterpret_cast<const float4*>(a.residual + (size_t)gm * a.ldr + gn);
-                o0 += rv.x; o1 += rv.y; o2 += rv.z; o3 += rv.w;
-              }
+              const float o0 = apply_act(v.x + bv.x, a.act) + rv[cc][it].x, o1 = apply_act(v.y + bv.y, a.act) + rv[cc][it].y;
+              const float o2 = apply_act(v.z + bv.z, a.act) + rv[cc][it].z, o3 = apply_act(v.w + bv.w, a.act) + rv[cc][it].w;
               *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
             }
           }
