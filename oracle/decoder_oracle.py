@@ -198,9 +198,9 @@ def generate_with_kv_cache(
     (teacher-forced replay: the forced token is emitted but log-prob / entropy are computed as
     usual), ``trace`` (dict that receives per-step logits etc.), ``kv_round``.
     """
-    if site_dup_threshold > 0:
-        raise NotImplementedError("site_dup gating (SURVEY H5) is outside the oracle")
     s = infer_shape(sd)
+    seen = torch.zeros(z.shape[0] if z is not None else cached_memory.shape[0], s["vocab_size"], dtype=torch.bool) \
+        if site_dup_threshold > 0 else None
     B = z.shape[0] if z is not None else cached_memory.shape[0]
     V = s["vocab_size"]
     max_len = max_len or s["max_len"]
@@ -225,6 +225,13 @@ def generate_with_kv_cache(
             logits = logits.masked_fill(~type_masks[pred_type], float("-inf"))
             if trace is not None:
                 trace.setdefault("type_logits", []).append(tl.clone())
+        if site_dup_threshold > 0 and position > 0:          # (:1424-1435) soft-suppress previously seen "elements"
+            dl = _lin(sd, "site_dup_head.2", F.gelu(_lin(sd, "site_dup_head.0", x))).squeeze(1).squeeze(-1)
+            suppress = torch.sigmoid(dl) < site_dup_threshold
+            if trace is not None:
+                trace.setdefault("site_dup_logit", []).append(dl.clone())
+            if suppress.any():
+                logits = logits.masked_fill(suppress.unsqueeze(1) & seen, -30.0)
         if stop_boost > 0:
             sl = stop_logit(sd, x).squeeze(1).squeeze(-1)
             sp = torch.sigmoid(sl)
@@ -277,6 +284,11 @@ def generate_with_kv_cache(
         toks.append(nxt)
         if return_log_probs:
             lps.append(lp)
+        if seen is not None:
+            # (:1525-1539) the id range 20..137 is the element range of the *pre-V13* vocabulary; kept as is
+            tok_flat = nxt.squeeze(-1)
+            is_elem = (tok_flat >= 20) & (tok_flat <= 137) & ~finished
+            seen[torch.arange(seen.shape[0])[is_elem], tok_flat[is_elem]] = True
         finished = finished | (nxt.squeeze(-1) == END_IDX)
         cur = nxt
         if stop_when_all_finished and bool(finished.all()):

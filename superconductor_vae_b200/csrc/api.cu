@@ -153,6 +153,11 @@ int WeightStore::load(const char* name, const float* src, int64_t numel, cudaStr
   return 0;
 }
 
+bool WeightStore::loaded(const std::string& name) const {
+  auto it = slots_.find(name);
+  return it != slots_.end() && it->second.loaded;
+}
+
 int WeightStore::missing(std::string* first) const {
   int n = 0;
   for (const auto& name : order_) {

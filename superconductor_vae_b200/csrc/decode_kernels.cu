@@ -404,12 +404,14 @@ __device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
   }
   const float length_boost =
       (stop_on && step > 10) ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
+  const bool dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(a.dup_logits[b]) < a.dup_threshold;
   const float* lg = a.logits + (size_t)b * a.ldl;
   const uint8_t* mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
   int bad = 0;
   for (int v = threadIdx.x; v < a.V; v += kSamplerThreads) {
     float l = lg[v];
     if (mk != nullptr && mk[v] == 0) l = -INFINITY;
+    if (dup_suppress && a.seen[(size_t)b * a.V + v] != 0) l = -30.0f;       // masked_fill(-30.0), even over a -inf
     if (v == kEndIdx && stop_on) l = l + a.stop_boost * sp;
     if (force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
     if (v == kEndIdx && stop_on && step > 10) l = l + length_boost;
@@ -426,6 +428,8 @@ __device__ void commit_token(const SamplerArgs& a, int b, int step, int token, f
   a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
   if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
   a.cur_tokens[b] = token;
+  // ids 20..137 are the element range of the pre-V13 vocabulary; the reference still uses it
+  if (a.seen != nullptr && token >= 20 && token <= 137 && a.finished[b] == 0) a.seen[(size_t)b * a.V + token] = 1;
   if (token == kEndIdx && a.finished[b] == 0) {
     a.finished[b] = 1;
     atomicSub(&a.st->n_unfinished, 1);

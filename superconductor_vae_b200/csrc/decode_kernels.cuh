@@ -56,6 +56,8 @@ struct SamplerArgs {
   float temperature = 1.f; int top_k = 0; float top_p = 1.f;
   int sort_n = 0;                                        // set by the launcher: padded vocabulary for top-k/top-p
   float stop_boost = 0.f, hard_stop = 0.f;
+  // site-duplication gating (reference :1424-1435, :1525-1539): seen[b, v] marks "element" ids already emitted
+  const float* dup_logits = nullptr; float dup_threshold = 0.f; unsigned char* seen = nullptr;
   int want_logprobs = 0, want_entropy = 0; unsigned flags = 0;
   int row_base = 0;                                      // first row of this sub-batch (Philox counter)
   long long* out_tokens = nullptr; float* out_logprobs = nullptr; float* out_entropy = nullptr; int out_ld = 0;

@@ -45,12 +45,12 @@ constexpr int kMaxSub = 4;
 struct GraphKey {
   int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced;
   unsigned flags;
-  float temperature, top_p, stop_boost, hard_stop;
+  float temperature, top_p, stop_boost, hard_stop, site_dup;
   bool operator==(const GraphKey& o) const {
     return B == o.B && M == o.M && steps_max == o.steps_max && n_sub == o.n_sub && top_k == o.top_k &&
            has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced &&
            flags == o.flags && temperature == o.temperature && top_p == o.top_p && stop_boost == o.stop_boost &&
-           hard_stop == o.hard_stop;
+           hard_stop == o.hard_stop && site_dup == o.site_dup;
   }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; };
@@ -73,6 +73,7 @@ struct scv_decoder {
   // workspaces (engine-owned, grown on demand)
   DevBuf x, xn, qkv, attn, q2, ff, h1, h2, t3, logits, tlog, slog, ckv, kvpool, cur, fin, ptab, state, mtmp;
   DevBuf xn_s, attn_s, ff_s, h2_s;   // SplitTile (bf16 hi/lo) activations feeding the tcgen05 projections
+  DevBuf seen, dlog;                 // site-dup gating: [B, V] seen-element bitmap, [B] site_dup_head logit
   DevBuf o_tok, o_lp, o_ent, masks_buf, forced_buf;   // engine-owned I/O so that a captured step never bakes caller pointers
   std::vector<GraphEntry> graphs;    // one instantiated CUDA graph of a decode step per call configuration
   size_t ws_signature = 0;
@@ -104,7 +105,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf})
+                      &forced_buf, &seen, &dlog})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -174,7 +175,7 @@ static int dec_register(scv_decoder* D) {
   SCV_TRY(W.add_linear("output_proj.4", c.vocab_size, d, &D->out_b, true, true));
   SCV_TRY(W.add_linear("stop_head.0", d / 4, d, &D->stop_a, true, true));
   SCV_TRY(W.add_linear("stop_head.2", 1, d / 4, &D->stop_b));
-  SCV_TRY(W.add_linear("site_dup_head.0", d / 4, d, &D->dup_a));
+  SCV_TRY(W.add_linear("site_dup_head.0", d / 4, d, &D->dup_a, true, true));
   SCV_TRY(W.add_linear("site_dup_head.2", 1, d / 4, &D->dup_b));
   for (const char* n : {"site_dup_head.0.weight", "site_dup_head.0.bias", "site_dup_head.2.weight", "site_dup_head.2.bias"})
     W.mark_optional(n);   // older checkpoints lack it; only used when site_dup_threshold > 0
@@ -373,6 +374,10 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   sp.type_masks = A->type_masks; sp.B = B; sp.V = c.vocab_size; sp.max_len = steps_max + 1;
   sp.temperature = A->temperature; sp.top_k = A->top_k; sp.top_p = A->top_p;
   sp.stop_boost = A->stop_boost; sp.hard_stop = A->hard_stop_threshold;
+  if (A->site_dup_threshold > 0.f) {
+    sp.dup_logits = D->dlog.as<float>() + r0; sp.dup_threshold = A->site_dup_threshold;
+    sp.seen = D->seen.as<unsigned char>() + (size_t)r0 * c.vocab_size;
+  }
   sp.want_logprobs = A->want_log_probs; sp.want_entropy = A->want_entropy; sp.flags = A->flags;
   sp.row_base = r0;
   sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens) + (size_t)r0 * steps_max;
@@ -464,6 +469,10 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(lin_args(x, d, D->stop_a, t3, d / 4, B, ACT_GELU, done), 0, s));
     SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, slog, 1, B, ACT_NONE, done), 0, s));
   }
+  if (A->site_dup_threshold > 0.f) {      // site_dup_head (:1427); position 0 never gates but the launch list stays fixed
+    SCV_TRY(launch_linear(lin_args(x, d, D->dup_a, t3, d / 4, B, ACT_GELU, done), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->dup_b, D->dlog.as<float>() + r0, 1, B, ACT_NONE, done), 0, s));
+  }
   return launch_sampler(sp, 1, s);
 }
 
@@ -472,7 +481,8 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const scv_generate_args* A_user = A;
   SCV_REQUIRE(A->batch > 0 && A->memory && A->out_tokens && A->out_steps, "generate: bad arguments");
   SCV_REQUIRE(A->n_memory > 0, "generate: n_memory must be positive");
-  SCV_REQUIRE(!(A->site_dup_threshold > 0.f), "generate: site_dup gating is not implemented in this build");
+  SCV_REQUIRE(!(A->site_dup_threshold > 0.f) || (D->ws.loaded("site_dup_head.0.weight") && D->ws.loaded("site_dup_head.2.weight")),
+              "generate: site_dup_threshold > 0 needs the site_dup_head weights, which this checkpoint did not provide");
   SCV_REQUIRE(!A->want_log_probs || A->out_log_probs, "generate: out_log_probs is NULL");
   SCV_REQUIRE(!A->want_entropy || A->out_entropy, "generate: out_entropy is NULL");
   SCV_REQUIRE(scv_decoder_missing_weights(D) == 0, "generate: weights missing");
@@ -504,6 +514,11 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   if (A->forced_tokens != nullptr) {
     SCV_CUDA(cudaMemcpyAsync(D->forced_buf.p, A->forced_tokens, io * sizeof(long long), cudaMemcpyDeviceToDevice, s));
     G.forced_tokens = D->forced_buf.as<int64_t>();
+  }
+  if (A->site_dup_threshold > 0.f) {
+    SCV_TRY(D->seen.ensure((size_t)B * c.vocab_size));
+    SCV_TRY(D->dlog.ensure((size_t)B * sizeof(float)));
+    SCV_CUDA(cudaMemsetAsync(D->seen.p, 0, (size_t)B * c.vocab_size, s));
   }
   SCV_CUDA(cudaMemsetAsync(D->o_tok.p, 0, io * sizeof(long long), s));
   if (A->want_log_probs) SCV_CUDA(cudaMemsetAsync(D->o_lp.p, 0, io * sizeof(float), s));
@@ -570,7 +585,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const bool use_graph = graph_env != 0 && !prof_enabled() && !sync_each && steps_max >= 3;
   const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
                      A->forced_tokens != nullptr, A->flags, A->temperature, A->top_p, A->stop_boost,
-                     A->hard_stop_threshold};
+                     A->hard_stop_threshold, A->site_dup_threshold};
   cudaGraphExec_t exec = nullptr;
   if (use_graph)
     for (auto& g : D->graphs) if (g.key == key) exec = g.exec;

@@ -34,6 +34,7 @@ class WeightStore {
   void mark_optional(const std::string& name);
   int load(const char* name, const float* src, int64_t numel, cudaStream_t s);
   int missing(std::string* first) const;
+  bool loaded(const std::string& name) const;
 
  private:
   struct TiledView { __nv_bfloat16* dst; int row0, rows; };

@@ -274,8 +274,6 @@ class EnhancedTransformerDecoder(nn.Module):
                                *, _forced_tokens: Optional[torch.Tensor] = None, _seed: Optional[int] = None
                                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
         self.eval()                                                         # side effect kept (:1368)
-        if site_dup_threshold and site_dup_threshold > 0:
-            raise NotImplementedError("site_dup gating (reference :1426-1435, SURVEY H5) is not built yet")
         max_len = max_len or self.max_len
         pe_max = self.pos_encoding.pe.shape[1]
         if max_len > pe_max:
@@ -316,7 +314,7 @@ class EnhancedTransformerDecoder(nn.Module):
                         batch=hi - lo, n_memory=M, max_len=max_len, memory=memory[lo:hi].data_ptr(),
                         temperature=float(temperature), top_k=int(top_k) if top_k else 0,
                         top_p=float(top_p) if top_p is not None else 1.0, stop_boost=float(stop_boost),
-                        hard_stop_threshold=float(hard_stop_threshold), site_dup_threshold=0.0,
+                        hard_stop_threshold=float(hard_stop_threshold), site_dup_threshold=float(site_dup_threshold or 0.0),
                         type_masks=masks_u8.data_ptr() if masks_u8 is not None else None,
                         want_log_probs=int(return_log_probs), want_entropy=int(return_entropy), flags=flags,
                         seed=_seed, offset=lo,

@@ -114,6 +114,13 @@ def decoder_cases(name, shape, B, masks, seed_in=1234, steps_logits=(0, 1, 5), r
                                              type_masks=masks)
     out["sample_masked_tokens"], out["sample_masked_logprobs"] = i16(t), lp
     out["sample_masked_entropy"], out["sample_masked_mask"] = en, mk
+    # (h) site-duplication gating (:1424-1435, :1525-1539)
+    t, _, _ = dec.generate_with_kv_cache(z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                         heads_pred=heads, site_dup_threshold=0.6)
+    out["sitedup_plain_tokens"] = i16(t)
+    t, _, _ = dec.generate_with_kv_cache(z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                         heads_pred=heads, site_dup_threshold=0.99, type_masks=masks, stop_boost=10.0)
+    out["sitedup_masked_tokens"] = i16(t)
     if extra:
         extra(dec, out, z, stoich, heads)
     hook.remove()

@@ -190,6 +190,22 @@ def test_greedy_tokens_bit_exact_vs_reference_goldens(golden_dir, name):
     assert dec.training is False
 
 
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4"])
+def test_site_dup_gating_bit_exact_vs_reference_goldens(golden_dir, name):
+    """site_dup_threshold > 0 (reference :1424-1435, :1525-1539; SURVEY H5: inert by default, old-vocabulary id range)."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    zc, sc, hc, mc = _cuda(z), _cuda(stoich), _cuda(heads), _cuda(masks)
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len, heads_pred=hc,
+                                         site_dup_threshold=0.6)
+    assert torch.equal(t.cpu().to(torch.int16), g["sitedup_plain_tokens"])
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len, heads_pred=hc,
+                                         site_dup_threshold=0.99, type_masks=mc, stop_boost=10.0)
+    assert torch.equal(t.cpu().to(torch.int16), g["sitedup_masked_tokens"])
+    # and the ungated call right after it is unaffected by the gate's state
+    t, _, _ = dec.generate_with_kv_cache(zc, stoich_pred=sc, temperature=0.001, max_len=shape.max_len, heads_pred=hc)
+    assert torch.equal(t.cpu().to(torch.int16), g["greedy_plain_tokens"])
+
+
 @pytest.mark.parametrize("name", ["tiny", "c512_b32"])
 def test_last_step_logits_within_tolerance(golden_dir, name):
     """Raw logits / hidden state of the final executed step vs the fp32 oracle: |diff| <= 2e-4 abs."""

@@ -75,6 +75,19 @@ def test_decoder_oracle_matches_reference(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["tiny", "c512b_b4"])
+def test_decoder_oracle_site_dup_gating_matches_reference(golden_dir, name):
+    """site_dup_threshold > 0 (reference :1424-1435, :1525-1539, old-vocabulary id range kept)."""
+    shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, name)
+    t, _, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                        heads_pred=heads, site_dup_threshold=0.6)
+    assert torch.equal(t.to(torch.int16), g["sitedup_plain_tokens"])
+    assert not torch.equal(g["sitedup_plain_tokens"], g["greedy_plain_tokens"])      # the gate really fires
+    t, _, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, temperature=0.001, max_len=shape.max_len,
+                                        heads_pred=heads, site_dup_threshold=0.99, type_masks=masks, stop_boost=10.0)
+    assert torch.equal(t.to(torch.int16), g["sitedup_masked_tokens"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "c512b_b4"])
 def test_decoder_oracle_sampling_matches_reference_rng(golden_dir, name):
     shape, g, sd, z, stoich, heads, masks = _setup(golden_dir, name)
     nh = shape.nhead
