@@ -112,7 +112,7 @@ struct TcArgs {
   const int* done_flag;
 };
 
-template <bool A_SPLIT, bool OUT_SPLIT, int STAGES, int BN>
+template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
   constexpr int STAGE_BYTES = stage_bytes(BN);
   constexpr uint32_t TMEM_COLS = BN;
@@ -227,23 +227,22 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
     // The residual is an input of the kernel: fetch this thread's share while the tensor core is still working
     // (it may alias the output, x += f(x), so the compiler could not hoist these loads above earlier stores).
     constexpr int NCC = BN / 64;
-    float4 rv[OUT_SPLIT ? 1 : NCC][OUT_SPLIT ? 1 : 8];
-    if constexpr (!OUT_SPLIT) {
+    float4 rv[HAS_RES ? NCC : 1][HAS_RES ? 8 : 1];
+    if constexpr (HAS_RES) {
 #pragma unroll
       for (int cc = 0; cc < NCC; ++cc) {
         const int gn = n0 + chalf * (BN / 2) + cc * 32 + 4 * (lane & 7);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int gm = m0 + quad * 32 + it * 4 + (lane >> 3);
-          rv[cc][it] = (a.residual != nullptr && gm < a.M && gn < a.N)
-                           ? *reinterpret_cast<const float4*>(a.residual + (size_t)gm * a.ldr + gn)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[cc][it] = (gm < a.M && gn < a.N) ? *reinterpret_cast<const float4*>(a.residual + (size_t)gm * a.ldr + gn)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-#pragma unroll
+#pragma unroll(HAS_RES ? BN / 64 : 1)
     for (int cc = 0; cc < BN / 64; ++cc) {
       const int c0 = chalf * (BN / 2) + cc * 32;
       uint32_t r[32];
@@ -265,8 +264,9 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
             const int row = it * 4 + rr, gm = m0 + quad * 32 + row;
             if (gm < a.M) {
               const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 4 * c4);
-              const float o0 = apply_act(v.x + bv.x, a.act) + rv[cc][it].x, o1 = apply_act(v.y + bv.y, a.act) + rv[cc][it].y;
-              const float o2 = apply_act(v.z + bv.z, a.act) + rv[cc][it].z, o3 = apply_act(v.w + bv.w, a.act) + rv[cc][it].w;
+              float o0 = apply_act(v.x + bv.x, a.act), o1 = apply_act(v.y + bv.y, a.act);
+              float o2 = apply_act(v.z + bv.z, a.act), o3 = apply_act(v.w + bv.w, a.act);
+              if constexpr (HAS_RES) { o0 += rv[cc][it].x; o1 += rv[cc][it].y; o2 += rv[cc][it].z; o3 += rv[cc][it].w; }
               *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
             }
           }
@@ -384,10 +384,11 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
   static bool attr_set = false;
   if (!attr_set) {
-#define SCV_SET_SMEM(A, O, S, N) \
-  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, N)))
-#define SCV_SET_ALL(S, N) \
-  SCV_SET_SMEM(false, false, S, N); SCV_SET_SMEM(false, true, S, N); SCV_SET_SMEM(true, false, S, N); SCV_SET_SMEM(true, true, S, N)
+#define SCV_SET_SMEM(A, O, R, S, N) \
+  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, R, S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, N)))
+#define SCV_SET_ALL(S, N)                                                                             \
+  SCV_SET_SMEM(false, false, false, S, N); SCV_SET_SMEM(false, true, false, S, N); SCV_SET_SMEM(true, false, false, S, N); \
+  SCV_SET_SMEM(true, true, false, S, N); SCV_SET_SMEM(false, false, true, S, N); SCV_SET_SMEM(true, false, true, S, N)
     SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256);
 #undef SCV_SET_ALL
 #undef SCV_SET_SMEM
@@ -401,7 +402,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
-  const bool as = a.a_split != nullptr, os = a.y_split != nullptr;
+  const bool as = a.a_split != nullptr, os = a.y_split != nullptr, res = a.residual != nullptr;
   // Tile choice: 128 x 128 with a deep 4-stage pipeline when the grid is at most one CTA per SM, else two 2-stage
   // CTAs per SM so that one CTA's epilogue overlaps the other's main loop; 128 x 256 (SCV_GEMM_BN=256) halves the
   // A re-reads but runs one CTA per SM.
@@ -410,11 +411,15 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // measured on B200 (profiles/README.md, r01e): the 256-wide tile is slower at these K (8-32 k-blocks, one CTA per
   // SM so no epilogue overlap), so it stays opt-in
   const bool wide = force_bn == 256 && n128 % 2 == 0;
-#define SCV_LAUNCH(A, O, S, N) SCV_CUDA(launch_k(gemm_tcgen05_kernel<A, O, S, N>, grid, dim3(NUM_THREADS), (size_t)smem_bytes(S, N), s, t))
-#define SCV_LAUNCH_MODE(S, N)                                                            \
-  do {                                                                                   \
-    if (as && os) SCV_LAUNCH(true, true, S, N); else if (as) SCV_LAUNCH(true, false, S, N); \
-    else if (os) SCV_LAUNCH(false, true, S, N); else SCV_LAUNCH(false, false, S, N);         \
+#define SCV_LAUNCH(A, O, R, S, N) SCV_CUDA(launch_k(gemm_tcgen05_kernel<A, O, R, S, N>, grid, dim3(NUM_THREADS), (size_t)smem_bytes(S, N), s, t))
+#define SCV_LAUNCH_MODE(S, N)                                                                        \
+  do {                                                                                               \
+    if (as && os) SCV_LAUNCH(true, true, false, S, N);                                               \
+    else if (os) SCV_LAUNCH(false, true, false, S, N);                                               \
+    else if (as && res) SCV_LAUNCH(true, false, true, S, N);                                         \
+    else if (as) SCV_LAUNCH(true, false, false, S, N);                                               \
+    else if (res) SCV_LAUNCH(false, false, true, S, N);                                              \
+    else SCV_LAUNCH(false, false, false, S, N);                                                      \
   } while (0)
   if (wide) {
     dim3 grid(n128 / 2, mt);

@@ -6,6 +6,8 @@
 // only difference from the fp32 oracle is summation order.  The tcgen05 path (gemm_tcgen05.cu) replaces it
 // where the batch makes the projection a dense contraction; this kernel remains for ragged/small shapes
 // (K = 1, 13, 24, 145, 513, 2214 ...) and as the in-library cross-check.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scv {
@@ -149,7 +151,50 @@ linear_simt_kernel(LinearArgs a, int x_vec_ok) {
     }
 }
 
+// Narrow heads (N <= 16: token-type logits, stop / site-dup logit, Tc, competence, family heads ...): one warp per
+// row, the row in registers, one warp reduction per output.  The tiled kernel above would spend a 128 x 128 tile on
+// 1-13 useful columns (ncu r01c: 45 us for the 5 token-type logits of 4096 rows).
+constexpr int kRowWarpMaxK = 1024;
+__global__ void __launch_bounds__(256) linear_rowwarp_kernel(LinearArgs a) {
+  pdl_wait();
+  if (a.done_flag != nullptr && *a.done_flag != 0) return;
+  pdl_launch_dependents();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= a.M) return;
+  float xv[kRowWarpMaxK / 32];
+  const float* xr = a.x + (size_t)row * a.ldx;
+#pragma unroll
+  for (int j = 0; j < kRowWarpMaxK / 32; ++j) {
+    const int k = lane + 32 * j;
+    xv[j] = k < a.K ? xr[k] : 0.f;
+  }
+  for (int n = 0; n < a.N; ++n) {
+    const __nv_bfloat16* wr = a.w + (size_t)n * a.ldw;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowWarpMaxK / 32; ++j) {
+      const int k = lane + 32 * j;
+      if (k < a.K) acc = fmaf(xv[j], __bfloat162float(wr[k]), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc;
+      if (a.bias != nullptr) v += a.bias[n];
+      v = apply_act(v, a.act);
+      if (a.residual != nullptr) v += a.residual[(size_t)row * a.ldr + n];
+      a.y[(size_t)row * a.ldy + n] = v;
+    }
+  }
+}
+
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s) {
+  static const bool rowwarp = [] { const char* e = getenv("SCV_ROWWARP"); return e ? atoi(e) != 0 : true; }();
+  if (rowwarp && a.N <= 16 && a.K <= kRowWarpMaxK && a.M > 0 && a.K > 0) {
+    ProfScope prof(PC_LINEAR, s, 2.0 * a.M * a.N * a.K, 2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N);
+    SCV_CUDA(launch_k(linear_rowwarp_kernel, dim3(ceil_div(a.M, 8)), dim3(256), 0, s, a));
+    SCV_LAUNCH_CHECK();
+    return 0;
+  }
   SCV_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear: empty shape M=%d N=%d K=%d", a.M, a.N, a.K);
   SCV_REQUIRE(a.ldw % 8 == 0 && a.ldw >= a.K, "linear: ldw=%d must be a multiple of 8 and >= K=%d", a.ldw, a.K);
   SCV_REQUIRE((reinterpret_cast<uintptr_t>(a.w) & 15u) == 0, "linear: weight pointer must be 16-byte aligned");
