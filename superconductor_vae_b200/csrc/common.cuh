@@ -168,7 +168,7 @@ size_t tc_packed_elems(int N, int K);
 size_t split_tile_bytes(int M, int K);             // bytes of a SplitTile buffer for an [M, K] activation
 // LayerNorm (or, with normalize = 0, a plain copy) of fp32 rows straight into SplitTile form
 int launch_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, void* out_split, int M,
-                           int N, int normalize, const int* done_flag, cudaStream_t s);
+                           int N, int normalize, const int* done_flag, cudaStream_t s, int act = ACT_NONE);
 int launch_pack_tiled(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s);
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s);   // impl 0 auto, 1 simt, 2 tcgen05
 

@@ -73,6 +73,7 @@ struct scv_decoder {
   // workspaces (engine-owned, grown on demand)
   DevBuf x, xn, qkv, attn, q2, ff, h1, h2, t3, logits, tlog, slog, ckv, kvpool, cur, fin, ptab, state, mtmp;
   DevBuf xn_s, attn_s, ff_s, h2_s;   // SplitTile (bf16 hi/lo) activations feeding the tcgen05 projections
+  DevBuf msplit;                     // SplitTile scratch of the memory builder / memory-token projection
   DevBuf seen, dlog;                 // site-dup gating: [B, V] seen-element bitmap, [B] site_dup_head logit
   DevBuf o_tok, o_lp, o_ent, masks_buf, forced_buf;   // engine-owned I/O so that a captured step never bakes caller pointers
   std::vector<GraphEntry> graphs;    // one instantiated CUDA graph of a decode step per call configuration
@@ -105,7 +106,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf, &seen, &dlog})
+                      &forced_buf, &seen, &dlog, &msplit})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -259,14 +260,40 @@ int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const fl
   float* t0 = D->mtmp.as<float>();
   float* t1 = t0 + (size_t)B * hid;
   int col = 0;
-  // latent tokens (:800-801)
-  if (c.memory_bottleneck_dim > 0) {
-    SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, D->l2m_a.N, B, ACT_NONE), 0, s));
-    SCV_TRY(launch_layernorm(t0, D->l2m_a.N, D->l2m_ln.g, D->l2m_ln.b, t0, D->l2m_a.N, B, D->l2m_a.N, ACT_GELU, nullptr, s));
+  // latent tokens (:800-801).  These two projections carry 85 % of the memory builder's flops: hand the activations
+  // over as SplitTiles (z split once, the hidden layer written split by the first GEMM's epilogue) instead of
+  // re-splitting fp32 rows inside every column tile of the GEMM.
+  const int Hd = D->l2m_a.N;
+  static const int forced_simt = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
+  const bool split_path = forced_simt != 1 && c.latent_dim % 64 == 0 && Hd % 64 == 0 && (d * c.n_memory_tokens) % 4 == 0 &&
+                          (c.memory_bottleneck_dim == 0 || Hd <= 1024) && ldm % 4 == 0;
+  if (split_path) {
+    const size_t zs_bytes = split_tile_bytes(B, c.latent_dim), hs_bytes = split_tile_bytes(B, Hd);
+    SCV_TRY(D->msplit.ensure(zs_bytes + hs_bytes));
+    unsigned char* zs = D->msplit.as<unsigned char>();
+    unsigned char* hs = zs + zs_bytes;
+    SCV_TRY(launch_layernorm_split(z, c.latent_dim, nullptr, nullptr, zs, B, c.latent_dim, 0, nullptr, s));
+    LinearArgs g1 = lin_args(z, c.latent_dim, D->l2m_a, t0, Hd, B, c.memory_bottleneck_dim > 0 ? ACT_NONE : ACT_GELU);
+    g1.a_split = zs;
+    if (c.memory_bottleneck_dim > 0) {
+      SCV_TRY(launch_linear(g1, 0, s));                                             // fp32 rows for the LayerNorm
+      SCV_TRY(launch_layernorm_split(t0, Hd, D->l2m_ln.g, D->l2m_ln.b, hs, B, Hd, 1, nullptr, s, ACT_GELU));
+    } else {
+      g1.y_split = hs;
+      SCV_TRY(launch_linear(g1, 0, s));
+    }
+    LinearArgs g2 = lin_args(t0, Hd, D->l2m_b, memory_out + col, ldm, B, ACT_NONE);
+    g2.a_split = hs;
+    SCV_TRY(launch_linear(g2, 0, s));
   } else {
-    SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, D->l2m_a.N, B, ACT_GELU), 0, s));
+    if (c.memory_bottleneck_dim > 0) {
+      SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, Hd, B, ACT_NONE), 0, s));
+      SCV_TRY(launch_layernorm(t0, Hd, D->l2m_ln.g, D->l2m_ln.b, t0, Hd, B, Hd, ACT_GELU, nullptr, s));
+    } else {
+      SCV_TRY(launch_linear(lin_args(z, c.latent_dim, D->l2m_a, t0, Hd, B, ACT_GELU), 0, s));
+    }
+    SCV_TRY(launch_linear(lin_args(t0, Hd, D->l2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
   }
-  SCV_TRY(launch_linear(lin_args(t0, D->l2m_a.N, D->l2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
   col += c.n_memory_tokens * d;
   if (use_skip) {                                                          // (:806-809)
     SCV_TRY(launch_linear(lin_args(skip, c.encoder_skip_dim, D->skip_a, t0, D->skip_a.N, B, ACT_GELU), 0, s));
@@ -526,9 +553,16 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   A = &G;
   // per-layer K/V projection of the memory tokens, once per call instead of once per step and layer
   // (the reference re-projects them inside nn.MultiheadAttention at every step, :1302-1307)
+  void* mem_split = nullptr;
+  if (use_tensor_cores(c, B)) {      // split the memory tokens once instead of once per layer and column tile
+    SCV_TRY(D->msplit.ensure(split_tile_bytes(B * M, d)));
+    mem_split = D->msplit.p;
+    SCV_TRY(launch_layernorm_split(A->memory, d, nullptr, nullptr, mem_split, B * M, d, 0, nullptr, s));
+  }
   for (int li = 0; li < c.num_layers; ++li) {
     const DecLayer& L = D->layers[li];
     LinearArgs a;
+    a.a_split = mem_split;
     a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld; a.wt = L.ca_kv_wt;
     a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
     a.M = B * M; a.N = 2 * d; a.K = d;

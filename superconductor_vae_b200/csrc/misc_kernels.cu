@@ -62,7 +62,7 @@ constexpr int kLnMaxChunks = 4;      // 8-element chunks per lane -> rows up to 
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                        const float* __restrict__ beta, uint8_t* __restrict__ out, int M, int N, int normalize,
-                       const int* done_flag) {
+                       int act, const int* done_flag) {
   pdl_wait();
   if (done_flag != nullptr && *done_flag != 0) return;
   pdl_launch_dependents();
@@ -71,6 +71,27 @@ layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __rest
   if (row >= M) return;
   const int n_chunks = N >> 3, KB = (N + 63) >> 6;
   const float* xr = x + (size_t)row * ldx;
+  if (!normalize) {
+    // plain split of a row of any width (latents, memory tokens): stream the chunks, no row statistics needed
+    const int mt = row >> 7, ri = row & 127;
+    for (int ch = lane; ch < KB * 8; ch += 32) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      if (ch < n_chunks) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + ch * 8), b = *reinterpret_cast<const float4*>(xr + ch * 8 + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) split_pair(o[2 * p], o[2 * p + 1], hi[p], lo[p]);
+      const int kb = ch >> 3, cj = ch & 7;
+      uint8_t* dst = out + ((size_t)mt * KB + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    return;
+  }
   float v[kLnMaxChunks][8];
   float s = 0.f;
 #pragma unroll
@@ -116,7 +137,7 @@ layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __rest
           const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+          for (int e = 0; e < 8; ++e) o[e] = apply_act((v[j][e] - mean) * rstd * gg[e] + bb[e], act);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = v[j][e];
@@ -134,13 +155,13 @@ layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __rest
 }
 
 int launch_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, void* out_split, int M,
-                           int N, int normalize, const int* done_flag, cudaStream_t s) {
-  SCV_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= kLnMaxChunks * 256, "layernorm_split: N=%d must be a multiple of 8, <= %d",
-              N, kLnMaxChunks * 256);
+                           int N, int normalize, const int* done_flag, cudaStream_t s, int act) {
+  SCV_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && (!normalize || N <= kLnMaxChunks * 256),
+              "layernorm_split: N=%d must be a multiple of 8 (and <= %d when normalising)", N, kLnMaxChunks * 256);
   SCV_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "layernorm_split: unaligned input");
   ProfScope prof(PC_LAYERNORM, s, 8.0 * M * N, 8.0 * M * N);
   SCV_CUDA(launch_k(layernorm_split_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, s, x, ldx, gamma, beta,
-                    static_cast<uint8_t*>(out_split), M, N, normalize, done_flag));
+                    static_cast<uint8_t*>(out_split), M, N, normalize, act, done_flag));
   SCV_LAUNCH_CHECK();
   return 0;
 }
