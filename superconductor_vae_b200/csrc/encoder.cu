@@ -177,9 +177,9 @@ struct scv_encoder {
   Lin co_a, co_b, co_c, cu_a, cu_b, cu_c, ir_a, ir_b; LNp co_ln, cu_ln, ir_ln;
   // never executed by the reference forward (element_properties=None) but present in its state_dict
   Lin prop_enc, combiner; LNp prop_ln;
-  DevBuf t0, t1, t2, fused_in, cond, sc_in, small;
+  DevBuf t0, t1, t2, fused_in, cond, sc_in, small, zsplit;
 
-  ~scv_encoder() { for (DevBuf* b : {&t0, &t1, &t2, &fused_in, &cond, &sc_in, &small}) b->release(); }
+  ~scv_encoder() { for (DevBuf* b : {&t0, &t1, &t2, &fused_in, &cond, &sc_in, &small, &zsplit}) b->release(); }
 };
 
 // nn.Linear with an extra tcgen05-tiled weight copy whenever the tensor-core path can take the projection
@@ -277,8 +277,9 @@ static int enc_register(scv_encoder* E) {
 }
 
 static int lin(const float* x, int ldx, const Lin& L, float* y, int ldy, int M, int act, cudaStream_t s,
-               const float* residual = nullptr, int ldr = 0) {
+               const float* residual = nullptr, int ldr = 0, const void* x_split = nullptr) {
   LinearArgs a;
+  a.a_split = (x_split != nullptr && L.wt != nullptr && L.N % 4 == 0) ? x_split : nullptr;   // SplitTile copy of x
   a.x = x; a.ldx = ldx; a.w = L.w; a.ldw = L.ldw; a.wt = L.wt; a.bias = L.b; a.y = y; a.ldy = ldy; a.M = M; a.N = L.N; a.K = L.K;
   a.act = act; a.residual = residual; a.ldr = ldr;
   return launch_linear(a, 0, s);
@@ -362,13 +363,23 @@ int scv_encoder_encode(scv_encoder* E, int32_t B, const int64_t* idx, const floa
   const float* h = fused;
   int hdim = F3;
   float* ping[2] = {t0, t2};
+  const void* h_split = nullptr;
   for (int j = 0; j < c.n_encoder_hidden; ++j) {
     float* o = ping[j & 1];
     SCV_TRY(lin(h, hdim, E->enc_lin[j], o, c.encoder_hidden[j], B, ACT_NONE, s));
-    SCV_TRY(ln(o, c.encoder_hidden[j], E->enc_ln[j], o, c.encoder_hidden[j], B, ACT_GELU, s));
+    const bool last = j == c.n_encoder_hidden - 1;
+    if (last && c.encoder_hidden[j] % 64 == 0 && c.encoder_hidden[j] <= 1024) {
+      // the only consumer is fc_mean: normalise + GELU straight into the tensor-core operand form
+      SCV_TRY(E->zsplit.ensure(split_tile_bytes(B, c.encoder_hidden[j])));
+      SCV_TRY(launch_layernorm_split(o, c.encoder_hidden[j], E->enc_ln[j].g, E->enc_ln[j].b, E->zsplit.p, B,
+                                     c.encoder_hidden[j], 1, nullptr, s, ACT_GELU));
+      h_split = E->zsplit.p;
+    } else {
+      SCV_TRY(ln(o, c.encoder_hidden[j], E->enc_ln[j], o, c.encoder_hidden[j], B, ACT_GELU, s));
+    }
     h = o; hdim = c.encoder_hidden[j];
   }
-  SCV_TRY(lin(h, hdim, E->fc_mean, z_out, c.latent_dim, B, ACT_NONE, s));
+  SCV_TRY(lin(h, hdim, E->fc_mean, z_out, c.latent_dim, B, ACT_NONE, s, nullptr, 0, h_split));
   return 0;
 }
 
@@ -398,13 +409,20 @@ int scv_encoder_heads(scv_encoder* E, int32_t B, const float* z, const scv_encod
   // sc_head input row starts with z itself (attention_vae.py:756-765)
   copy_cols_kernel<<<std::min(ceil_div(B * L, 256), 148 * 8), 256, 0, s>>>(z, L, sci, ld_sc, B, L);
   SCV_LAUNCH_CHECK();
+  // z feeds the backbone, competence, fraction and high-pressure heads: split it once for all four projections
+  const void* z_split = nullptr;
+  if (L % 64 == 0) {
+    SCV_TRY(E->zsplit.ensure(split_tile_bytes(B, L)));
+    SCV_TRY(launch_layernorm_split(z, L, nullptr, nullptr, E->zsplit.p, B, L, 0, nullptr, s));
+    z_split = E->zsplit.p;
+  }
   // backbone h -> cond[:, :bb]  (decode, :689)
   const float* h = z;
   int hdim = L;
   for (int j = 0; j < c.n_decoder_hidden; ++j) {
     const bool last = j == c.n_decoder_hidden - 1;
     float* o = (j & 1) ? t1 : t0;
-    SCV_TRY(lin(h, hdim, E->bb_lin[j], o, c.decoder_hidden[j], B, ACT_NONE, s));
+    SCV_TRY(lin(h, hdim, E->bb_lin[j], o, c.decoder_hidden[j], B, ACT_NONE, s, nullptr, 0, j == 0 ? z_split : nullptr));
     float* dst = last ? cond : o;
     const int ldd = last ? ld_cond : c.decoder_hidden[j];
     SCV_TRY(ln(o, c.decoder_hidden[j], E->bb_ln[j], dst, ldd, B, ACT_GELU, s));
@@ -434,15 +452,15 @@ int scv_encoder_heads(scv_encoder* E, int32_t B, const float* z, const scv_encod
   SCV_TRY(lin(cond, ld_cond, E->cls_a, t0, 256, B, ACT_GELU, s));
   SCV_TRY(lin(t0, 256, E->cls_b, sci + c_cls, ld_sc, B, ACT_NONE, s));
   // competence (:734)
-  SCV_TRY(lin(z, L, E->comp_a, t0, L / 4, B, ACT_GELU, s));
+  SCV_TRY(lin(z, L, E->comp_a, t0, L / 4, B, ACT_GELU, s, nullptr, 0, z_split));
   SCV_TRY(lin(t0, L / 4, E->comp_b, sci + c_comp, ld_sc, B, ACT_SIGMOID, s));
   // fraction head (:738-740): 12 fractions + count land contiguously in the sc_head input
-  SCV_TRY(lin(z, L, E->frac_a, t0, 256, B, ACT_NONE, s));
+  SCV_TRY(lin(z, L, E->frac_a, t0, 256, B, ACT_NONE, s, nullptr, 0, z_split));
   SCV_TRY(ln(t0, 256, E->frac_ln, t0, 256, B, ACT_GELU, s));
   SCV_TRY(lin(t0, 256, E->frac_b, t1, 128, B, ACT_GELU, s));
   SCV_TRY(lin(t1, 128, E->frac_c, sci + c_fr, ld_sc, B, ACT_NONE, s));
   // high-pressure head (:747)
-  SCV_TRY(lin(z, L, E->hp_a, t0, 256, B, ACT_RELU, s));
+  SCV_TRY(lin(z, L, E->hp_a, t0, 256, B, ACT_RELU, s, nullptr, 0, z_split));
   SCV_TRY(lin(t0, 256, E->hp_b, sci + c_hp, ld_sc, B, ACT_NONE, s));
   // SC head over the concatenation (:756-766): Linear, GELU, LayerNorm, Linear, GELU, Linear
   SCV_TRY(lin(sci, ld_sc, E->sc_a, t0, 512, B, ACT_GELU, s));
