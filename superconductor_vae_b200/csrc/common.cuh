@@ -81,8 +81,24 @@ enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
 constexpr int kEndIdx = 2;    // END_IDX (models/autoregressive_decoder.py:97)
 constexpr int kStartIdx = 1;  // START_IDX (:96)
 
+// erf with one code path (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 + fp32 rounding): the library erff has
+// two branches that a warp usually executes both of (~38 instructions per element), and the FFN1 epilogue applies GELU
+// to 128 x 128 values per tile with only eight warps (measured: 9.3 of 31 us of that projection).  An absolute error
+// of ~2e-7 on erf is the same order as fp32's own rounding of 1 + erf(x) in the reference and 30x below the 2^-17
+// relative precision the hi/lo activation split keeps.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  return copysignf(1.0f - p * t * e, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -93,6 +109,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case ACT_SIGMOID: return sigmoidf_(v);
     default: return v;
   }
+}
+
+// ACT >= 0: the activation is known at compile time; ACT < 0: decided by `act` at run time.
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float v, int act) {
+  if constexpr (ACT == ACT_NONE) return v;
+  else if constexpr (ACT == ACT_GELU) return gelu_erf(v);
+  else if constexpr (ACT == ACT_RELU) return v > 0.f ? v : 0.f;
+  else if constexpr (ACT == ACT_SIGMOID) return sigmoidf_(v);
+  else return apply_act(v, act);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -116,6 +142,28 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ha), b - __bfloat162float(hb));
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- F24: 3-byte storage of cached keys / values (decode_kernels.cu, "KV cache format") ----
+// A cached row of W values is [W x u16 | W x u8]: the top 16 bits of each fp32 (sign, exponent, 7 mantissa bits)
+// followed by the next 8 mantissa bits, i.e. fp32 rounded to nearest-even at 16 significant bits -- the same
+// precision the hi/lo split keeps on the activation side of every projection -- in 3/4 of the bytes.
+__device__ __forceinline__ uint32_t f24_round(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u + 0x7fu + ((u >> 8) & 1u);            // bits 31..8 are the stored value (finite inputs)
+}
+__device__ __forceinline__ void f24_pack4(float a, float b, float c, float d, uint2& hi, uint32_t& lo) {
+  const uint32_t r0 = f24_round(a), r1 = f24_round(b), r2 = f24_round(c), r3 = f24_round(d);
+  hi.x = __byte_perm(r0, r1, 0x7632);
+  hi.y = __byte_perm(r2, r3, 0x7632);
+  lo = __byte_perm(__byte_perm(r0, r1, 0x0051), __byte_perm(r2, r3, 0x0051), 0x5410);
+}
+// hi2 holds two u16 (elements 0, 1), lo the byte of element 0 in bits 7..0 and of element 1 in bits 15..8
+__device__ __forceinline__ float f24_get0(uint32_t hi2, uint32_t lo) {
+  return __uint_as_float((hi2 << 16) | ((lo & 0xffu) << 8));
+}
+__device__ __forceinline__ float f24_get1(uint32_t hi2, uint32_t lo) {
+  return __uint_as_float((hi2 & 0xffff0000u) | (lo & 0xff00u));
 }
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the multinomial sampler ----
@@ -157,12 +205,16 @@ struct LinearArgs {
   const float* residual = nullptr; int ldr = 0;    // may alias y
   float* y = nullptr; int ldy = 0;
   void* y_split = nullptr;                         // write the output in SplitTile form instead of fp32 rows
+  void* y_f24 = nullptr; int f24_w = 0;            // write the output as F24 rows of f24_w values (N % f24_w == 0):
+                                                   // output (m, n) -> row m * (N / f24_w) + n / f24_w (tcgen05 path only)
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
 };
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
+bool tc_persistent_ok(const LinearArgs& a);
+int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s);
 bool tc_shape_ok(const LinearArgs& a);
 size_t tc_packed_elems(int N, int K);
 size_t split_tile_bytes(int M, int K);             // bytes of a SplitTile buffer for an [M, K] activation

@@ -19,98 +19,15 @@
 // warp 8 allocates TMEM and its lane 0 issues the UMMAs.
 #include <cstdlib>
 
-#include "common.cuh"
+#include <type_traits>
+
+#include "tcgen05_common.cuh"
 
 namespace scv {
 
+using namespace tc;
+
 namespace {
-
-constexpr int BM = 128, BK = 64;
-constexpr int TILE_BYTES = 128 * 128;                       // 128 rows x 64 bf16 = 16 KB
-__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * TILE_BYTES + bn * 128; }       // A_hi, A_lo, W (bn rows x 128 B)
-__host__ __device__ constexpr int smem_bytes(int stages, int bn) { return stages * stage_bytes(bn) + 1024 /*align*/ + 128 /*barriers*/; }
-constexpr int STG_PITCH = 36;                               // floats per staged epilogue row (32 + pad, 16-byte aligned)
-constexpr int GROUP_THREADS = 128;
-constexpr int NUM_THREADS = 288;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128-byte swizzle: 8-row atoms of 1024 B (SBO = 1024), LBO unused, descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn.
-__host__ __device__ constexpr uint32_t idesc_for(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t kIdesc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-struct TcArgs {
-  const float* x; int ldx;          // fp32 activations (A_SPLIT = false)
-  const uint8_t* a_split;           // SplitTile activations (A_SPLIT = true)
-  const __nv_bfloat16* wt;          // tiled + swizzled weights
-  int kblocks;                      // ceil(K / 64)
-  const float* bias;
-  const float* residual; int ldr;
-  float* y; int ldy;                // fp32 output (OUT_SPLIT = false)
-  uint8_t* y_split; int kb_out;     // SplitTile output with kb_out = ceil(N / 64) k-blocks per row tile
-  int M, N, K, act;
-  const int* done_flag;
-};
 
 template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
@@ -242,6 +159,10 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    // The activation is uniform over the launch: pick it once (a per-element switch costs branches and, for
+    // GELU, kept ~200 call sites alive in the unrolled epilogue).
+    auto epilogue = [&](auto act_tag) {
+    constexpr int ACT = decltype(act_tag)::value;
 #pragma unroll(HAS_RES ? BN / 64 : 1)
     for (int cc = 0; cc < BN / 64; ++cc) {
       const int c0 = chalf * (BN / 2) + cc * 32;
@@ -264,10 +185,19 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
             const int row = it * 4 + rr, gm = m0 + quad * 32 + row;
             if (gm < a.M) {
               const float4 v = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + 4 * c4);
-              float o0 = apply_act(v.x + bv.x, a.act), o1 = apply_act(v.y + bv.y, a.act);
-              float o2 = apply_act(v.z + bv.z, a.act), o3 = apply_act(v.w + bv.w, a.act);
+              float o0 = apply_act_t<ACT>(v.x + bv.x, a.act), o1 = apply_act_t<ACT>(v.y + bv.y, a.act);
+              float o2 = apply_act_t<ACT>(v.z + bv.z, a.act), o3 = apply_act_t<ACT>(v.w + bv.w, a.act);
               if constexpr (HAS_RES) { o0 += rv[cc][it].x; o1 += rv[cc][it].y; o2 += rv[cc][it].z; o3 += rv[cc][it].w; }
-              *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
+              if (!HAS_RES && a.y_f24 != nullptr) {
+                const int part = gn / a.f24_w, e = gn - part * a.f24_w;
+                uint8_t* rowp = a.y_f24 + ((size_t)gm * (a.N / a.f24_w) + part) * (size_t)(3 * a.f24_w);
+                uint2 hi; uint32_t lo;
+                f24_pack4(o0, o1, o2, o3, hi, lo);
+                *reinterpret_cast<uint2*>(rowp + 2 * e) = hi;
+                *reinterpret_cast<uint32_t*>(rowp + 2 * a.f24_w + e) = lo;
+              } else {
+                *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
+              }
             }
           }
         }
@@ -291,8 +221,8 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
 #pragma unroll
               for (int p2 = 0; p2 < 4; ++p2) {
                 // columns >= N are the zero padding of the next projection's K
-                const float o0 = gn + 2 * p2 < a.N ? apply_act(vv[2 * p2] + bb[2 * p2], a.act) : 0.f;
-                const float o1 = gn + 2 * p2 + 1 < a.N ? apply_act(vv[2 * p2 + 1] + bb[2 * p2 + 1], a.act) : 0.f;
+                const float o0 = gn + 2 * p2 < a.N ? apply_act_t<ACT>(vv[2 * p2] + bb[2 * p2], a.act) : 0.f;
+                const float o1 = gn + 2 * p2 + 1 < a.N ? apply_act_t<ACT>(vv[2 * p2 + 1] + bb[2 * p2 + 1], a.act) : 0.f;
                 split_pair(o0, o1, hi[p2], lo[p2]);
               }
               uint8_t* dst = a.y_split + ((size_t)m_tile * a.kb_out + kb2) * (2 * TILE_BYTES) + (size_t)ri * 128 +
@@ -304,6 +234,10 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
         }
       }
     }
+    };
+    if (a.act == ACT_NONE) epilogue(std::integral_constant<int, ACT_NONE>{});
+    else if (a.act == ACT_GELU) epilogue(std::integral_constant<int, ACT_GELU>{});
+    else epilogue(std::integral_constant<int, -1>{});
     __syncwarp();
     tc_fence_before();
   } else {
@@ -370,7 +304,11 @@ bool tc_shape_ok(const LinearArgs& a) {
   if (a.a_split == nullptr) {
     if (a.x == nullptr || a.K % 4 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15u) != 0) return false;
   }
-  if (a.y_split == nullptr) {
+  if (a.y_f24 != nullptr) {
+    if (a.y_split != nullptr || a.residual != nullptr || a.f24_w <= 0 || a.f24_w % 8 != 0 || a.N % a.f24_w != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.y_f24) & 15u) != 0) return false;
+    if (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15u) != 0) return false;
+  } else if (a.y_split == nullptr) {
     if (a.y == nullptr || a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) return false;
     if (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15u) != 0) return false;
     if (a.residual != nullptr && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15u) != 0)) return false;
@@ -382,6 +320,7 @@ bool tc_shape_ok(const LinearArgs& a) {
 
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
+  if (a.y_f24 == nullptr && tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
   static bool attr_set = false;
   if (!attr_set) {
 #define SCV_SET_SMEM(A, O, R, S, N) \
@@ -398,6 +337,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;
   t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
+  t.y_f24 = reinterpret_cast<uint8_t*>(a.y_f24); t.f24_w = a.f24_w;
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,

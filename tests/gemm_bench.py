@@ -29,7 +29,7 @@ def bench(M, name, N, K, residual, split_out, iters=50):
     def run():
         _lib.check(L.scv_op_linear_split(_lib.ptr(xs), _lib.ptr(wt), _lib.ptr(b), _lib.ptr(r) if residual else None, N,
                                          None if split_out else _lib.ptr(y), N, _lib.ptr(ys) if split_out else None,
-                                         M, N, K, 1 if split_out else 0, st))
+                                         M, N, K, int(os.environ.get("GB_ACT", "1")) if split_out else 0, st))
     for _ in range(5):
         run()
     torch.cuda.synchronize()

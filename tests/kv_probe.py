@@ -1,0 +1,40 @@
+"""Probe (not a test): rows whose greedy tokens differ from the fp32 CPU oracle, for the KV cache format selected by
+SCV_KV_BITS (24 = F24 rows, 32 = fp32 rows).  usage: python tests/kv_probe.py [rows] [seed]"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import superconductor_vae_b200 as S                     # noqa: E402
+from superconductor_vae_b200 import synthetic as W      # noqa: E402
+from oracle import decoder_oracle as DO                 # noqa: E402
+from oracle import vocab as OV                          # noqa: E402
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1234
+shape = W.C512
+sd = W.make_decoder_state_dict(shape, 0)
+dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device="cuda:0")
+z = W.make_latents(rows, shape.latent_dim, seed)
+stoich, heads = W.make_conditioning(rows, shape.stoich_input_dim, seed)
+masks = OV.type_masks()
+
+
+def cu(t):
+    return {k: v.cuda() for k, v in t.items()} if isinstance(t, dict) else t.cuda()
+
+
+kw = dict(temperature=0.001, max_len=64, stop_boost=10.0, hard_stop_threshold=0.8)
+t, _, _ = dec.generate_with_kv_cache(cu(z), stoich_pred=cu(stoich), heads_pred=cu(heads), type_masks=cu(masks), **kw)
+t0 = time.time()
+torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+rt, _, _ = DO.generate_with_kv_cache(sd, 8, z, stoich_pred=stoich, heads_pred=heads, type_masks=masks, **kw)
+dt = time.time() - t0
+lens = DO.first_end_lengths(rt)
+tc = t.cpu()
+bad = [r for r in range(rows) if not torch.equal(tc[r, : int(lens[r])], rt[r, : int(lens[r])])]
+print(f"SCV_KV_BITS={os.environ.get('SCV_KV_BITS', '24')} SCV_LINEAR_IMPL={os.environ.get('SCV_LINEAR_IMPL', '0')} "
+      f"rows={rows} seed={seed}: {rows - len(bad)}/{rows} rows equal to the oracle up to their END "
+      f"(oracle {dt:.1f} s); differing rows: {bad[:16]}")
