@@ -4,6 +4,8 @@
 // argmax / Philox multinomial, log-prob, finished bookkeeping).
 #include <limits.h>
 
+#include <cstdlib>
+
 #include "decode_kernels.cuh"
 
 namespace scv {
@@ -216,18 +218,20 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
       const size_t off = row_off(n - 1) + e0;
       *reinterpret_cast<float4*>(a.kcache + off) = *reinterpret_cast<const float4*>(a.knew + (size_t)b * a.ldn + h * hd + e0);
       *reinterpret_cast<float4*>(a.vcache + off) = *reinterpret_cast<const float4*>(a.vnew + (size_t)b * a.ldn + h * hd + e0);
+      // (plain stores: the row is read back a few lines below by the other lanes of this warp)
     }
     __syncwarp();            // the appended row is read below by other lanes of this warp
   }
 
-  // scores: UNR * PPI positions in flight per warp
+  // scores: UNR * PPI positions in flight per warp (UNR 2 and 8 both measured ~2.5 % slower per decode: fewer
+  // loads in flight, or fewer resident warps)
   constexpr int UNR = 4;
   for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
     float4 kv[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int p = p0 + u * PPI + grp;
-      kv[u] = (p < n && e_ok) ? *reinterpret_cast<const float4*>(a.kcache + row_off(p) + e0) : zero4;
+      kv[u] = (p < n && e_ok) ? __ldcs(reinterpret_cast<const float4*>(a.kcache + row_off(p) + e0)) : zero4;
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
     for (int u = 0; u < UNR; ++u) {
       const int p = p0 + u * PPI + grp;
       const bool ok = p < n && e_ok;
-      vv[u] = ok ? *reinterpret_cast<const float4*>(a.vcache + row_off(p) + e0) : zero4;
+      vv[u] = ok ? __ldcs(reinterpret_cast<const float4*>(a.vcache + row_off(p) + e0)) : zero4;
       w[u] = ok ? sc[p] : 0.f;
     }
 #pragma unroll
@@ -546,10 +550,15 @@ __device__ int block_argmax(const float* sl, int V, float* redv, int* redi) {
   return bi;
 }
 
-// Stage the row's logits with type mask (:1416-1422), stop boost (:1438-1441), hard stop (:1444-1448) and
-// length boost (:1455-1457) applied, in the reference's order.  Returns bit0: row has nan/+-inf,
-// bit1: row has nan/+inf (a genuine numerical failure rather than a mask).
-__device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
+// Row context of the logit adjustments: type mask (:1416-1422), site-dup gate (:1426-1435), stop boost (:1438-1441),
+// hard stop (:1444-1448) and length boost (:1455-1457), applied per element in the reference's order.
+struct RowCtx {
+  const uint8_t* mk; const unsigned char* seen_row;
+  bool stop_on, force, dup_suppress, late;
+  float boost, length_boost;
+};
+__device__ __forceinline__ RowCtx make_row_ctx(const SamplerArgs& a, int b, int step) {
+  RowCtx c;
   int pred_type = 0;
   if (a.type_masks != nullptr) {
     const float* tl = a.type_logits + (size_t)b * a.ldt;
@@ -557,29 +566,47 @@ __device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
     for (int t = 1; t < 5; ++t)
       if (arg_better(tl[t], t, bv, pred_type)) { bv = tl[t]; pred_type = t; }
   }
-  const bool stop_on = a.stop_boost > 0.f;
+  c.stop_on = a.stop_boost > 0.f;
   float sp = 0.f;
-  bool force = false;
-  if (stop_on) {
+  c.force = false;
+  if (c.stop_on) {
     sp = sigmoidf_(a.stop_logits[b]);
-    force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
+    c.force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
   }
-  const float length_boost =
-      (stop_on && step > 10) ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
-  const bool dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(a.dup_logits[b]) < a.dup_threshold;
+  c.boost = a.stop_boost * sp;
+  c.late = c.stop_on && step > 10;
+  c.length_boost = c.late ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
+  c.dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(a.dup_logits[b]) < a.dup_threshold;
+  c.seen_row = c.dup_suppress ? a.seen + (size_t)b * a.V : nullptr;
+  c.mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
+  return c;
+}
+// allowed = type-mask byte of v (1 when no mask is given), seen = site-dup byte of v (0 when the gate is off)
+__device__ __forceinline__ float adjust_logit(const RowCtx& c, int v, float l, unsigned allowed, unsigned seen) {
+  if (allowed == 0) l = -INFINITY;
+  if (seen != 0) l = -30.0f;                                  // masked_fill(-30.0), even over a -inf
+  if (v == kEndIdx && c.stop_on) l = l + c.boost;
+  if (c.force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
+  if (v == kEndIdx && c.late) l = l + c.length_boost;
+  return l;
+}
+__device__ __forceinline__ int logit_flags(float l) {         // bit0: nan/+-inf, bit1: nan/+inf
+  int bad = 0;
+  if (isnan(l) || isinf(l)) bad |= 1;
+  if (isnan(l) || (isinf(l) && l > 0.f)) bad |= 2;
+  return bad;
+}
+
+// Stage the row's adjusted logits in shared memory.  Returns bit0: row has nan/+-inf, bit1: row has nan/+inf (a
+// genuine numerical failure rather than a mask).
+__device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
+  const RowCtx c = make_row_ctx(a, b, step);
   const float* lg = a.logits + (size_t)b * a.ldl;
-  const uint8_t* mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
   int bad = 0;
   for (int v = threadIdx.x; v < a.V; v += kSamplerThreads) {
-    float l = lg[v];
-    if (mk != nullptr && mk[v] == 0) l = -INFINITY;
-    if (dup_suppress && a.seen[(size_t)b * a.V + v] != 0) l = -30.0f;       // masked_fill(-30.0), even over a -inf
-    if (v == kEndIdx && stop_on) l = l + a.stop_boost * sp;
-    if (force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
-    if (v == kEndIdx && stop_on && step > 10) l = l + length_boost;
+    const float l = adjust_logit(c, v, lg[v], c.mk != nullptr ? c.mk[v] : 1u, c.seen_row != nullptr ? c.seen_row[v] : 0u);
     sl[v] = l;
-    if (isnan(l) || isinf(l)) bad |= 1;
-    if (isnan(l) || (isinf(l) && l > 0.f)) bad |= 2;
+    bad |= logit_flags(l);
   }
   return bad;
 }
@@ -617,6 +644,65 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
   }
   const int tok = block_argmax(sl, a.V, redv, redi);                                          // (:1507)
   if (threadIdx.x == 0) commit_token(a, b, step, tok, 0.f);
+}
+
+// Plain greedy decoding (temperature < 0.01, no entropy): one warp per row, no staging -- the adjusted logits are
+// consumed as they stream in (16-byte loads, 4 mask bytes at a time) and only the running argmax is kept.  Same
+// per-element arithmetic as phase 1 above (adjust, / temperature, first-occurrence argmax with NaN as maximum).
+__global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
+  pdl_wait();
+  if (a.st->done) return;
+  pdl_launch_dependents();
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= a.B) return;
+  const int step = a.st->step;
+  const RowCtx c = make_row_ctx(a, b, step);
+  const float4* lg = reinterpret_cast<const float4*>(a.logits + (size_t)b * a.ldl);
+  const uint32_t* mk4 = reinterpret_cast<const uint32_t*>(c.mk);
+  const uint32_t* sn4 = reinterpret_cast<const uint32_t*>(c.seen_row);
+  const bool scale = a.temperature != 1.0f;
+  float bv = -INFINITY;
+  int bi = INT_MAX, bad = 0;
+  const int n4 = a.V >> 2;
+  constexpr int UNR = 4;
+  for (int i0 = lane; i0 < n4; i0 += 32 * UNR) {
+    float4 x[UNR];
+    uint32_t m[UNR], sn[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + 32 * u;
+      const bool ok = i < n4;
+      x[u] = ok ? __ldcs(lg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      m[u] = (ok && mk4 != nullptr) ? mk4[i] : 0x01010101u;
+      sn[u] = (ok && sn4 != nullptr) ? sn4[i] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < n4) {
+        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int v = 4 * i + e;
+          float l = adjust_logit(c, v, xs[e], (m[u] >> (8 * e)) & 0xffu, (sn[u] >> (8 * e)) & 0xffu);
+          bad |= logit_flags(l);
+          if (scale) l = l / a.temperature;                     // (:1485-1486)
+          if (arg_better(l, v, bv, bi)) { bv = l; bi = v; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    if (bad & 1) atomicOr(&a.st->degenerate, 1);
+    commit_token(a, b, step, bi, 0.f);                          // (:1507)
+  }
 }
 
 // Phase 2: entropy, temperature, multinomial (or argmax) and log-prob, given the batch-global flag.
@@ -820,7 +906,12 @@ int launch_sampler(const SamplerArgs& a_in, int which, cudaStream_t s) {
     attr_set = true;
   }
   SCV_REQUIRE(smem <= 200 * 1024, "sampler: vocabulary of %d tokens does not fit in shared memory", a.V);
-  if (which == 1) {
+  const bool vec_ok = a.V % 4 == 0 && a.ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a.type_masks) & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.seen) & 3u) == 0;
+  if (which == 1 && !two_phase && vec_ok) {
+    SCV_CUDA(launch_k(sampler_greedy_kernel, dim3(ceil_div(a.B, 8)), dim3(256), 0, s, a));
+    SCV_LAUNCH_CHECK();
+  } else if (which == 1) {
     SCV_CUDA(launch_k(sampler_phase1_kernel, dim3(a.B), dim3(kSamplerThreads), smem, s, a, two_phase ? 0 : 1));
     SCV_LAUNCH_CHECK();
   } else if (two_phase) {

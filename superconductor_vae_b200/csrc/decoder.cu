@@ -673,7 +673,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     if (sync_each) {
       SCV_CUDA(cudaStreamSynchronize(s));
     }
-    const int poll = use_graph ? 2 : 4;
+    const int poll = use_graph ? 1 : 2;
     if ((step % poll) == poll - 1 && step + 1 < steps_max) {
       // bound the host's run-ahead to <= 2 * poll steps and stop enqueueing once every row has finished
       const int k = (step / poll) & 1;
