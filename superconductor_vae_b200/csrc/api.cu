@@ -174,7 +174,7 @@ int WeightStore::missing(std::string* first) const {
 // SCV_LINEAR_IMPL=1 in the environment forces the CUDA-core path everywhere (A/B testing of the two paths).
 int launch_linear(const LinearArgs& a, int impl, cudaStream_t s) {
   static const int forced = [] { const char* e = getenv("SCV_LINEAR_IMPL"); return e ? atoi(e) : 0; }();
-  if (a.a_split != nullptr || a.y_split != nullptr || a.y_f24 != nullptr) return launch_linear_tcgen05(a, s);   // no fp32 copy exists
+  if (a.a_split != nullptr || a.y_split != nullptr) return launch_linear_tcgen05(a, s);   // no fp32 copy exists
   if (impl == 0) impl = forced;
   if (impl == 2) return launch_linear_tcgen05(a, s);
   if (impl == 0 && tc_shape_ok(a)) return launch_linear_tcgen05(a, s);

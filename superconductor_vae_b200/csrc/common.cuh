@@ -144,28 +144,6 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// ---- F24: 3-byte storage of cached keys / values (decode_kernels.cu, "KV cache format") ----
-// A cached row of W values is [W x u16 | W x u8]: the top 16 bits of each fp32 (sign, exponent, 7 mantissa bits)
-// followed by the next 8 mantissa bits, i.e. fp32 rounded to nearest-even at 16 significant bits -- the same
-// precision the hi/lo split keeps on the activation side of every projection -- in 3/4 of the bytes.
-__device__ __forceinline__ uint32_t f24_round(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return u + 0x7fu + ((u >> 8) & 1u);            // bits 31..8 are the stored value (finite inputs)
-}
-__device__ __forceinline__ void f24_pack4(float a, float b, float c, float d, uint2& hi, uint32_t& lo) {
-  const uint32_t r0 = f24_round(a), r1 = f24_round(b), r2 = f24_round(c), r3 = f24_round(d);
-  hi.x = __byte_perm(r0, r1, 0x7632);
-  hi.y = __byte_perm(r2, r3, 0x7632);
-  lo = __byte_perm(__byte_perm(r0, r1, 0x0051), __byte_perm(r2, r3, 0x0051), 0x5410);
-}
-// hi2 holds two u16 (elements 0, 1), lo the byte of element 0 in bits 7..0 and of element 1 in bits 15..8
-__device__ __forceinline__ float f24_get0(uint32_t hi2, uint32_t lo) {
-  return __uint_as_float((hi2 << 16) | ((lo & 0xffu) << 8));
-}
-__device__ __forceinline__ float f24_get1(uint32_t hi2, uint32_t lo) {
-  return __uint_as_float((hi2 & 0xffff0000u) | (lo & 0xff00u));
-}
-
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the multinomial sampler ----
 struct Philox {
   __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -205,8 +183,6 @@ struct LinearArgs {
   const float* residual = nullptr; int ldr = 0;    // may alias y
   float* y = nullptr; int ldy = 0;
   void* y_split = nullptr;                         // write the output in SplitTile form instead of fp32 rows
-  void* y_f24 = nullptr; int f24_w = 0;            // write the output as F24 rows of f24_w values (N % f24_w == 0):
-                                                   // output (m, n) -> row m * (N / f24_w) + n / f24_w (tcgen05 path only)
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0

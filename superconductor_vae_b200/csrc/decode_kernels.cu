@@ -297,153 +297,6 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   }
 }
 
-// F24 variant: keys / values are stored in 3 bytes each (common.cuh, "F24"), LPP lanes x 8 head-dim elements cover
-// one cached position (16 B of u16 halves + 8 B of mantissa bytes per lane).  Attention is bound by the bytes of K
-// and V it streams (ncu r01i: 85-90 % of the HBM peak with fp32 rows), so the cache format is the lever: 3/4 of the
-// traffic at the 16-significant-bit precision the projections already work in.  kcache / vcache are byte pointers and
-// page_stride / seq_stride / row_stride are in BYTES in this mode.
-__device__ __forceinline__ void f24_load8(const uint8_t* row, int hi_off, int lo_off, float (&v)[8]) {
-  const uint4 h = *reinterpret_cast<const uint4*>(row + hi_off);
-  const uint2 l = *reinterpret_cast<const uint2*>(row + lo_off);
-  v[0] = f24_get0(h.x, l.x);       v[1] = f24_get1(h.x, l.x);
-  v[2] = f24_get0(h.y, l.x >> 16); v[3] = f24_get1(h.y, l.x >> 16);
-  v[4] = f24_get0(h.z, l.y);       v[5] = f24_get1(h.z, l.y);
-  v[6] = f24_get0(h.w, l.y >> 16); v[7] = f24_get1(h.w, l.y >> 16);
-}
-__device__ __forceinline__ void f24_store8(uint8_t* row, int hi_off, int lo_off, const float4& a, const float4& b) {
-  uint2 h0, h1; uint32_t l0, l1;
-  f24_pack4(a.x, a.y, a.z, a.w, h0, l0);
-  f24_pack4(b.x, b.y, b.z, b.w, h1, l1);
-  *reinterpret_cast<uint4*>(row + hi_off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-  *reinterpret_cast<uint2*>(row + lo_off) = make_uint2(l0, l1);
-}
-
-template <int LPP>
-__global__ void __launch_bounds__(256) attention_decode_f24_kernel(AttnArgs a) {
-  extern __shared__ float sc_all[];
-  pdl_wait();
-  if (a.st->done) return;
-  pdl_launch_dependents();
-  constexpr int PPI = 32 / LPP;
-  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (gw >= a.B * a.nhead) return;
-  const int b = gw / a.nhead, h = gw % a.nhead;
-  const int hd = a.hd, d = a.nhead * a.hd;
-  const int n = a.fixed_len >= 0 ? a.fixed_len : a.st->step + 1;
-  float* sc = sc_all + (size_t)warp_in_block * a.max_n;
-  const int grp = lane / LPP, e0 = 8 * (lane % LPP);
-  const bool e_ok = e0 < hd;
-  const int hi_off = 2 * (h * hd + e0), lo_off = 2 * d + h * hd + e0;
-  uint8_t* kc = reinterpret_cast<uint8_t*>(a.kcache);
-  uint8_t* vc = reinterpret_cast<uint8_t*>(a.vcache);
-
-  const bool paged = a.page_table != nullptr;
-  const int* pt = paged ? a.page_table + (size_t)b * a.pages_per_seq : nullptr;
-  auto row_off = [&](int p) -> size_t {
-    if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride;
-    return (size_t)b * a.seq_stride + (size_t)p * a.row_stride;
-  };
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* qp = a.q + (size_t)b * a.ldq + h * hd + e0;
-  const float4 qa = e_ok ? *reinterpret_cast<const float4*>(qp) : zero4;
-  const float4 qb = e_ok ? *reinterpret_cast<const float4*>(qp + 4) : zero4;
-
-  if (a.knew != nullptr) {   // append (torch.cat in the reference, :1266-1267)
-    if (grp == 0 && e_ok) {
-      const size_t off = row_off(n - 1);
-      const float* kn = a.knew + (size_t)b * a.ldn + h * hd + e0;
-      const float* vn = a.vnew + (size_t)b * a.ldn + h * hd + e0;
-      f24_store8(kc + off, hi_off, lo_off, *reinterpret_cast<const float4*>(kn), *reinterpret_cast<const float4*>(kn + 4));
-      f24_store8(vc + off, hi_off, lo_off, *reinterpret_cast<const float4*>(vn), *reinterpret_cast<const float4*>(vn + 4));
-    }
-    __syncwarp();            // the appended row is read below by other lanes of this warp
-  }
-
-  constexpr int UNR = 4;
-  for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
-    float kv[UNR][8];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * PPI + grp;
-      if (p < n && e_ok) {
-        f24_load8(kc + row_off(p), hi_off, lo_off, kv[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) kv[u][j] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      float d0 = fmaf(qa.x, kv[u][0], fmaf(qa.y, kv[u][1], fmaf(qa.z, kv[u][2], qa.w * kv[u][3])));
-      float d1 = fmaf(qb.x, kv[u][4], fmaf(qb.y, kv[u][5], fmaf(qb.z, kv[u][6], qb.w * kv[u][7])));
-      float dsum = d0 + d1;
-#pragma unroll
-      for (int o = LPP / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-      const int p = p0 + u * PPI + grp;
-      if ((lane % LPP) == 0 && p < n) sc[p] = dsum * a.scale;
-    }
-  }
-  __syncwarp();
-  float m = -INFINITY;
-  for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
-  m = warp_max(m);
-  float sum = 0.f;
-  for (int p = lane; p < n; p += 32) {
-    const float e = expf(sc[p] - m);
-    sc[p] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
-  __syncwarp();
-
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
-    float vv[UNR][8];
-    float w[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * PPI + grp;
-      const bool ok = p < n && e_ok;
-      if (ok) {
-        f24_load8(vc + row_off(p), hi_off, lo_off, vv[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vv[u][j] = 0.f;
-      }
-      w[u] = ok ? sc[p] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u], vv[u][j], acc[j]);
-  }
-#pragma unroll
-  for (int o = LPP; o < 32; o <<= 1)         // combine the PPI position groups
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-  if (grp == 0 && e_ok) {
-    if (a.out_split == nullptr) {
-      float* op = a.out + (size_t)b * a.ldo + h * hd + e0;
-      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int p2 = 0; p2 < 4; ++p2) split_pair(acc[2 * p2], acc[2 * p2 + 1], hi[p2], lo[p2]);
-      const int col = h * hd + e0;
-      const int mt = b >> 7, ri = b & 127, kb = col >> 6, cj = (col & 63) >> 3;
-      uint8_t* dst = a.out_split + ((size_t)mt * a.kb_out + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
-}
-
 int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a_in.hd >= 1 && a_in.hd <= 128, "attention: head_dim %d not in 1..128", a_in.hd);
   SCV_REQUIRE(a_in.max_n >= 1, "attention: max_n must be positive");
@@ -454,21 +307,6 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   const int blocks = ceil_div(a.B * a.nhead, warps);
   const size_t smem = (size_t)warps * a.max_n * sizeof(float);
   const int epl = ceil_div(a.hd, 32);
-  if (a.kv_f24) {
-    SCV_REQUIRE(a.hd % 8 == 0 && (a.nhead * a.hd) % 16 == 0 && a.ldq % 4 == 0 && (a.knew == nullptr || a.ldn % 4 == 0) &&
-                    (a.out_split != nullptr || a.ldo % 4 == 0) && a.row_stride % 16 == 0 && a.seq_stride % 16 == 0 &&
-                    a.page_stride % 16 == 0,
-                "attention: F24 cache needs head_dim %% 8 == 0, d_model %% 16 == 0 and 16-byte aligned rows");
-    const double n_hint = a.fixed_len >= 0 ? a.fixed_len : a.host_len_hint;
-    ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
-                   1.0 * a.B * a.nhead * a.hd * (6.0 * n_hint + 8.0 + (a.knew ? 14.0 : 0.0)));
-    const int lanes = a.hd / 8;
-    if (lanes <= 4) SCV_CUDA(launch_k(attention_decode_f24_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a));
-    else if (lanes <= 8) SCV_CUDA(launch_k(attention_decode_f24_kernel<8>, dim3(blocks), dim3(warps * 32), smem, s, a));
-    else SCV_CUDA(launch_k(attention_decode_f24_kernel<16>, dim3(blocks), dim3(warps * 32), smem, s, a));
-    SCV_LAUNCH_CHECK();
-    return 0;
-  }
   const bool v4 = a.hd % 4 == 0 && a.ldq % 4 == 0 && a.row_stride % 4 == 0 && a.seq_stride % 4 == 0 && a.page_stride % 4 == 0 &&
                   (a.knew == nullptr || a.ldn % 4 == 0) && (a.out_split != nullptr || a.ldo % 4 == 0);
   const double n_hint = a.fixed_len >= 0 ? a.fixed_len : a.host_len_hint;

@@ -43,8 +43,6 @@ struct AttnArgs {
   int fixed_len = -1;                                    // cross: memory tokens; self: -1 -> step + 1
   int max_n = 0;                                         // smem scores per warp
   int host_len_hint = 0;                                 // host's view of step + 1 (profiling byte counts only)
-  int kv_f24 = 0;                                        // K/V rows stored as F24 (3 bytes per value): kcache / vcache are
-                                                         // byte pointers and the three strides above are in bytes
   const StepState* st = nullptr;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);

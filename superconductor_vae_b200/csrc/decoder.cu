@@ -325,13 +325,6 @@ static bool use_tensor_cores(const scv_decoder_config& c, int B) {
          c.vocab_size % 4 == 0 && c.d_model <= 1024;
 }
 
-// Cached keys / values (paged self-attention cache and projected memory tokens) in the 3-byte F24 format: only with
-// the tensor-core step (its K/V projection writes F24 rows from the GEMM epilogue), SCV_KV_BITS=32 keeps fp32 rows.
-static bool kv_f24(const scv_decoder_config& c, int B) {
-  static const int bits = [] { const char* e = getenv("SCV_KV_BITS"); return e ? atoi(e) : 24; }();
-  return bits == 24 && use_tensor_cores(c, B) && c.d_model % 16 == 0;
-}
-
 static int ensure_workspace(scv_decoder* D, int B, int M) {
   const scv_decoder_config& c = D->cfg;
   const size_t d = c.d_model, f = sizeof(float);
@@ -397,7 +390,6 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   // Tensor-core step: every projection input is handed over as a bf16 hi/lo SplitTile written by its producer
   // (LayerNorm, attention, previous GEMM epilogue); nullptr selects the fp32 CUDA-core path.
   const bool tc = use_tensor_cores(c, Bfull);
-  const bool f24 = kv_f24(c, Bfull);          // cached K / V rows in 3 bytes per value (common.cuh "F24"), else fp32
   auto tile_off = [&](const DevBuf& b, int K) -> void* {
     return static_cast<unsigned char*>(b.p) + (size_t)(r0 / 128) * ceil_div(K, 64) * 32768;
   };
@@ -443,16 +435,9 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(a, 0, s));
     AttnArgs sa;
     sa.q = qkv; sa.ldq = 3 * d; sa.knew = qkv + d; sa.vnew = qkv + 2 * d; sa.ldn = 3 * d;
-    if (f24) {     // same page geometry with 3 * d bytes per cached row; strides in bytes
-      unsigned char* pool = D->kvpool.as<unsigned char>();
-      sa.kcache = reinterpret_cast<float*>(pool + (size_t)(li * 2 + 0) * kPagePos * 3 * d);
-      sa.vcache = reinterpret_cast<float*>(pool + (size_t)(li * 2 + 1) * kPagePos * 3 * d);
-      sa.page_stride = page_stride * 3; sa.row_stride = 3 * d; sa.kv_f24 = 1;
-    } else {
-      sa.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
-      sa.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d;
-      sa.page_stride = page_stride; sa.row_stride = d;
-    }
+    sa.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
+    sa.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d;
+    sa.page_stride = page_stride; sa.row_stride = d;
     sa.page_table = page_table; sa.pages_per_seq = pps;
     sa.out = attn; sa.ldo = d; sa.B = B; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale; sa.fixed_len = -1;
     sa.max_n = std::max(c.pe_len, M); sa.st = st; sa.host_len_hint = host_step + 1;
@@ -469,14 +454,8 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
     ca.q = q2; ca.ldq = d;
-    if (f24) {     // the K and V rows of a memory token are consecutive F24 rows of 3 * d bytes
-      unsigned char* ckv = D->ckv.as<unsigned char>() + ((size_t)li * Bfull + r0) * M * 2 * 3 * d;
-      ca.kcache = reinterpret_cast<float*>(ckv); ca.vcache = reinterpret_cast<float*>(ckv + 3 * d);
-      ca.seq_stride = (long long)M * 6 * d; ca.row_stride = 6 * d; ca.kv_f24 = 1;
-    } else {
-      float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + r0) * M * 2 * d;
-      ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d; ca.row_stride = 2 * d;
-    }
+    float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + r0) * M * 2 * d;
+    ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d; ca.row_stride = 2 * d;
     ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
     ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
     ca.out_split = static_cast<unsigned char*>(attn_s); ca.kb_out = d / 64;
@@ -588,9 +567,6 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     a.a_split = mem_split;
     a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld; a.wt = L.ca_kv_wt;
     a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
-    if (kv_f24(c, B)) {
-      a.y = nullptr; a.y_f24 = D->ckv.as<unsigned char>() + (size_t)li * B * M * 2 * 3 * d; a.f24_w = d;
-    }
     a.M = B * M; a.N = 2 * d; a.K = d;
     SCV_TRY(launch_linear(a, 0, s));
   }

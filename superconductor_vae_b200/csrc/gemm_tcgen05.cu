@@ -188,16 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
               float o0 = apply_act_t<ACT>(v.x + bv.x, a.act), o1 = apply_act_t<ACT>(v.y + bv.y, a.act);
               float o2 = apply_act_t<ACT>(v.z + bv.z, a.act), o3 = apply_act_t<ACT>(v.w + bv.w, a.act);
               if constexpr (HAS_RES) { o0 += rv[cc][it].x; o1 += rv[cc][it].y; o2 += rv[cc][it].z; o3 += rv[cc][it].w; }
-              if (!HAS_RES && a.y_f24 != nullptr) {
-                const int part = gn / a.f24_w, e = gn - part * a.f24_w;
-                uint8_t* rowp = a.y_f24 + ((size_t)gm * (a.N / a.f24_w) + part) * (size_t)(3 * a.f24_w);
-                uint2 hi; uint32_t lo;
-                f24_pack4(o0, o1, o2, o3, hi, lo);
-                *reinterpret_cast<uint2*>(rowp + 2 * e) = hi;
-                *reinterpret_cast<uint32_t*>(rowp + 2 * a.f24_w + e) = lo;
-              } else {
-                *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
-              }
+              *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
             }
           }
         }
@@ -304,11 +295,7 @@ bool tc_shape_ok(const LinearArgs& a) {
   if (a.a_split == nullptr) {
     if (a.x == nullptr || a.K % 4 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15u) != 0) return false;
   }
-  if (a.y_f24 != nullptr) {
-    if (a.y_split != nullptr || a.residual != nullptr || a.f24_w <= 0 || a.f24_w % 8 != 0 || a.N % a.f24_w != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(a.y_f24) & 15u) != 0) return false;
-    if (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15u) != 0) return false;
-  } else if (a.y_split == nullptr) {
+  if (a.y_split == nullptr) {
     if (a.y == nullptr || a.ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) return false;
     if (a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15u) != 0) return false;
     if (a.residual != nullptr && (a.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(a.residual) & 15u) != 0)) return false;
@@ -320,7 +307,7 @@ bool tc_shape_ok(const LinearArgs& a) {
 
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
-  if (a.y_f24 == nullptr && tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
+  if (tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
   static bool attr_set = false;
   if (!attr_set) {
 #define SCV_SET_SMEM(A, O, R, S, N) \
@@ -337,7 +324,6 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;
   t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
-  t.y_f24 = reinterpret_cast<uint8_t*>(a.y_f24); t.f24_w = a.f24_w;
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,

@@ -235,7 +235,6 @@ int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s) {
   t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;
   t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
-  t.y_f24 = nullptr; t.f24_w = 0;
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   const int ntn = ceil_div(a.N, P_BN), ntm = ceil_div(a.M, BM), n_tiles = ntn * ntm;
   const int grid = std::min(n_tiles, 148);

@@ -88,7 +88,6 @@ struct TcArgs {
   const float* residual; int ldr;
   float* y; int ldy;                // fp32 output (OUT_SPLIT = false)
   uint8_t* y_split; int kb_out;     // SplitTile output with kb_out = ceil(N / 64) k-blocks per row tile
-  uint8_t* y_f24; int f24_w;        // F24 output rows (OUT_SPLIT = false, no residual); null -> fp32 y
   int M, N, K, act;
   const int* done_flag;
 };
