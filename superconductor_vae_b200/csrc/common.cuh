@@ -186,6 +186,7 @@ struct LinearArgs {
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
+  const void* next_w = nullptr; size_t next_w_bytes = 0;   // tiled weights of the NEXT projection: prefetched into L2
 };
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);

@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   extern __shared__ float sc_all[];
   pdl_wait();
   if (a.st->done) return;
-  pdl_launch_dependents();
   constexpr int PPI = 32 / LPP;
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -274,6 +273,7 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
       acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
     }
   }
+  if (threadIdx.x == 0) pdl_launch_dependents();   // all K / V of this CTA's first warp are in: let the next kernel ramp up
 #pragma unroll
   for (int o = LPP; o < 32; o <<= 1) {       // combine the PPI position groups
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
@@ -490,7 +490,6 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
 __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
   pdl_wait();
   if (a.st->done) return;
-  pdl_launch_dependents();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= a.B) return;
   const int step = a.st->step;
@@ -530,6 +529,7 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
       }
     }
   }
+  if (threadIdx.x == 0) pdl_launch_dependents();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, bv, o);

@@ -393,6 +393,10 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   auto tile_off = [&](const DevBuf& b, int K) -> void* {
     return static_cast<unsigned char*>(b.p) + (size_t)(r0 / 128) * ceil_div(K, 64) * 32768;
   };
+  // each tensor-core projection prefetches the tiled weights of the projection that follows it (common.cuh next_w)
+  auto next = [&](LinearArgs& l, const __nv_bfloat16* wt, int N, int K) {
+    if (tc && wt != nullptr) { l.next_w = wt; l.next_w_bytes = tc_packed_elems(N, K) * sizeof(__nv_bfloat16); }
+  };
   void* xn_s = tc ? tile_off(D->xn_s, d) : nullptr; void* attn_s = tc ? tile_off(D->attn_s, d) : nullptr;
   void* ff_s = tc ? tile_off(D->ff_s, dff) : nullptr; void* h2_s = tc ? tile_off(D->h2_s, d) : nullptr;
   SamplerArgs sp;
@@ -432,6 +436,7 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     LinearArgs a;
     a.x = xn; a.ldx = d; a.a_split = xn_s; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.wt = L.sa_in_wt; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
     a.M = B; a.N = 3 * d; a.K = d; a.done_flag = done;
+    next(a, L.sa_out.wt, d, d);
     SCV_TRY(launch_linear(a, 0, s));
     AttnArgs sa;
     sa.q = qkv; sa.ldq = 3 * d; sa.knew = qkv + d; sa.vnew = qkv + 2 * d; sa.ldn = 3 * d;
@@ -445,12 +450,14 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_attention(sa, s));
     LinearArgs o = lin_args(attn, d, L.sa_out, x, d, B, ACT_NONE, done);
     o.residual = x; o.ldr = d; o.a_split = attn_s;
+    next(o, L.ca_q_wt, d, d);
     SCV_TRY(launch_linear(o, 0, s));
     // ---- cross attention to the memory tokens (:1299-1308)
     SCV_TRY(norm(L.n2, xn));
     LinearArgs q;
     q.x = xn; q.ldx = d; q.a_split = xn_s; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.wt = L.ca_q_wt; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
     q.M = B; q.N = d; q.K = d; q.done_flag = done;
+    next(q, L.ca_out.wt, d, d);
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
     ca.q = q2; ca.ldq = d;
@@ -462,14 +469,17 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_attention(ca, s));
     LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
     co.residual = x; co.ldr = d; co.a_split = attn_s;
+    next(co, L.ff1.wt, dff, d);
     SCV_TRY(launch_linear(co, 0, s));
     // ---- feed forward (:1311-1313)
     SCV_TRY(norm(L.n3, xn));
     LinearArgs f1 = lin_args(xn, d, L.ff1, ff, dff, B, ACT_GELU, done);
     f1.a_split = xn_s; f1.y_split = ff_s;
+    next(f1, L.ff2.wt, d, dff);
     SCV_TRY(launch_linear(f1, 0, s));
     LinearArgs f2 = lin_args(ff, dff, L.ff2, x, d, B, ACT_NONE, done);
     f2.residual = x; f2.ldr = d; f2.a_split = ff_s;
+    if (li + 1 < c.num_layers) next(f2, D->layers[li + 1].sa_in_wt, 3 * d, d); else next(f2, D->out_a.wt, d, d);
     SCV_TRY(launch_linear(f2, 0, s));
   }
   // ---- heads (:1413, 1417, 1439)
@@ -480,6 +490,7 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   SCV_TRY(norm(D->out_ln, h1));
   LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done);
   oa.a_split = xn_s; oa.y_split = h2_s;
+  next(oa, D->out_b.wt, c.vocab_size, d);
   SCV_TRY(launch_linear(oa, 0, s));
   LinearArgs ob = lin_args(h2, d, D->out_b, logits, c.vocab_size, B, ACT_NONE, done);
   ob.a_split = h2_s;
@@ -527,7 +538,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const int steps_max = max_len - 1;
   SCV_REQUIRE(steps_max >= 1, "generate: max_len %d leaves no step to run", A->max_len);
   const int B = A->batch, M = A->n_memory, d = c.d_model;
-  set_pdl_for_call(B < 1024);
+  set_pdl_for_call(true);
   SCV_TRY(ensure_workspace(D, B, M));
   StepState* st = D->state.as<StepState>();
   SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s));

@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   // tail; from here on this kernel reads what its predecessors wrote.
   pdl_wait();
   const bool skip = a.done_flag != nullptr && *a.done_flag != 0;     // every row finished: nothing left to compute
-  pdl_launch_dependents();
   // weight tiles are packed per 128 output rows: a 256-wide CTA tile is two of them (same k-block, KB tiles apart)
   const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * (BN / 128) * KB * (TILE_BYTES / 2);
 
@@ -159,6 +158,10 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    // The main loop of this CTA is over: once every CTA is here (or gone) the next kernel of the stream may start
+    // launching, so its launch latency and prologue overlap this epilogue and the grid's drain.  (Triggering at kernel
+    // entry instead let early dependents take shared memory / TMEM from CTAs of this grid that had not started yet.)
+    if (tid == 0) pdl_launch_dependents();
     // The activation is uniform over the launch: pick it once (a per-element switch costs branches and, for
     // GELU, kept ~200 call sites alive in the unrolled epilogue).
     auto epilogue = [&](auto act_tag) {
@@ -234,6 +237,14 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   } else {
     // ===================== MMA issuer (warp 8) =====================
     if (lane == 0) {
+      // While this projection runs, pull the next one's weights into L2 (they were evicted by a whole decode step of
+      // activations and K/V traffic): its first k-blocks then start from L2 instead of a DRAM round trip.
+      if (a.next_w_bytes != 0) {
+        const uint32_t ncta = gridDim.x * gridDim.y, cid = blockIdx.y * gridDim.x + blockIdx.x;
+        const uint32_t chunk = ((a.next_w_bytes + ncta - 1) / ncta + 127u) & ~127u;
+        const uint32_t off = cid * chunk;
+        if (off < a.next_w_bytes) bulk_prefetch_l2(a.next_w + off, min(chunk, a.next_w_bytes - off) & ~15u);
+      }
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
@@ -325,6 +336,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
+  t.next_w = static_cast<const uint8_t*>(a.next_w); t.next_w_bytes = (uint32_t)a.next_w_bytes;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));

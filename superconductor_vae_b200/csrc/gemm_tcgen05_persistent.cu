@@ -236,6 +236,7 @@ int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s) {
   t.kblocks = ceil_div(a.K, BK); t.bias = a.bias; t.residual = a.residual; t.ldr = a.ldr; t.y = a.y; t.ldy = a.ldy;
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
+  t.next_w = nullptr; t.next_w_bytes = 0;
   const int ntn = ceil_div(a.N, P_BN), ntm = ceil_div(a.M, BM), n_tiles = ntn * ntm;
   const int grid = std::min(n_tiles, 148);
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,

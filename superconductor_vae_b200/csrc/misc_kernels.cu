@@ -65,7 +65,7 @@ layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __rest
                        int act, const int* done_flag) {
   pdl_wait();
   if (done_flag != nullptr && *done_flag != 0) return;
-  pdl_launch_dependents();
+  if (!normalize) pdl_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -122,6 +122,7 @@ layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __rest
     }
     rstd = 1.0f / sqrtf(warp_sum(q) / (float)N + 1e-5f);
   }
+  if (threadIdx.x == 0) pdl_launch_dependents();   // the row is in registers: only the stores are left
   const int mt = row >> 7, ri = row & 127;
 #pragma unroll
   for (int j = 0; j < kLnMaxChunks; ++j) {

@@ -79,6 +79,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 struct TcArgs {
   const float* x; int ldx;          // fp32 activations (A_SPLIT = false)
   const uint8_t* a_split;           // SplitTile activations (A_SPLIT = true)
@@ -90,6 +94,7 @@ struct TcArgs {
   uint8_t* y_split; int kb_out;     // SplitTile output with kb_out = ceil(N / 64) k-blocks per row tile
   int M, N, K, act;
   const int* done_flag;
+  const uint8_t* next_w; uint32_t next_w_bytes;   // L2 prefetch of the next projection's weights (0 = none)
 };
 
 
