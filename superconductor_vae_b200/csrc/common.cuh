@@ -187,12 +187,16 @@ struct LinearArgs {
   int act = ACT_NONE;
   const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
   const void* next_w = nullptr; size_t next_w_bytes = 0;   // tiled weights of the NEXT projection: prefetched into L2
+  // LayerNorm(y) written as a SplitTile by the same kernel (gemm_tcgen05_ln.cu; callers check tc_res_ln_ok first)
+  const float* ln_gamma = nullptr; const float* ln_beta = nullptr; void* ln_out_split = nullptr;
 };
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
 bool tc_persistent_ok(const LinearArgs& a);
 int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s);
 bool tc_shape_ok(const LinearArgs& a);
+bool tc_res_ln_ok(const LinearArgs& a);
+int launch_linear_res_ln(const LinearArgs& a, cudaStream_t s);
 size_t tc_packed_elems(int N, int K);
 size_t split_tile_bytes(int M, int K);             // bytes of a SplitTile buffer for an [M, K] activation
 // LayerNorm (or, with normalize = 0, a plain copy) of fp32 rows straight into SplitTile form

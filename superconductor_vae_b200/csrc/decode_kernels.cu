@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
   const int b = blockIdx.x, step = a.st->step;
   const int bad = stage_logits(a, b, step, sl);
   const int row_bad = __syncthreads_or(bad & 1);
-  if (threadIdx.x == 0 && row_bad) atomicOr(&a.st->degenerate, 1);
+  // test before the atomic: with a type mask every row is "bad" and they would all serialise on this one word
+  if (threadIdx.x == 0 && row_bad && *reinterpret_cast<volatile int*>(&a.st->degenerate) == 0) atomicOr(&a.st->degenerate, 1);
   if (!finalize) return;
   if (a.temperature != 1.0f) {
     for (int v = threadIdx.x; v < a.V; v += kSamplerThreads) sl[v] = sl[v] / a.temperature;   // (:1485-1486)
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
   const uint32_t* sn4 = reinterpret_cast<const uint32_t*>(c.seen_row);
   const bool scale = a.temperature != 1.0f;
   float bv = -INFINITY;
-  int bi = INT_MAX, bad = 0;
+  int bi = INT_MAX;
   const int n4 = a.V >> 2;
   constexpr int UNR = 4;
   for (int i0 = lane; i0 < n4; i0 += 32 * UNR) {
@@ -522,7 +523,6 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
         for (int e = 0; e < 4; ++e) {
           const int v = 4 * i + e;
           float l = adjust_logit(c, v, xs[e], (m[u] >> (8 * e)) & 0xffu, (sn[u] >> (8 * e)) & 0xffu);
-          bad |= logit_flags(l);
           if (scale) l = l / a.temperature;                     // (:1485-1486)
           if (arg_better(l, v, bv, bi)) { bv = l; bi = v; }
         }
@@ -534,13 +534,11 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
     if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
   }
-  if (lane == 0) {
-    if (bad & 1) atomicOr(&a.st->degenerate, 1);
-    commit_token(a, b, step, bi, 0.f);                          // (:1507)
-  }
+  // (the batch-global degenerate flag, :1464-1466, only changes how probabilities are sampled; argmax ignores it,
+  // and with a type mask every row would hit the same atomic: 4096 serialised updates cost ~75 us per step)
+  if (lane == 0) commit_token(a, b, step, bi, 0.f);             // (:1507)
 }
 
 // Phase 2: entropy, temperature, multinomial (or argmax) and log-prob, given the batch-global flag.

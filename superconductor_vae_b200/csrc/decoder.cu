@@ -423,16 +423,27 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
               : launch_layernorm(x, d, P.g, P.b, fp32_out, d, B, d, ACT_NONE, done, s);
   };
 
+  // A residual projection followed by LayerNorm P of the row it wrote: one cluster kernel when the shape allows
+  // (gemm_tcgen05_ln.cu), else the projection and then the LayerNorm kernel.
+  auto residual_then_norm = [&](LinearArgs& l, const LNp& P, float* fp32_out) -> int {
+    if (tc) { l.ln_gamma = P.g; l.ln_beta = P.b; l.ln_out_split = xn_s; }
+    if (tc && tc_res_ln_ok(l)) return launch_linear_res_ln(l, s);
+    l.ln_out_split = nullptr;
+    SCV_TRY(launch_linear(l, 0, s));
+    return norm(P, fp32_out);
+  };
+
   EmbedArgs e;
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
   e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
   SCV_TRY(launch_embed(e, s));
 
   const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
+  float* h1_ = D->h1.as<float>() + (size_t)r0 * d;     // fp32 output of the head LayerNorm (CUDA-core path)
   for (int li = 0; li < c.num_layers; ++li) {
     const DecLayer& L = D->layers[li];
-    // ---- self attention (:1244-1296)
-    SCV_TRY(norm(L.n1, xn));
+    // ---- self attention (:1244-1296); norm1 of layers >= 1 was produced by the previous layer's linear2 kernel
+    if (li == 0) SCV_TRY(norm(L.n1, xn));
     LinearArgs a;
     a.x = xn; a.ldx = d; a.a_split = xn_s; a.w = L.sa_in_w; a.ldw = L.sa_in_ld; a.wt = L.sa_in_wt; a.bias = L.sa_in_b; a.y = qkv; a.ldy = 3 * d;
     a.M = B; a.N = 3 * d; a.K = d; a.done_flag = done;
@@ -451,9 +462,8 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     LinearArgs o = lin_args(attn, d, L.sa_out, x, d, B, ACT_NONE, done);
     o.residual = x; o.ldr = d; o.a_split = attn_s;
     next(o, L.ca_q_wt, d, d);
-    SCV_TRY(launch_linear(o, 0, s));
     // ---- cross attention to the memory tokens (:1299-1308)
-    SCV_TRY(norm(L.n2, xn));
+    SCV_TRY(residual_then_norm(o, L.n2, xn));
     LinearArgs q;
     q.x = xn; q.ldx = d; q.a_split = xn_s; q.w = L.ca_in_w; q.ldw = L.ca_in_ld; q.wt = L.ca_q_wt; q.bias = L.ca_in_b; q.y = q2; q.ldy = d;
     q.M = B; q.N = d; q.K = d; q.done_flag = done;
@@ -470,9 +480,8 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
     co.residual = x; co.ldr = d; co.a_split = attn_s;
     next(co, L.ff1.wt, dff, d);
-    SCV_TRY(launch_linear(co, 0, s));
     // ---- feed forward (:1311-1313)
-    SCV_TRY(norm(L.n3, xn));
+    SCV_TRY(residual_then_norm(co, L.n3, xn));
     LinearArgs f1 = lin_args(xn, d, L.ff1, ff, dff, B, ACT_GELU, done);
     f1.a_split = xn_s; f1.y_split = ff_s;
     next(f1, L.ff2.wt, d, dff);
@@ -480,14 +489,13 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     LinearArgs f2 = lin_args(ff, dff, L.ff2, x, d, B, ACT_NONE, done);
     f2.residual = x; f2.ldr = d; f2.a_split = ff_s;
     if (li + 1 < c.num_layers) next(f2, D->layers[li + 1].sa_in_wt, 3 * d, d); else next(f2, D->out_a.wt, d, d);
-    SCV_TRY(launch_linear(f2, 0, s));
+    SCV_TRY(residual_then_norm(f2, li + 1 < c.num_layers ? D->layers[li + 1].n1 : D->out_ln, li + 1 < c.num_layers ? xn : h1_));
   }
   // ---- heads (:1413, 1417, 1439)
   float* h1 = D->h1.as<float>() + (size_t)r0 * d; float* h2 = D->h2.as<float>() + (size_t)r0 * d;
   float* t3 = D->t3.as<float>() + (size_t)r0 * (d / 4);
   float* logits = D->logits.as<float>() + (size_t)r0 * c.vocab_size;
   float* tlog = D->tlog.as<float>() + (size_t)r0 * 8; float* slog = D->slog.as<float>() + r0;
-  SCV_TRY(norm(D->out_ln, h1));
   LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done);
   oa.a_split = xn_s; oa.y_split = h2_s;
   next(oa, D->out_b.wt, c.vocab_size, d);
