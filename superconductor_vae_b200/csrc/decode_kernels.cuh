@@ -47,6 +47,26 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 
+// ---- small-batch persistent step (decode_small.cu): the step as a list of phases separated by grid barriers
+struct SmallOp {               // y = act(LN?(x) W^T + b) (+ residual) for all B rows
+  const float* in; int ld_in; int K;
+  const float* ln_g; const float* ln_b;          // LayerNorm of the input rows (null: none)
+  const __nv_bfloat16* w; int ldw;               // [N, ldw] row-major bf16, zero padded beyond K, ldw % 8 == 0
+  const float* bias; int N; int act;
+  const float* res; int ldr;                      // residual added after the activation (may alias out)
+  float* out; int ldo;
+};
+struct SmallPhase {
+  int kind;                                       // 0: up to four independent projections, 1: attention
+  int nops;
+  SmallOp op[4];
+  AttnArgs attn;
+};
+size_t small_step_smem_bytes();
+bool small_phase_fits(const SmallPhase& ph, int grid);
+int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const StepState* st, unsigned* bar, int grid,
+                        cudaStream_t s);
+
 struct SamplerArgs {
   const float* logits = nullptr; int ldl = 0;
   const float* type_logits = nullptr; int ldt = 0;

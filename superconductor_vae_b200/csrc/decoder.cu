@@ -86,6 +86,11 @@ struct scv_decoder {
   cudaEvent_t ev_fork = nullptr;
   int last_B = 0;
   int launches_per_step = 0;               // kernels in one step (what a replayed graph launches)
+  // small-batch persistent step (decode_small.cu)
+  DevBuf sm_phases, sm_bar, sm_h2b, sm_t3s, sm_t3d;
+  std::vector<SmallPhase> sm_host;
+  int sm_n_phases = 0, sm_grid = 0;
+  bool small_active = false;               // this call decodes through the persistent small-batch kernel
 
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
@@ -106,7 +111,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf, &seen, &dlog, &msplit})
+                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -372,6 +377,103 @@ static int ensure_workspace(scv_decoder* D, int B, int M) {
   return 0;
 }
 
+// Phase list of the small-batch persistent step: the same operations, buffers and order as decode_rows() below.
+static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B, int M) {
+  const scv_decoder_config& c = D->cfg;
+  const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward, pps = ceil_div(c.pe_len, kPagePos);
+  D->small_active = false;
+  static const int env = [] { const char* e = getenv("SCV_SMALL"); return e ? atoi(e) : 0; }();   // opt-in, see decode_small.cu
+  if (!env || B > 32 || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
+  if (D->sm_grid == 0) {
+    int dev = 0, sms = 0;
+    SCV_CUDA(cudaGetDevice(&dev));
+    SCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    D->sm_grid = sms;
+  }
+  // fixed sizes: a captured step holds these pointers, so they must never be reallocated
+  SCV_TRY(D->sm_bar.ensure(sizeof(unsigned)));
+  SCV_TRY(D->sm_h2b.ensure((size_t)32 * d * sizeof(float)));
+  SCV_TRY(D->sm_t3s.ensure((size_t)32 * d * sizeof(float)));
+  SCV_TRY(D->sm_t3d.ensure((size_t)32 * d * sizeof(float)));
+  SCV_TRY(D->sm_phases.ensure((size_t)(8 * c.num_layers + 3) * sizeof(SmallPhase)));
+  StepState* st = D->state.as<StepState>();
+  float* x = D->x.as<float>(); float* qkv = D->qkv.as<float>(); float* attn = D->attn.as<float>();
+  float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>(); float* h2 = D->h2.as<float>();
+  float* t3 = D->t3.as<float>();
+  std::vector<SmallPhase>& P = D->sm_host;
+  P.clear();
+  auto op = [](const float* in, int ld_in, int K, const LNp* ln, const __nv_bfloat16* w, int ldw, const float* bias,
+               int N, int act, const float* res, int ldr, float* out, int ldo) {
+    SmallOp o;
+    o.in = in; o.ld_in = ld_in; o.K = K; o.ln_g = ln ? ln->g : nullptr; o.ln_b = ln ? ln->b : nullptr;
+    o.w = w; o.ldw = ldw; o.bias = bias; o.N = N; o.act = act; o.res = res; o.ldr = ldr; o.out = out; o.ldo = ldo;
+    return o;
+  };
+  auto lin = [&](const float* in, int ld_in, const LNp* ln, const Lin& L, int act, const float* res, float* out, int ldo) {
+    return op(in, ld_in, L.K, ln, L.w, L.ldw, L.b, L.N, act, res, ldo, out, ldo);
+  };
+  auto gemv = [&](std::initializer_list<SmallOp> ops) {
+    SmallPhase ph;
+    ph.kind = 0; ph.nops = 0;
+    for (const SmallOp& o : ops) ph.op[ph.nops++] = o;
+    P.push_back(ph);
+  };
+  const float scale = (float)(1.0 / std::sqrt((double)hd));
+  const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& L = D->layers[li];
+    gemv({op(x, d, d, &L.n1, L.sa_in_w, L.sa_in_ld, L.sa_in_b, 3 * d, ACT_NONE, nullptr, 0, qkv, 3 * d)});
+    SmallPhase sa;
+    sa.kind = 1; sa.nops = 0;
+    sa.attn.q = qkv; sa.attn.ldq = 3 * d; sa.attn.knew = qkv + d; sa.attn.vnew = qkv + 2 * d; sa.attn.ldn = 3 * d;
+    sa.attn.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
+    sa.attn.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d;
+    sa.attn.page_table = D->ptab.as<int>(); sa.attn.pages_per_seq = pps; sa.attn.page_stride = page_stride;
+    sa.attn.row_stride = d; sa.attn.out = attn; sa.attn.ldo = d; sa.attn.B = B; sa.attn.nhead = c.nhead; sa.attn.hd = hd;
+    sa.attn.scale = scale; sa.attn.fixed_len = -1; sa.attn.max_n = std::max(c.pe_len, M); sa.attn.st = st;
+    P.push_back(sa);
+    gemv({lin(attn, d, nullptr, L.sa_out, ACT_NONE, x, x, d)});
+    gemv({op(x, d, d, &L.n2, L.ca_in_w, L.ca_in_ld, L.ca_in_b, d, ACT_NONE, nullptr, 0, q2, d)});
+    SmallPhase ca;
+    ca.kind = 1; ca.nops = 0;
+    float* ckv = D->ckv.as<float>() + (size_t)li * B * M * 2 * d;
+    ca.attn.q = q2; ca.attn.ldq = d; ca.attn.kcache = ckv; ca.attn.vcache = ckv + d; ca.attn.seq_stride = (long long)M * 2 * d;
+    ca.attn.row_stride = 2 * d; ca.attn.out = attn; ca.attn.ldo = d; ca.attn.B = B; ca.attn.nhead = c.nhead; ca.attn.hd = hd;
+    ca.attn.scale = scale; ca.attn.fixed_len = M; ca.attn.max_n = std::max(c.pe_len, M); ca.attn.st = st;
+    P.push_back(ca);
+    gemv({lin(attn, d, nullptr, L.ca_out, ACT_NONE, x, x, d)});
+    gemv({lin(x, d, &L.n3, L.ff1, ACT_GELU, nullptr, ff, dff)});
+    gemv({lin(ff, dff, nullptr, L.ff2, ACT_NONE, x, x, d)});
+  }
+  const bool type = A->type_masks != nullptr, stop = A->stop_boost > 0.f, dup = A->site_dup_threshold > 0.f;
+  float* h2b = D->sm_h2b.as<float>(); float* t3s = D->sm_t3s.as<float>(); float* t3d = D->sm_t3d.as<float>();
+  {
+    SmallPhase ph;
+    ph.kind = 0; ph.nops = 0;
+    ph.op[ph.nops++] = lin(x, d, &D->out_ln, D->out_a, ACT_GELU, nullptr, h2, d);
+    if (type) ph.op[ph.nops++] = lin(x, d, &D->tt_ln, D->tt_a, ACT_GELU, nullptr, h2b, d);
+    if (stop) ph.op[ph.nops++] = lin(x, d, nullptr, D->stop_a, ACT_GELU, nullptr, t3s, d / 4);
+    if (dup) ph.op[ph.nops++] = lin(x, d, nullptr, D->dup_a, ACT_GELU, nullptr, t3d, d / 4);
+    P.push_back(ph);
+  }
+  {
+    SmallPhase ph;
+    ph.kind = 0; ph.nops = 0;
+    ph.op[ph.nops++] = lin(h2, d, nullptr, D->out_b, ACT_NONE, nullptr, D->logits.as<float>(), c.vocab_size);
+    if (type) ph.op[ph.nops++] = lin(h2b, d, nullptr, D->tt_b, ACT_GELU, nullptr, t3, d / 4);
+    if (stop) ph.op[ph.nops++] = lin(t3s, d / 4, nullptr, D->stop_b, ACT_NONE, nullptr, D->slog.as<float>(), 1);
+    if (dup) ph.op[ph.nops++] = lin(t3d, d / 4, nullptr, D->dup_b, ACT_NONE, nullptr, D->dlog.as<float>(), 1);
+    P.push_back(ph);
+  }
+  if (type) gemv({lin(t3, d / 4, nullptr, D->tt_c, ACT_NONE, nullptr, D->tlog.as<float>(), 8)});
+  for (const SmallPhase& ph : P)
+    if (!small_phase_fits(ph, D->sm_grid)) return 0;          // some shape does not fit: the per-projection path decodes
+  SCV_REQUIRE(P.size() <= (size_t)(8 * c.num_layers + 3), "small-batch step: phase list overflow");
+  D->sm_n_phases = (int)P.size();
+  D->small_active = true;
+  return 0;
+}
+
 // One decode step for rows [r0, r0 + B) of the call's batch (a sub-batch; every buffer is row-major by batch row and
 // the SplitTile buffers are tiled by 128 rows, so a sub-batch is a pointer offset).  phase 1 = everything up to and
 // including the first sampler kernel, phase 2 = the second sampler kernel (sampling / entropy only).
@@ -437,6 +539,11 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
   e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
   SCV_TRY(launch_embed(e, s));
+  if (D->small_active) {     // layers and heads in one persistent kernel (decode_small.cu); its barrier counter starts at 0
+    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, sizeof(unsigned), s));
+    SCV_TRY(launch_decode_small(D->sm_phases.as<SmallPhase>(), D->sm_n_phases, B, st, D->sm_bar.as<unsigned>(), D->sm_grid, s));
+    return launch_sampler(sp, 1, s);
+  }
 
   const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
   float* h1_ = D->h1.as<float>() + (size_t)r0 * d;     // fp32 output of the head LayerNorm (CUDA-core path)
@@ -572,6 +679,9 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   if (A->want_log_probs) SCV_CUDA(cudaMemsetAsync(D->o_lp.p, 0, io * sizeof(float), s));
   if (A->want_entropy) SCV_CUDA(cudaMemsetAsync(D->o_ent.p, 0, io * sizeof(float), s));
   A = &G;
+  SCV_TRY(build_small_phases(D, A, B, M));
+  if (D->small_active)
+    SCV_CUDA(cudaMemcpyAsync(D->sm_phases.p, D->sm_host.data(), D->sm_host.size() * sizeof(SmallPhase), cudaMemcpyHostToDevice, s));
   // per-layer K/V projection of the memory tokens, once per call instead of once per step and layer
   // (the reference re-projects them inside nn.MultiheadAttention at every step, :1302-1307)
   void* mem_split = nullptr;

@@ -448,3 +448,27 @@ def test_config2_4096_latents_properties(golden_dir):
     # every row that finished ends with END exactly once up to its length
     fl = DO.first_end_lengths(tc)
     assert int((tc == 2).any(dim=1).sum()) >= 1 and int(fl.max()) <= tc.shape[1]
+
+
+# ------------------------------------------------------------------------------------------ opt-in kernels
+@pytest.mark.gpu
+def test_optin_kernels_match_default_tokens():
+    """The opt-in kernels (persistent small-batch step, fused residual + LayerNorm cluster projection, persistent
+    tcgen05 projection) must decode the same greedy tokens as the default path: 32 rows (the small-batch kernel's
+    range) and 640 rows (multi-wave projections), with and without masks / stop head."""
+    import subprocess
+    import sys as _sys
+    script = os.path.join(os.path.dirname(__file__), "optin_check.py")
+
+    def digest(extra):
+        env = dict(os.environ)
+        env.update(extra)
+        r = subprocess.run([_sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")]
+        assert line, r.stdout[-2000:]
+        return line[0]
+
+    base = digest({})
+    for extra in ({"SCV_SMALL": "1"}, {"SCV_FUSE_LN": "1"}, {"SCV_GEMM_PERSISTENT": "1"}):
+        assert digest(extra) == base, f"{extra} decodes different tokens"
