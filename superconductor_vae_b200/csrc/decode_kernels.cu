@@ -225,20 +225,51 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   // scores: UNR * PPI positions in flight per warp (UNR 2 and 8 both measured ~2.5 % slower per decode: fewer
   // loads in flight, or fewer resident warps)
   constexpr int UNR = 4;
+  // ncu (r01n): issue slots 61-73 % busy at 46-77 % of the DRAM peak, i.e. instruction issue limits this kernel as much
+  // as HBM does.  Two savings: (1) one page lookup and one 64-bit base per iteration (the UNR * PPI positions of an
+  // iteration never straddle a 16-position page), (2) for 16 lanes per position the four dot products of an iteration
+  // are reduced together (5 shuffles instead of 16; same pairing order, so the sums are bit-identical).
+  constexpr bool kFastAddr = UNR * PPI <= kPagePos;
+  const long long kv_delta = a.vcache - a.kcache;
+  auto iter_base = [&](int p0) -> const float* {     // K row of position p0 for this lane's head slice
+    if (paged) return a.kcache + (size_t)pt[p0 >> kPageShift] * a.page_stride + (size_t)(p0 & (kPagePos - 1)) * a.row_stride + h * hd + e0;
+    return a.kcache + (size_t)b * a.seq_stride + (size_t)p0 * a.row_stride + h * hd + e0;
+  };
   for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
     float4 kv[UNR];
+    const float* kb = kFastAddr ? iter_base(p0) : nullptr;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int p = p0 + u * PPI + grp;
-      kv[u] = (p < n && e_ok) ? __ldcs(reinterpret_cast<const float4*>(a.kcache + row_off(p) + e0)) : zero4;
+      if (kFastAddr) kv[u] = (p < n && e_ok) ? __ldcs(reinterpret_cast<const float4*>(kb + (u * PPI + grp) * a.row_stride)) : zero4;
+      else kv[u] = (p < n && e_ok) ? __ldcs(reinterpret_cast<const float4*>(a.kcache + row_off(p) + e0)) : zero4;
     }
+    float d[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      float d = fmaf(q4.x, kv[u].x, fmaf(q4.y, kv[u].y, fmaf(q4.z, kv[u].z, q4.w * kv[u].w)));
+    for (int u = 0; u < UNR; ++u) d[u] = fmaf(q4.x, kv[u].x, fmaf(q4.y, kv[u].y, fmaf(q4.z, kv[u].z, q4.w * kv[u].w)));
+    if constexpr (LPP == 16 && UNR == 4) {
+      const int sub = lane & 15;
+      const bool up8 = (sub & 8) != 0, up4 = (sub & 4) != 0;
+      // level 1 (partner lane ^ 8): lower half keeps positions u = 0, 1, upper half keeps u = 2, 3
+      const float r0 = __shfl_xor_sync(0xffffffffu, up8 ? d[0] : d[2], 8);
+      const float r1 = __shfl_xor_sync(0xffffffffu, up8 ? d[1] : d[3], 8);
+      const float e0s = (up8 ? d[2] : d[0]) + r0, e1s = (up8 ? d[3] : d[1]) + r1;
+      // level 2 (partner lane ^ 4): keep one of the two
+      float f = (up4 ? e1s : e0s) + __shfl_xor_sync(0xffffffffu, up4 ? e0s : e1s, 4);
+      f += __shfl_xor_sync(0xffffffffu, f, 2);
+      f += __shfl_xor_sync(0xffffffffu, f, 1);
+      const int u_mine = 2 * (sub >> 3) + ((sub >> 2) & 1);
+      const int p = p0 + u_mine * PPI + grp;
+      if ((sub & 3) == 0 && p < n) sc[p] = f * a.scale;
+    } else {
 #pragma unroll
-      for (int o = LPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      const int p = p0 + u * PPI + grp;
-      if ((lane % LPP) == 0 && p < n) sc[p] = d * a.scale;
+      for (int u = 0; u < UNR; ++u) {
+        float dd = d[u];
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        const int p = p0 + u * PPI + grp;
+        if ((lane % LPP) == 0 && p < n) sc[p] = dd * a.scale;
+      }
     }
   }
   __syncwarp();
@@ -260,11 +291,13 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
     float4 vv[UNR];
     float w[UNR];
+    const float* vb = kFastAddr ? iter_base(p0) + kv_delta : nullptr;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int p = p0 + u * PPI + grp;
       const bool ok = p < n && e_ok;
-      vv[u] = ok ? __ldcs(reinterpret_cast<const float4*>(a.vcache + row_off(p) + e0)) : zero4;
+      if (kFastAddr) vv[u] = ok ? __ldcs(reinterpret_cast<const float4*>(vb + (u * PPI + grp) * a.row_stride)) : zero4;
+      else vv[u] = ok ? __ldcs(reinterpret_cast<const float4*>(a.vcache + row_off(p) + e0)) : zero4;
       w[u] = ok ? sc[p] : 0.f;
     }
 #pragma unroll
