@@ -26,7 +26,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/scvae_nccl_debug.%h.%p")   # NCCL prints its version banner to stdout otherwise; stdout must stay one JSON line
+# stdout must carry the JSON lines only: NCCL (and anything else in native code) prints its banner to fd 1, so fd 1 is
+# pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 METRIC = "formulas/sec (KV-cache decode, bf16)"
 UNIT = "formulas/s"
@@ -138,7 +146,7 @@ def run_reference(args, rank, world):
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
     sample = (f"{rows} latents of the config-2 workload per step (the 4096-latent batch is bounded to {rows} rows "
               f"for the CPU), {L} executed steps, torch {threads} threads, fp32")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -222,7 +230,7 @@ def run_engine(args, rank, local_rank, world):
             step_resident()
         t = step_resident()
         torch.cuda.synchronize()
-        print(json.dumps({"ncu_run": True, "executed_decode_steps": int(t.shape[1]),
+        emit(({"ncu_run": True, "executed_decode_steps": int(t.shape[1]),
                           "launches_per_decode": _lib.launch_count() // (args.warmup + 1)}))
         return
 
@@ -307,7 +315,7 @@ def run_engine(args, rank, local_rank, world):
             "tensor_algorithmic_tflops": algorithmic_flops(B, L) / (per_gpu_ms * 1e9),
             "tensor_frac": algorithmic_flops(B, L) / (per_gpu_ms * 1e9) / pk["bf16_tflops_sustained"],
             "note": "SURVEY 8d cost model over the executed steps, fp32 KV cache (49,152 B per cached position)"}
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 weights, fp32 activations/accumulate/KV", "data": "synthetic",

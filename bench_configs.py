@@ -13,7 +13,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/scvae_nccl_debug.%h.%p")   # NCCL prints its version banner to stdout otherwise; stdout must stay one JSON line
+# stdout must carry the JSON lines only: NCCL (and anything else in native code) prints its banner to fd 1, so fd 1 is
+# pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 import torch
 import torch.distributed as dist
@@ -63,7 +71,7 @@ def main():
         fn = lambda: dec.sample_for_reinforce(z, stoich_pred=st, temperature=1.2, max_len=64, stop_boost=10.0,
                                               heads_pred=hp, _seed=7)
         ms, (t, lp, en, mk) = timed(fn)
-        print(json.dumps({"config": 3, "what": "RLOO rollouts: 2048 latents x 4 samples, temperature 1.2, per-token log-probs, "
+        emit(({"config": 3, "what": "RLOO rollouts: 2048 latents x 4 samples, temperature 1.2, per-token log-probs, "
                           "entropy and mask (stop_boost 10, no hard masks so the reference's H2 fallback cannot trip)",
                           "rows": B * k, "executed_decode_steps": int(t.shape[1]), "ms": ms,
                           "formulas_per_s": B * k / (ms / 1e3), "mean_len": float(mk.sum(1).mean())}))
@@ -77,7 +85,7 @@ def main():
             st, hp = enc.conditioning(z)
             return dec.precompute_memory(z, None, st, hp)
         ms, mem = timed(fn)
-        print(json.dumps({"config": 5, "what": "three-branch encoder + all heads + memory tokens on 52,800 synthetic compositions",
+        emit(({"config": 5, "what": "three-branch encoder + all heads + memory tokens on 52,800 synthetic compositions",
                           "rows": n, "ms": ms, "rows_per_s": n / (ms / 1e3), "memory_shape": list(mem.shape),
                           "algorithmic_tflops": n * 103.4e6 / (ms * 1e9)}))
 
@@ -117,7 +125,7 @@ def main():
             dt = float(tmax)
         if rank == 0:
             lens = (gathered == 2).int().argmax(dim=1) + 1
-            print(json.dumps({"config": 4, "what": "SLERP latents -> heads_from_latent -> greedy decode (masks + stop head), "
+            emit(({"config": 4, "what": "SLERP latents -> heads_from_latent -> greedy decode (masks + stop head), "
                               "sharded over ranks, gather of int16 token ids", "latents": N, "n_gpus": world,
                               "seconds": dt, "formulas_per_s": N / dt, "max_len_gathered": int(gathered.shape[1]),
                               "mean_formula_len": float(lens.float().mean()), "sample": tok.decode_batch(gathered[:2])}))
