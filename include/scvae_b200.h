@@ -153,6 +153,13 @@ int scv_encoder_heads(scv_encoder* enc, int32_t batch, const float* z, const scv
 int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const int32_t* i2, const float* t,
                    int64_t n_rows, float* out, int32_t* fallback_flag_dev, void* stream);
 
+/* Candidate post-processing (replaces the per-row Python loop of tokens_to_formula,
+ * scripts/holdout/holdout_search.py:88-99, and FractionAwareTokenizer.decode, tokenizer/fraction_tokenizer.py:478-519,
+ * at scale): tokens [n_rows, row_len] int64 -> canonical [n_rows, row_len] int16 (ids up to the first END, PAD after),
+ * hash [n_rows] (64-bit FNV-1a of the canonical ids) and, if not NULL, length [n_rows] (position of the first END). */
+int scv_tokens_canonical_hash(const int64_t* tokens, int64_t n_rows, int32_t row_len, int16_t* canonical,
+                              uint64_t* hash, int32_t* length, void* stream);
+
 /* ---------------------------------------------------------------- kernel-level taps (tests) */
 /* y[M,N] = act(x[M,K] * w[N,K]^T + bias) (+ residual); w is bf16 with row stride ldw (elements).
  * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 1 SIMT fp32 (w_bf16 row-major), 2 tcgen05 hi/lo bf16

@@ -14,3 +14,20 @@ def slerp(z1: torch.Tensor, z2: torch.Tensor, t) -> torch.Tensor:
         return (1 - t) * z1 + t * z2
     mag = (1 - t) * z1.norm(dim=-1, keepdim=True) + t * z2.norm(dim=-1, keepdim=True)
     return (torch.sin((1 - t) * omega) / so * n1 + torch.sin(t * omega) / so * n2) * mag
+
+
+def unique_formulas(tokens, decode):
+    """Reference semantics of candidate post-processing (scripts/holdout/holdout_search.py:88-99 applied to every row,
+    then grouped): formulas[i] = decode(row i); returns (distinct formulas in first-occurrence order, index of each
+    row's formula in that list, counts).  `decode` is FractionAwareTokenizer.decode (stops at the first END)."""
+    seen, order, inverse, counts = {}, [], [], []
+    for row in tokens.tolist():
+        f = decode(row)
+        if f not in seen:
+            seen[f] = len(order)
+            order.append(f)
+            counts.append(0)
+        inverse.append(seen[f])
+        counts[seen[f]] += 1
+    return order, inverse, counts
+

@@ -85,6 +85,8 @@ SIGNATURES = {
     "scv_encoder_heads": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(EncoderHeadsOut), C.c_void_p]),
     "scv_slerp_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "scv_tokens_canonical_hash": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "scv_op_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p]),

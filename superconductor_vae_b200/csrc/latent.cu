@@ -79,3 +79,53 @@ extern "C" int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* 
   SCV_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Candidate post-processing at scale (scripts/holdout/holdout_search.py:88-99 turns every generated row
+// into a string with a Python loop, the wall-clock bottleneck at 1 M candidates).  A formula is the tokens up to the
+// first END with PAD / START skipped (tokenizer/fraction_tokenizer.py:478-519), so rows are canonicalised (everything
+// from the first END on -> PAD, ids narrowed to int16) and hashed on the device; the host then groups identical rows
+// and builds strings for the unique ones only.  One warp per row; hash = 64-bit FNV-1a over the canonical ids.
+// ---------------------------------------------------------------------------------------------
+namespace scv {
+static __global__ void canonical_hash_kernel(const long long* __restrict__ tokens, long long n_rows, int L,
+                                      short* __restrict__ canon, unsigned long long* __restrict__ hash,
+                                      int* __restrict__ length) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const long long* tr = tokens + row * L;
+  // first END position of the row (L if none)
+  int first_end = L;
+  for (int p0 = 0; p0 < L; p0 += 32) {
+    const int p = p0 + lane;
+    const bool is_end = p < L && tr[p] == kEndIdx;
+    const unsigned m = __ballot_sync(0xffffffffu, is_end);
+    if (m != 0u) { first_end = p0 + __ffs(m) - 1; break; }
+  }
+  for (int p = lane; p < L; p += 32) canon[row * L + p] = p < first_end ? (short)tr[p] : (short)0;
+  if (lane == 0) {
+    unsigned long long h = 1469598103934665603ull;
+    for (int p = 0; p < first_end; ++p) {
+      const unsigned long long t = (unsigned long long)tr[p];
+      h = (h ^ (t & 0xffull)) * 1099511628211ull;
+      h = (h ^ ((t >> 8) & 0xffull)) * 1099511628211ull;
+    }
+    hash[row] = h;
+    if (length != nullptr) length[row] = first_end;
+  }
+}
+}  // namespace scv
+
+extern "C" int scv_tokens_canonical_hash(const int64_t* tokens, int64_t n_rows, int32_t row_len, int16_t* canonical,
+                                         uint64_t* hash, int32_t* length, void* stream) {
+  SCV_REQUIRE(tokens && canonical && hash && n_rows > 0 && row_len > 0, "canonical_hash: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long threads = n_rows * 32;
+  scv::canonical_hash_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const long long*>(tokens), (long long)n_rows, row_len, canonical,
+      reinterpret_cast<unsigned long long*>(hash), length);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+

@@ -60,3 +60,41 @@ def decode_z_batch(encoder, decoder, z: torch.Tensor, temperature: float = 0.001
         z=z, stoich_pred=stoich, temperature=temperature, max_len=max_len, heads_pred=heads, type_masks=type_masks,
         stop_boost=stop_boost, hard_stop_threshold=hard_stop_threshold, return_log_probs=return_log_probs)
     return (toks, lps) if return_log_probs else toks
+
+
+@torch.no_grad()
+def unique_sequences(tokens: torch.Tensor):
+    """Group identical generated rows on the device.
+
+    tokens [N, L] int64 on CUDA -> (unique_rows int16 [U, L] (ids up to the first END, PAD after), inverse int64 [N]
+    (row -> index into unique_rows), counts int64 [U], lengths int32 [N]).  A row's formula depends only on the ids
+    before its first END (tokenizer decode), so rows are canonicalised and hashed by one kernel
+    (scv_tokens_canonical_hash), grouped by hash with torch.unique, and every row is then compared with its group's
+    representative; a hash collision (never observed) falls back to an exact row-wise unique."""
+    L = _lib.lib()
+    _lib.require_cuda(tokens, "tokens")
+    dev = tokens.device
+    tokens = tokens.to(torch.int64).contiguous()
+    n, ln = tokens.shape
+    canon = torch.empty((n, ln), dtype=torch.int16, device=dev)
+    hsh = torch.empty((n,), dtype=torch.int64, device=dev)        # 64-bit pattern; only equality matters
+    lengths = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.scv_tokens_canonical_hash(_lib.ptr(tokens), n, ln, _lib.ptr(canon), _lib.ptr(hsh), _lib.ptr(lengths),
+                                               _lib.current_stream()), "tokens_canonical_hash")
+    _, inverse, counts = torch.unique(hsh, return_inverse=True, return_counts=True)
+    first = torch.full((counts.numel(),), n, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inverse, torch.arange(n, device=dev), reduce="amin")
+    uniq = canon[first]
+    if not bool((canon == uniq[inverse]).all()):                  # two different rows with one hash
+        uniq, inverse, counts = torch.unique(canon, dim=0, return_inverse=True, return_counts=True)
+    return uniq, inverse, counts, lengths
+
+
+@torch.no_grad()
+def decode_unique(tokenizer, tokens: torch.Tensor):
+    """tokens [N, L] -> (formulas of the U distinct rows, inverse [N], counts [U]): strings are built once per distinct
+    candidate instead of once per row (the reference loops over every row, scripts/holdout/holdout_search.py:88-99)."""
+    uniq, inverse, counts, _ = unique_sequences(tokens)
+    return tokenizer.decode_batch(uniq.to(torch.int64)), inverse, counts
+

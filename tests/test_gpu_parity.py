@@ -417,6 +417,43 @@ def test_slerp_matches_reference(golden_dir):
     torch.testing.assert_close(out.cpu(), g["slerp_parallel"], rtol=1e-5, atol=1e-5)
 
 
+def test_unique_sequences_and_decode_unique():
+    """rows grouped on the device by the ids before their first END; strings built once per distinct row.
+    Checked against the reference semantics (decode every row, then group: oracle/latent.py unique_formulas)."""
+    from oracle import latent as OL
+    tok = S.FractionAwareTokenizer(max_len=24, fractions=[f"{i + 1}/997" for i in range(64)])
+    gen = torch.Generator().manual_seed(5)
+    n, ln = 6000, 23
+    pool = torch.randint(3, tok.vocab_size, (40, ln), generator=gen)              # 40 base rows -> many duplicates
+    rows = pool[torch.randint(0, 40, (n,), generator=gen)].clone()
+    ends = torch.randint(0, ln + 4, (n,), generator=gen)                          # >= ln: the row has no END
+    for r in range(n):
+        e = int(ends[r]) % 7 if r % 3 == 0 else int(ends[r])
+        if e < ln:
+            rows[r, e] = 2
+            rows[r, e + 1:] = torch.randint(0, tok.vocab_size, (ln - e - 1,), generator=gen)   # garbage after END
+    rows[::50, 0] = 0                                                              # a PAD before the END is skipped by decode
+    formulas, inverse, counts = S.latent.decode_unique(tok, rows.to(DEV))
+    uniq, inv2, cnt2, lengths = S.latent.unique_sequences(rows.to(DEV))
+    assert torch.equal(inverse, inv2) and torch.equal(counts, cnt2)
+    assert int(counts.sum()) == n and len(formulas) == counts.numel()
+    ref_formulas, ref_inverse, ref_counts = OL.unique_formulas(rows, tok.decode)
+    inv = inverse.cpu().tolist()
+    assert all(formulas[inv[r]] == ref_formulas[ref_inverse[r]] for r in range(n))
+    # per-formula totals agree (distinct id rows may spell the same formula; the device groups by ids)
+    agg = {}
+    for f, c in zip(formulas, counts.cpu().tolist()):
+        agg[f] = agg.get(f, 0) + c
+    assert agg == dict(zip(ref_formulas, ref_counts))
+    assert counts.numel() < n // 4                                                # duplicates were actually merged
+    first_end = [(r.tolist() + [2]).index(2) for r in rows]
+    assert lengths.cpu().tolist() == first_end
+    # every row equals its representative up to its first END
+    rep = uniq[inverse].cpu()
+    for r in range(0, n, 37):
+        assert rep[r, :first_end[r]].tolist() == rows[r, :first_end[r]].tolist() and int(rep[r, first_end[r]:].abs().sum()) == 0
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_config2_4096_latents_properties(golden_dir):
     """BASELINE config 2 at full size (4096 latents, masks + stop head, greedy): bit-exact vs the oracle on the
