@@ -276,7 +276,10 @@ def run_engine(args, rank, local_rank, world):
                     "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                     "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "launches": v["launches"],
                     "avg_launch_us": 1e3 * v["ms"] / v["launches"],
-                    "algorithmic_flops_per_launch": v["flops"] / v["launches"]}
+                    "algorithmic_flops_per_launch": v["flops"] / v["launches"],
+                    # the tensor pipe executes two MMAs (bf16 hi and lo halves of every fp32 activation) per weight
+                    # tile, so it is this busy; `achieved` / `frac` count each multiply-add once
+                    "frac_executed_on_pipe": (2.0 * ach / pk["bf16_tflops_sustained"]) if name == "gemm_tcgen05" else None}
         else:
             ach = v["bytes"] / (v["ms"] * 1e6)
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
