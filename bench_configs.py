@@ -60,7 +60,7 @@ def main():
     tok = FractionAwareTokenizer(max_len=64, fractions=[f"{i + 1}/100003" for i in range(4317)],
                                  isotopes=[f"{300 + i}Og" for i in range(291)])
     masks = tok.get_type_masks(dev)
-    todo = [int(c) for c in args.configs.split(",")]
+    todo = [int(c) if c.isdigit() else c for c in args.configs.split(",")]
 
     if 3 in todo and rank == 0:
         # RLOO: 2048 latents x k = 4 samples (sample-major repeat), temperature 1.2, log-probs + entropy + mask
@@ -89,6 +89,22 @@ def main():
                           "rows": n, "ms": ms, "rows_per_s": n / (ms / 1e3), "memory_shape": list(mem.shape),
                           "algorithmic_tflops": n * 103.4e6 / (ms * 1e9)}))
 
+    if "f3" in todo and rank == 0:
+        # teacher-forced forward: 256 sequences x 63 positions in one pass
+        Bf, Lf = 256, 64
+        z = Sy.make_latents(Bf, 2048, 1234).to(dev)
+        st, hp = Sy.make_conditioning(Bf, 13, 1234)
+        st, hp = st.to(dev), {k: v.to(dev) for k, v in hp.items()}
+        g = torch.Generator().manual_seed(3)
+        tgt = torch.randint(3, dec.vocab_size, (Bf, Lf), generator=g)
+        tgt[:, 0] = 1
+        tgt[::2, 40:] = 0
+        tgt = tgt.to(dev)
+        mem = dec.precompute_memory(z, None, st, hp)
+        ms, out = timed(lambda: dec(z, tgt, cached_memory=mem), warmup=2, iters=5)
+        emit(({"config": "f3", "what": "teacher-forced forward, 256 sequences x 63 positions (16,128 rows per projection), "
+                                       "logits + stop / type / site-dup heads at every position", "ms": ms,
+               "positions_per_s": Bf * (Lf - 1) / (ms / 1e3), "logits_shape": list(out[0].shape)}))
     if 4 in todo:
         # 1M SLERP-interpolated latents between 1024 anchors, conditioning from z alone (notebook pipeline),
         # greedy decode with masks + stop head, rows sharded over the ranks, NCCL gather of token ids only

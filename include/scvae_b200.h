@@ -98,6 +98,24 @@ typedef struct scv_generate_args {
 /* Enqueues the decode loop and synchronises `stream` once at the end to read *out_steps. */
 int scv_decoder_generate(scv_decoder* dec, const scv_generate_args* args, void* stream);
 
+/* Teacher-forced forward, teacher_forcing_ratio = 1.0 (EnhancedTransformerDecoder.forward,
+ * models/autoregressive_decoder.py:901-985): every position of every row in one pass -- projections with
+ * batch * seq_len rows, causal self-attention with the key padding mask of :952 (input id == PAD), cross-attention to
+ * the row's memory tokens, then output_proj / stop_head / token_type_head / site_dup_head at every position. */
+typedef struct scv_forward_args {
+  int32_t batch;
+  int32_t seq_len;          /* L = target length - 1 (<= pe_len) */
+  int32_t n_memory;
+  const float* memory;      /* [batch, n_memory, d_model] fp32 */
+  const int64_t* tokens;    /* input ids target[:, :-1]: [batch, L], row stride ld_tokens elements */
+  int32_t ld_tokens;
+  float* out_logits;        /* [batch, L, vocab] */
+  float* out_stop;          /* [batch, L] or NULL */
+  float* out_type;          /* [batch, L, 5] or NULL */
+  float* out_dup;           /* [batch, L] or NULL; needs the site_dup_head weights */
+} scv_forward_args;
+int scv_decoder_forward(scv_decoder* dec, const scv_forward_args* args, void* stream);
+
 /* Debug taps (tests): copy engine-internal fp32 state of the LAST executed step to `dst`.
  * what: 0 final hidden [B,d]; 1 raw logits [B,V]; 2 type logits [B,5]; 3 stop logit [B] */
 int scv_decoder_debug_read(scv_decoder* dec, int32_t what, float* dst, int64_t numel, void* stream);

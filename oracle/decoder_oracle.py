@@ -183,6 +183,48 @@ def stop_logit(sd, x):
     return _lin(sd, "stop_head.2", F.gelu(_lin(sd, "stop_head.0", x)))
 
 
+def forward_teacher_forced(sd, nhead, z, target_tokens, encoder_skip=None, stoich_pred=None, cached_memory=None,
+                           heads_pred=None):
+    """EnhancedTransformerDecoder.forward with teacher_forcing_ratio = 1.0 (:901-985): all positions in parallel,
+    causal mask plus key padding mask (input token == PAD, :952), no final norm.  Returns
+    (logits [B,L,V], generated [B,L], stop_logits [B,L], type_logits [B,L,5], site_dup_logits [B,L] or None)."""
+    memory = cached_memory if cached_memory is not None else build_memory(sd, z, encoder_skip, stoich_pred, heads_pred, nhead)
+    inp = target_tokens[:, :-1]
+    B, L = inp.shape
+    pe = sd["pos_encoding.pe"]
+    if L > pe.shape[1]:
+        raise RuntimeError(f"sequence of {L} positions exceeds the PE buffer ({pe.shape[1]})")
+    x = F.embedding(inp, sd["token_embedding.weight"]) + pe[:, :L, :]
+    d = x.shape[-1]
+    hd = d // nhead
+    n_layers = infer_shape(sd)["num_layers"]
+    pos = torch.arange(L)
+    blocked = (pos[None, :] > pos[:, None])[None, None] | (inp == 0)[:, None, None, :]      # [B,1,L(query),L(key)]
+    M = memory.shape[1]
+    for li in range(n_layers):
+        p = f"transformer_decoder.layers.{li}."
+        xn = _ln(sd, p + "norm1", x)
+        q, k, v = F.linear(xn, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"]).chunk(3, dim=-1)
+        qh, kh, vh = _mha_heads(q, B, L, nhead), _mha_heads(k, B, L, nhead), _mha_heads(v, B, L, nhead)
+        sc = (torch.matmul(qh, kh.transpose(-2, -1)) * (hd ** -0.5)).masked_fill(blocked, float("-inf"))
+        a = torch.matmul(F.softmax(sc, dim=-1), vh).transpose(1, 2).contiguous().view(B, L, d)
+        x = x + _lin(sd, p + "self_attn.out_proj", a)
+        xn = _ln(sd, p + "norm2", x)
+        W, bvec = sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"]
+        qc = _mha_heads(F.linear(xn, W[:d], bvec[:d]), B, L, nhead)
+        kc = _mha_heads(F.linear(memory, W[d:2 * d], bvec[d:2 * d]), B, M, nhead)
+        vc = _mha_heads(F.linear(memory, W[2 * d:], bvec[2 * d:]), B, M, nhead)
+        wc = F.softmax(torch.matmul(qc, kc.transpose(-2, -1)) * (hd ** -0.5), dim=-1)
+        x = x + _lin(sd, p + "multihead_attn.out_proj", torch.matmul(wc, vc).transpose(1, 2).contiguous().view(B, L, d))
+        xn = _ln(sd, p + "norm3", x)
+        x = x + _lin(sd, p + "linear2", F.gelu(_lin(sd, p + "linear1", xn)))
+    logits = decode_logits(sd, x)
+    dup = None
+    if "site_dup_head.0.weight" in sd:
+        dup = _lin(sd, "site_dup_head.2", F.gelu(_lin(sd, "site_dup_head.0", x))).squeeze(-1)
+    return logits, logits.argmax(dim=-1), stop_logit(sd, x).squeeze(-1), type_logits(sd, x), dup
+
+
 def generate_with_kv_cache(
     sd, nhead, z, encoder_skip=None, stoich_pred=None, temperature: float = 1.0,
     top_k: Optional[int] = None, top_p: Optional[float] = None, max_len: Optional[int] = None,

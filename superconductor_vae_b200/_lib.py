@@ -38,6 +38,13 @@ class GenerateArgs(C.Structure):
         ("out_steps", C.POINTER(C.c_int32)), ("forced_tokens", C.c_void_p)]
 
 
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("seq_len", C.c_int32), ("n_memory", C.c_int32), ("memory", C.c_void_p),
+        ("tokens", C.c_void_p), ("ld_tokens", C.c_int32), ("out_logits", C.c_void_p), ("out_stop", C.c_void_p),
+        ("out_type", C.c_void_p), ("out_dup", C.c_void_p)]
+
+
 class EncoderConfig(C.Structure):
     _fields_ = [
         ("n_element_rows", C.c_int32), ("element_embed_dim", C.c_int32), ("n_attention_heads", C.c_int32),
@@ -85,6 +92,7 @@ SIGNATURES = {
     "scv_encoder_heads": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(EncoderHeadsOut), C.c_void_p]),
     "scv_slerp_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "scv_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scv_tokens_canonical_hash": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "scv_op_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

@@ -37,6 +37,28 @@ int launch_embed(const EmbedArgs& a, cudaStream_t s) {
   return 0;
 }
 
+__global__ void __launch_bounds__(128) embed_sequence_kernel(const __nv_bfloat16* __restrict__ table, int ld_table,
+                                                             const float* __restrict__ pe, int d,
+                                                             const long long* __restrict__ tokens, int ld_tokens, int L,
+                                                             int vocab, float* __restrict__ x,
+                                                             unsigned char* __restrict__ key_skip) {
+  const int r = blockIdx.x, b = r / L, t = r - b * L;
+  long long tok = tokens[(size_t)b * ld_tokens + t];
+  if (threadIdx.x == 0) key_skip[r] = tok == 0 ? 1 : 0;          // PAD_IDX keys are masked (:952)
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);          // the host validated the ids; never index outside the table
+  const __nv_bfloat16* row = table + (size_t)tok * ld_table;
+  const float* per = pe + (size_t)t * d;
+  float* xr = x + (size_t)r * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) xr[i] = __bfloat162float(row[i]) + per[i];
+}
+
+int launch_embed_sequence(const __nv_bfloat16* table, int ld_table, const float* pe, int d, const long long* tokens,
+                          int ld_tokens, int B, int L, int vocab, float* x, unsigned char* key_skip, cudaStream_t s) {
+  embed_sequence_kernel<<<B * L, 128, 0, s>>>(table, ld_table, pe, d, tokens, ld_tokens, L, vocab, x, key_skip);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Flash-decode attention for ONE query token per (row, head): one warp per (row, head).
 //   self  (:1259-1290): append this step's k,v to the paged cache, attend over positions 0..step
@@ -191,14 +213,15 @@ template <int LPP>
 __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   extern __shared__ float sc_all[];
   pdl_wait();
-  if (a.st->done) return;
+  if (a.st != nullptr && a.st->done) return;
   constexpr int PPI = 32 / LPP;
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   if (gw >= a.B * a.nhead) return;
   const int b = gw / a.nhead, h = gw % a.nhead;
   const int hd = a.hd;
-  const int n = a.fixed_len >= 0 ? a.fixed_len : a.st->step + 1;
+  const int sb = a.rows_per_seq > 0 ? b / a.rows_per_seq : b;          // sequence whose K / V this query row attends to
+  const int n = a.fixed_len >= 0 ? a.fixed_len : (a.rows_per_seq > 0 ? b - sb * a.rows_per_seq + 1 : a.st->step + 1);
   float* sc = sc_all + (size_t)warp_in_block * a.max_n;
   const int grp = lane / LPP, e0 = 4 * (lane % LPP);
   const bool e_ok = e0 < hd;
@@ -207,7 +230,7 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   const int* pt = paged ? a.page_table + (size_t)b * a.pages_per_seq : nullptr;
   auto row_off = [&](int p) -> size_t {
     if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
-    return (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * hd;
+    return (size_t)sb * a.seq_stride + (size_t)p * a.row_stride + h * hd;
   };
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 q4 = e_ok ? *reinterpret_cast<const float4*>(a.q + (size_t)b * a.ldq + h * hd + e0) : zero4;
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   const long long kv_delta = a.vcache - a.kcache;
   auto iter_base = [&](int p0) -> const float* {     // K row of position p0 for this lane's head slice
     if (paged) return a.kcache + (size_t)pt[p0 >> kPageShift] * a.page_stride + (size_t)(p0 & (kPagePos - 1)) * a.row_stride + h * hd + e0;
-    return a.kcache + (size_t)b * a.seq_stride + (size_t)p0 * a.row_stride + h * hd + e0;
+    return a.kcache + (size_t)sb * a.seq_stride + (size_t)p0 * a.row_stride + h * hd + e0;
   };
   for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
     float4 kv[UNR];
@@ -273,6 +296,12 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
     }
   }
   __syncwarp();
+  if (a.key_skip != nullptr) {                 // padded keys take no weight (masked_fill(-inf) before the softmax)
+    const unsigned char* ks = a.key_skip + (size_t)sb * a.rows_per_seq;
+    for (int p = lane; p < n; p += 32)
+      if (ks[p] != 0) sc[p] = -INFINITY;
+    __syncwarp();
+  }
   float m = -INFINITY;
   for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
   m = warp_max(m);
@@ -346,6 +375,7 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   // algorithmic traffic: K and V rows of every attended position (fp32) + q, out, and the appended row
   ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
                  4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
+  SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
   if (v4) {
     const int lanes = a.hd / 4;
     if (lanes <= 4) SCV_CUDA(launch_k(attention_decode_v4_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a));

@@ -30,6 +30,9 @@ struct EmbedArgs {
   StepState* st;
 };
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
+// x[b * L + t] = token_embedding[tokens[b, t]] + pe[t] for every position (teacher-forced forward, :947-949)
+int launch_embed_sequence(const __nv_bfloat16* table, int ld_table, const float* pe, int d, const long long* tokens,
+                          int ld_tokens, int B, int L, int vocab, float* x, unsigned char* key_skip, cudaStream_t s);
 
 struct AttnArgs {
   const float* q = nullptr; int ldq = 0;
@@ -43,7 +46,12 @@ struct AttnArgs {
   int fixed_len = -1;                                    // cross: memory tokens; self: -1 -> step + 1
   int max_n = 0;                                         // smem scores per warp
   int host_len_hint = 0;                                 // host's view of step + 1 (profiling byte counts only)
-  const StepState* st = nullptr;
+  // Teacher-forced forward (all positions at once): query row r belongs to sequence r / rows_per_seq, position
+  // r % rows_per_seq; it attends over positions <= its own (self) of that sequence's contiguous K/V, skipping keys
+  // whose key_skip[sequence, position] byte is set (tgt_key_padding_mask, :952).  0 = one row per sequence (decode).
+  int rows_per_seq = 0;
+  const unsigned char* key_skip = nullptr;
+  const StepState* st = nullptr;                         // null: no done flag / step counter (forward)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 

@@ -87,6 +87,7 @@ struct scv_decoder {
   int last_B = 0;
   int launches_per_step = 0;               // kernels in one step (what a replayed graph launches)
   // small-batch persistent step (decode_small.cu)
+  DevBuf fw_skip;                          // teacher-forced forward: [B, L] key padding bytes
   DevBuf sm_phases, sm_bar, sm_h2b, sm_t3s, sm_t3d;
   std::vector<SmallPhase> sm_host;
   int sm_n_phases = 0, sm_grid = 0;
@@ -111,7 +112,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d})
+                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d, &fw_skip})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -799,6 +800,140 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   const StepState* hs = reinterpret_cast<const StepState*>(&D->pinned[2]);
   *A_user->out_steps = hs->done ? hs->out_len : hs->step;
   D->last_B = B;
+  return 0;
+}
+
+// Teacher-forced forward (:901-985, teacher_forcing_ratio = 1.0): the layer stack of decode_rows() applied to
+// R = batch * seq_len rows at once.  Row r = b * L + t is position t of sequence b; the self-attention of a row
+// attends over rows b * L .. r of the qkv buffer itself (no cache), skipping padded keys.
+int scv_decoder_forward(scv_decoder* D, const scv_forward_args* A, void* stream) {
+  SCV_REQUIRE(D && A, "forward: null argument");
+  SCV_REQUIRE(A->batch > 0 && A->seq_len > 0 && A->n_memory > 0 && A->memory && A->tokens && A->out_logits &&
+                  A->ld_tokens >= A->seq_len, "forward: bad arguments");
+  SCV_REQUIRE(scv_decoder_missing_weights(D) == 0, "forward: weights missing");
+  const scv_decoder_config& c = D->cfg;
+  SCV_REQUIRE(A->seq_len <= c.pe_len, "forward: %d positions exceed the positional-encoding buffer (%d)", A->seq_len, c.pe_len);
+  const bool have_dup = D->ws.loaded("site_dup_head.0.weight") && D->ws.loaded("site_dup_head.2.weight");
+  SCV_REQUIRE(A->out_dup == nullptr || have_dup, "forward: out_dup needs the site_dup_head weights");
+  const long long Rll = (long long)A->batch * A->seq_len;
+  SCV_REQUIRE(Rll <= 262144, "forward: %lld rows (batch * seq_len) exceed one call's limit of 262144", Rll);
+  const int B = A->batch, L = A->seq_len, M = A->n_memory, R = (int)Rll;
+  const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  set_pdl_for_call(true);
+  const size_t f = sizeof(float);
+  SCV_TRY(D->x.ensure((size_t)R * d * f)); SCV_TRY(D->xn.ensure((size_t)R * d * f));
+  SCV_TRY(D->qkv.ensure((size_t)R * 3 * d * f)); SCV_TRY(D->attn.ensure((size_t)R * d * f));
+  SCV_TRY(D->q2.ensure((size_t)R * d * f)); SCV_TRY(D->ff.ensure((size_t)R * dff * f));
+  SCV_TRY(D->h1.ensure((size_t)R * d * f)); SCV_TRY(D->h2.ensure((size_t)R * d * f));
+  SCV_TRY(D->t3.ensure((size_t)R * d * f)); SCV_TRY(D->tlog.ensure((size_t)R * 8 * f));
+  SCV_TRY(D->ckv.ensure((size_t)c.num_layers * B * M * 2 * d * f));
+  SCV_TRY(D->fw_skip.ensure((size_t)R));
+  const bool tc = use_tensor_cores(c, R);
+  if (tc) {
+    for (DevBuf* b : {&D->xn_s, &D->attn_s, &D->h2_s}) {
+      const size_t need = split_tile_bytes(R, d);
+      if (need > b->cap) { SCV_TRY(b->ensure(need)); SCV_CUDA(cudaMemset(b->p, 0, need)); }
+    }
+    const size_t need = split_tile_bytes(R, dff);
+    if (need > D->ff_s.cap) { SCV_TRY(D->ff_s.ensure(need)); SCV_CUDA(cudaMemset(D->ff_s.p, 0, need)); }
+  }
+  float* x = D->x.as<float>(); float* xn = D->xn.as<float>(); float* qkv = D->qkv.as<float>();
+  float* attn = D->attn.as<float>(); float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>();
+  float* h1 = D->h1.as<float>(); float* h2 = D->h2.as<float>(); float* t3 = D->t3.as<float>();
+  void* xn_s = tc ? D->xn_s.p : nullptr; void* attn_s = tc ? D->attn_s.p : nullptr;
+  void* ff_s = tc ? D->ff_s.p : nullptr; void* h2_s = tc ? D->h2_s.p : nullptr;
+  unsigned char* skip = D->fw_skip.as<unsigned char>();
+  const float scale = (float)(1.0 / std::sqrt((double)hd));
+  auto norm = [&](const LNp& P, float* fp32_out) -> int {
+    return tc ? launch_layernorm_split(x, d, P.g, P.b, xn_s, R, d, 1, nullptr, s)
+              : launch_layernorm(x, d, P.g, P.b, fp32_out, d, R, d, ACT_NONE, nullptr, s);
+  };
+  SCV_TRY(launch_embed_sequence(D->emb, D->ld_emb, D->pe, d, reinterpret_cast<const long long*>(A->tokens), A->ld_tokens,
+                                B, L, c.vocab_size, x, skip, s));
+  // K / V projection of the memory tokens, once per layer (shared by all L positions of a sequence)
+  void* mem_split = nullptr;
+  if (use_tensor_cores(c, B * M)) {
+    SCV_TRY(D->msplit.ensure(split_tile_bytes(B * M, d)));
+    mem_split = D->msplit.p;
+    SCV_TRY(launch_layernorm_split(A->memory, d, nullptr, nullptr, mem_split, B * M, d, 0, nullptr, s));
+  }
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& Lr = D->layers[li];
+    LinearArgs a;
+    a.a_split = mem_split;
+    a.x = A->memory; a.ldx = d; a.w = Lr.ca_in_w + (size_t)d * Lr.ca_in_ld; a.ldw = Lr.ca_in_ld; a.wt = Lr.ca_kv_wt;
+    a.bias = Lr.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
+    a.M = B * M; a.N = 2 * d; a.K = d;
+    SCV_TRY(launch_linear(a, 0, s));
+  }
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& Lr = D->layers[li];
+    SCV_TRY(norm(Lr.n1, xn));
+    LinearArgs a;
+    a.x = xn; a.ldx = d; a.a_split = xn_s; a.w = Lr.sa_in_w; a.ldw = Lr.sa_in_ld; a.wt = Lr.sa_in_wt; a.bias = Lr.sa_in_b;
+    a.y = qkv; a.ldy = 3 * d; a.M = R; a.N = 3 * d; a.K = d;
+    SCV_TRY(launch_linear(a, 0, s));
+    AttnArgs sa;
+    sa.q = qkv; sa.ldq = 3 * d; sa.kcache = qkv + d; sa.vcache = qkv + 2 * d; sa.seq_stride = (long long)L * 3 * d;
+    sa.row_stride = 3 * d; sa.out = attn; sa.ldo = d; sa.B = R; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale;
+    sa.fixed_len = -1; sa.rows_per_seq = L; sa.key_skip = skip; sa.max_n = std::max(L, M); sa.host_len_hint = (L + 1) / 2;
+    sa.out_split = static_cast<unsigned char*>(attn_s); sa.kb_out = d / 64;
+    SCV_TRY(launch_attention(sa, s));
+    LinearArgs o = lin_args(attn, d, Lr.sa_out, x, d, R, ACT_NONE);
+    o.residual = x; o.ldr = d; o.a_split = attn_s;
+    SCV_TRY(launch_linear(o, 0, s));
+    SCV_TRY(norm(Lr.n2, xn));
+    LinearArgs q;
+    q.x = xn; q.ldx = d; q.a_split = xn_s; q.w = Lr.ca_in_w; q.ldw = Lr.ca_in_ld; q.wt = Lr.ca_q_wt; q.bias = Lr.ca_in_b;
+    q.y = q2; q.ldy = d; q.M = R; q.N = d; q.K = d;
+    SCV_TRY(launch_linear(q, 0, s));
+    AttnArgs ca;
+    float* ckv = D->ckv.as<float>() + (size_t)li * B * M * 2 * d;
+    ca.q = q2; ca.ldq = d; ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d; ca.row_stride = 2 * d;
+    ca.out = attn; ca.ldo = d; ca.B = R; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale; ca.fixed_len = M;
+    ca.rows_per_seq = L; ca.max_n = std::max(L, M);
+    ca.out_split = static_cast<unsigned char*>(attn_s); ca.kb_out = d / 64;
+    SCV_TRY(launch_attention(ca, s));
+    LinearArgs co = lin_args(attn, d, Lr.ca_out, x, d, R, ACT_NONE);
+    co.residual = x; co.ldr = d; co.a_split = attn_s;
+    SCV_TRY(launch_linear(co, 0, s));
+    SCV_TRY(norm(Lr.n3, xn));
+    LinearArgs f1 = lin_args(xn, d, Lr.ff1, ff, dff, R, ACT_GELU);
+    f1.a_split = xn_s; f1.y_split = ff_s;
+    SCV_TRY(launch_linear(f1, 0, s));
+    LinearArgs f2 = lin_args(ff, dff, Lr.ff2, x, d, R, ACT_NONE);
+    f2.residual = x; f2.ldr = d; f2.a_split = ff_s;
+    SCV_TRY(launch_linear(f2, 0, s));
+  }
+  // heads at every position (:975-979): logits straight into the caller's tensor
+  SCV_TRY(norm(D->out_ln, h1));
+  LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, R, ACT_GELU);
+  oa.a_split = xn_s; oa.y_split = h2_s;
+  SCV_TRY(launch_linear(oa, 0, s));
+  LinearArgs ob = lin_args(h2, d, D->out_b, A->out_logits, c.vocab_size, R, ACT_NONE);
+  ob.a_split = h2_s;
+  SCV_TRY(launch_linear(ob, 0, s));
+  if (A->out_type != nullptr) {
+    SCV_TRY(norm(D->tt_ln, h1));
+    LinearArgs ta = lin_args(h1, d, D->tt_a, h2, d, R, ACT_GELU);
+    ta.a_split = xn_s; ta.y_split = h2_s;
+    SCV_TRY(launch_linear(ta, 0, s));
+    LinearArgs tb = lin_args(h2, d, D->tt_b, t3, d / 4, R, ACT_GELU);
+    tb.a_split = h2_s;
+    SCV_TRY(launch_linear(tb, 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, D->tlog.as<float>(), 8, R, ACT_NONE), 0, s));
+    SCV_CUDA(cudaMemcpy2DAsync(A->out_type, 5 * f, D->tlog.p, 8 * f, 5 * f, (size_t)R, cudaMemcpyDeviceToDevice, s));
+  }
+  if (A->out_stop != nullptr) {
+    SCV_TRY(launch_linear(lin_args(x, d, D->stop_a, t3, d / 4, R, ACT_GELU), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, A->out_stop, 1, R, ACT_NONE), 0, s));
+  }
+  if (A->out_dup != nullptr) {
+    SCV_TRY(launch_linear(lin_args(x, d, D->dup_a, t3, d / 4, R, ACT_GELU), 0, s));
+    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->dup_b, A->out_dup, 1, R, ACT_NONE), 0, s));
+  }
+  D->last_B = 0;     // the step taps no longer describe a decode
   return 0;
 }
 

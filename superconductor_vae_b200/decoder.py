@@ -168,9 +168,44 @@ class EnhancedTransformerDecoder(nn.Module):
         """Build from an instance of the reference class (same state_dict layout)."""
         return cls.from_state_dict(module.state_dict(), nhead=module.nhead, device=device)
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("teacher-forced training forward is outside the B200 decode engine "
-                                  "(SURVEY.md section 8f row 3); use the reference module for training")
+    def forward(self, z, target_tokens, encoder_skip=None, teacher_forcing_ratio: float = 1.0, stoich_pred=None,
+                cached_memory=None, heads_pred=None):
+        """Teacher-forced forward with ``teacher_forcing_ratio = 1.0`` (reference :901-985), inference
+        only (no autograd graph): every position of every row in one engine pass.
+
+        Returns ``(logits [B, L-1, V], generated [B, L-1], stop_logits [B, L-1], type_logits [B, L-1, 5],
+        site_dup_logits [B, L-1] or None when the checkpoint has no site_dup_head)``, like the reference.
+        Scheduled sampling (ratio < 1, the reference's two-pass scheme :987-1100) is not built."""
+        if teacher_forcing_ratio < 1.0:
+            raise NotImplementedError("scheduled sampling (teacher_forcing_ratio < 1) is outside the B200 engine "
+                                      "(SURVEY.md section 8f row 3 covers the parallel teacher-forced pass only)")
+        with torch.no_grad():
+            L = self._sync_engine()
+            memory = self._f32(cached_memory, "cached_memory") if cached_memory is not None else \
+                self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
+            device = memory.device
+            B, M = memory.size(0), memory.size(1)
+            tokens = target_tokens.to(device=device, dtype=torch.int64)
+            if tokens.dim() != 2 or tokens.size(0) != B or tokens.size(1) < 2:
+                raise RuntimeError(f"target_tokens must be [{B}, seq_len >= 2], got {tuple(tokens.shape)}")
+            if int(tokens.min()) < 0 or int(tokens.max()) >= self.vocab_size:
+                raise IndexError("index out of range in self")                  # nn.Embedding's error
+            seq = tokens.size(1) - 1
+            if seq > self.pos_encoding.pe.shape[1]:
+                raise RuntimeError(f"The size of tensor a ({seq}) must match the size of tensor b "
+                                   f"({self.pos_encoding.pe.shape[1]}) at non-singleton dimension 1")
+            tokens = tokens.contiguous()
+            logits = torch.empty((B, seq, self.vocab_size), dtype=torch.float32, device=device)
+            stop = torch.empty((B, seq), dtype=torch.float32, device=device)
+            typ = torch.empty((B, seq, N_TOKEN_TYPES), dtype=torch.float32, device=device)
+            has_dup = hasattr(self, "site_dup_head")
+            dup = torch.empty((B, seq), dtype=torch.float32, device=device) if has_dup else None
+            args = _lib.ForwardArgs(batch=B, seq_len=seq, n_memory=M, memory=_lib.ptr(memory), tokens=_lib.ptr(tokens),
+                                    ld_tokens=tokens.size(1), out_logits=_lib.ptr(logits), out_stop=_lib.ptr(stop),
+                                    out_type=_lib.ptr(typ), out_dup=_lib.ptr(dup) if has_dup else None)
+            with torch.cuda.device(device):
+                _lib.check(L.scv_decoder_forward(self._engine, C.byref(args), _lib.current_stream()), "forward")
+            return logits, logits.argmax(dim=-1), stop, typ, dup
 
     # ------------------------------------------------------------------ engine plumbing
     def _config(self) -> _lib.DecoderConfig:

@@ -454,6 +454,36 @@ def test_unique_sequences_and_decode_unique():
         assert rep[r, :first_end[r]].tolist() == rows[r, :first_end[r]].tolist() and int(rep[r, first_end[r]:].abs().sum()) == 0
 
 
+# ------------------------------------------------------------------------------------------ teacher-forced forward
+@pytest.mark.parametrize("name,shape", [("tiny", W.TINY), ("c512", W.C512)])
+def test_teacher_forced_forward_matches_reference(golden_dir, name, shape):
+    """forward(z, target_tokens) with teacher_forcing_ratio = 1 against the reference's own outputs
+    (tests/golden/forward_tf.pt): logits / stop / type / site-dup logits at every position, causal + padding masks.
+    Tolerance: bf16-exact weights, fp32 accumulate, bf16 hi/lo activations on the tensor-core path -> 2e-3 abs on
+    logits of magnitude ~1 (the fp32 oracle meets 2e-4 on CPU)."""
+    g = torch.load(os.path.join(golden_dir, "forward_tf.pt"), weights_only=False)[name]
+    sd = W.make_decoder_state_dict(shape, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shape.nhead, device=DEV)
+    z = W.make_latents(g["B"], shape.latent_dim, g["seed_in"])
+    stoich, heads = W.make_conditioning(g["B"], shape.stoich_input_dim, g["seed_in"])
+    logits, gen, stop, typ, dup = dec(_cuda(z), g["target_tokens"].to(DEV), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads))
+    assert logits.shape == g["logits"].shape and gen.dtype == torch.int64
+    torch.testing.assert_close(logits.cpu(), g["logits"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(stop.cpu(), g["stop_logits"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(typ.cpu(), g["type_logits"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(dup.cpu(), g["site_dup_logits"], rtol=2e-3, atol=2e-3)
+    assert (gen.cpu().to(torch.int16) == g["generated"]).float().mean() > 0.98
+    # consistency with the decode path: teacher forcing on the ids the greedy decode emitted reproduces them
+    t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), temperature=0.001,
+                                         max_len=g["target_tokens"].shape[1])
+    tgt = torch.cat([torch.ones((t.shape[0], 1), dtype=torch.int64, device=t.device), t], dim=1)
+    _, gen2, _, _, _ = dec(_cuda(z), tgt, stoich_pred=_cuda(stoich), heads_pred=_cuda(heads))
+    agree = (gen2 == t)[tgt[:, :-1] != 0]          # PAD inputs are masked as keys in forward but not in generation
+    assert agree.float().mean() > 0.99
+    with pytest.raises(NotImplementedError):
+        dec(_cuda(z), tgt, teacher_forcing_ratio=0.5)
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_config2_4096_latents_properties(golden_dir):
     """BASELINE config 2 at full size (4096 latents, masks + stop head, greedy): bit-exact vs the oracle on the

@@ -184,3 +184,20 @@ def test_vocab_layout_matches_reference(golden_dir):
     assert m.shape == (5, g["vocab_size"]) == (5, 4752)
     assert m.sum(dim=1).tolist() == g["mask_row_sums"].tolist() == [118, 20, 4317, 296, 1]
     assert int(m.sum()) == g["vocab_size"]
+
+
+@pytest.mark.parametrize("name,shape,nhead", [("tiny", W.TINY, None), ("c512", W.C512, 8)])
+def test_teacher_forced_forward_matches_reference(golden_dir, name, shape, nhead):
+    """EnhancedTransformerDecoder.forward (teacher forcing, causal + key padding masks)."""
+    g = torch.load(os.path.join(golden_dir, "forward_tf.pt"), weights_only=False)[name]
+    sd = W.make_decoder_state_dict(shape, 0)
+    z = W.make_latents(g["B"], shape.latent_dim, g["seed_in"])
+    stoich, heads = W.make_conditioning(g["B"], shape.stoich_input_dim, g["seed_in"])
+    logits, gen, stop, typ, dup = DO.forward_teacher_forced(sd, nhead or shape.nhead, z, g["target_tokens"],
+                                                           stoich_pred=stoich, heads_pred=heads)
+    torch.testing.assert_close(logits, g["logits"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(stop, g["stop_logits"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(typ, g["type_logits"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(dup, g["site_dup_logits"], rtol=2e-4, atol=2e-4)
+    assert (gen.to(torch.int16) == g["generated"]).float().mean() > 0.99
+
