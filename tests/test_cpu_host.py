@@ -1,5 +1,6 @@
 """CPU-only checks of the host side: C-ABI exports, state_dict layout, tokenizer ids, sharding logic
 (gloo, world_size 2), and that the product path fails loudly without a GPU (no CPU fallback)."""
+import inspect
 import os
 import re
 import socket
@@ -61,8 +62,12 @@ def test_no_cpu_fallback():
     m = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=W.TINY.nhead, device="cpu")
     with pytest.raises(S.EngineError):
         m.generate_with_kv_cache(W.make_latents(2, W.TINY.latent_dim), temperature=0.001)
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 64), torch.zeros(1, 4, dtype=torch.long))
+    with pytest.raises(S.EngineError):                       # teacher-forced forward: engine only, no CPU path either
+        m(torch.zeros(1, W.TINY.latent_dim), torch.zeros(1, 4, dtype=torch.long))
+    with pytest.raises(NotImplementedError):                 # scheduled sampling is not built
+        m(torch.zeros(1, W.TINY.latent_dim), torch.zeros(1, 4, dtype=torch.long), teacher_forcing_ratio=0.5)
+    names = list(inspect.signature(S.EnhancedTransformerDecoder.forward).parameters)[1:8]
+    assert names == ["z", "target_tokens", "encoder_skip", "teacher_forcing_ratio", "stoich_pred", "cached_memory", "heads_pred"]
 
 
 def test_positional_signature_order():
