@@ -61,6 +61,7 @@ struct SmallOp {               // y = act(LN?(x) W^T + b) (+ residual) for all B
   const float* ln_g; const float* ln_b;          // LayerNorm of the input rows (null: none)
   const __nv_bfloat16* w; int ldw;               // [N, ldw] row-major bf16, zero padded beyond K, ldw % 8 == 0
   const float* bias; int N; int act;
+  int cpc;                                        // output columns per CTA (small_cols_per_cta)
   const float* res; int ldr;                      // residual added after the activation (may alias out)
   float* out; int ldo;
 };
@@ -71,6 +72,7 @@ struct SmallPhase {
   AttnArgs attn;
 };
 size_t small_step_smem_bytes();
+int small_cols_per_cta(int N, int grid);
 bool small_phase_fits(const SmallPhase& ph, int grid);
 int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const StepState* st, unsigned* bar, int grid,
                         cudaStream_t s);

@@ -31,9 +31,13 @@ namespace scv {
 namespace {
 
 constexpr int SM_THREADS = 256, SM_WARPS = 8;
-constexpr int KC = 1024;                      // columns of the input staged per chunk (LayerNorm inputs fit in one)
-constexpr int XS_PITCH = KC + 4;              // floats; row r starts 16 B further in the banks than row r-1
-constexpr int W_BUF_BYTES = 40 * 1024;        // weight rows of one phase for one CTA
+constexpr int KC = 640;                       // widest input staged in one piece (a LayerNorm input must be: d_model <= 640)
+constexpr int KCH = 512;                      // wider inputs (the feed-forward width) are staged in chunks of 512 columns
+constexpr int A_PITCH = KC + 8;               // bf16 per staged row: 1296 B, consecutive rows 16 B apart in the banks
+constexpr int W_BUF_BYTES = 64 * 1024;        // weight rows of one phase for one CTA
+constexpr int W_ROW_PAD = 16;                 // bytes added to every staged weight row (same bank rotation as A)
+constexpr int NT_MAX = 6;                     // 8-column MMA tiles per CTA and projection (<= 48 output columns)
+constexpr int RED_PITCH = NT_MAX * 8;         // floats per row of the cross-warp partial sums
 constexpr int MAX_N_SCORES = 256;             // positions per (row, head) the score buffer can hold
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -49,8 +53,20 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// D += A (16x16 bf16, row) * B (16x8 bf16, col), fp32 accumulate
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // Grid-wide barrier over co-resident CTAs (the launch is cooperative: one CTA per SM).  `bar` counts arrivals and is
-// reset to zero by step_end_kernel after the kernel has finished.
+// reset to zero by a memset before the launch.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -65,257 +81,387 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 
 struct Smem {
   SmallPhase ph[2];                               // descriptors of the running and of the next phase (copied from global)
-  float xs[32 * XS_PITCH];
+  // the staged input rows as bf16 hi / lo (x = hi + lo to 16 significant bits, the split of the tcgen05 path);
+  // a_hi doubles as the cross-warp partial-sum buffer of a projection and as the score buffer of an attention phase
+  __align__(16) __nv_bfloat16 a_hi[32 * A_PITCH];
+  __align__(16) __nv_bfloat16 a_lo[32 * A_PITCH];
   __align__(16) unsigned char w[2][W_BUF_BYTES];
-  float sc[SM_WARPS * MAX_N_SCORES];
-  float gb[2 * KC];                               // LayerNorm weight and bias of the op being staged
 };
+static_assert(4 * 32 * RED_PITCH * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi");
+static_assert(SM_WARPS * MAX_N_SCORES * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "scores alias a_hi");
 
-__device__ __forceinline__ int cols_of_cta(int N) { return (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x; }
+// Output columns are dealt to the CTAs in contiguous blocks of op.cpc (a multiple of 8 = whole MMA column tiles, see
+// small_cols_per_cta): CTA c owns [c * cpc, c * cpc + nc); CTAs beyond N / cpc skip the projection (and its staging).
+__device__ __forceinline__ void cols_of_cta(const SmallOp& op, int& n0, int& nc) {
+  n0 = (int)blockIdx.x * op.cpc;
+  nc = max(0, min(op.cpc, op.N - n0));
+}
+
+__device__ void prefetch_attention(const AttnArgs& a, Smem& sm, int buf, int step);
 
 // Issue the cp.async copies of this CTA's weight rows of every op of `ph` into buffer `buf`.
-__device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf) {
-  if (ph.kind != 0) return;
+__device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf, int step) {
+  if (ph.kind != 0) { prefetch_attention(ph.attn, sm, buf, step); return; }
   unsigned char* dst = sm.w[buf];
   for (int o = 0; o < ph.nops; ++o) {
     const SmallOp& op = ph.op[o];
-    const int nc = cols_of_cta(op.N), row_bytes = op.ldw * 2, chunks = row_bytes / 16;
+    int n0, nc;
+    cols_of_cta(op, n0, nc);
+    const int row_bytes = op.ldw * 2, chunks = row_bytes / 16, wp = row_bytes + W_ROW_PAD;
     for (int i = threadIdx.x; i < nc * chunks; i += SM_THREADS) {
       const int j = i / chunks, c = i - j * chunks;
-      const int n = (int)blockIdx.x + j * (int)gridDim.x;
-      cp_async16(dst + (size_t)j * row_bytes + 16 * c, reinterpret_cast<const unsigned char*>(op.w + (size_t)n * op.ldw) + 16 * c);
+      cp_async16(dst + (size_t)j * wp + 16 * c, reinterpret_cast<const unsigned char*>(op.w + (size_t)(n0 + j) * op.ldw) + 16 * c);
     }
-    dst += (size_t)nc * row_bytes;
+    dst += (size_t)nc * wp;
   }
   cp_async_commit();
 }
 
-__device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B) {
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Stage columns [k0, k0 + kc) of the B input rows as bf16 hi / lo, LayerNorm applied on the way (then the chunk is the
+// whole row).  Warp w owns rows 4w .. 4w+3, R rows at a time, a row spread over the lanes as NJ float4s; every load of
+// a round (and the LayerNorm weights) is in flight at once: the input was written by other CTAs in the previous phase
+// and comes through L2, so a round costs one L2 round trip.
+template <int NJ, int R>
+__device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0, int kc, int B) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned char* wbase = sm.w[buf];
-  for (int o = 0; o < ph.nops; ++o) {
-    const SmallOp op = ph.op[o];                  // by value: the descriptor lives in shared memory, the hot fields in registers
-    const int K = op.K, nc = cols_of_cta(op.N);
-    const int row_bytes = op.ldw * 2;
-    const bool multi_chunk = K > KC;              // then nc <= 8 (small_phase_fits)
-    float acc_mc = 0.f;
-    for (int k0 = 0; k0 < K; k0 += KC) {
-      const int kc = min(KC, K - k0), kc8 = (kc + 7) & ~7;
-      __syncthreads();                            // the previous chunk / op / phase is done with xs
-      if ((kc & 3) == 0 && (op.ld_in & 3) == 0 && (reinterpret_cast<uintptr_t>(op.in) & 15u) == 0) {
-        // asynchronous 16-byte copies L2 -> shared memory (cp.async.cg reads through L2, where the other CTAs'
-        // results of the previous phase are): every copy of the chunk is in flight at once
-        const int q4 = kc >> 2, total = B * q4;
-        for (int i = threadIdx.x; i < total; i += SM_THREADS) {
-          const int r = i / q4, c = i - r * q4;
-          cp_async16(sm.xs + r * XS_PITCH + 4 * c, op.in + (size_t)r * op.ld_in + k0 + 4 * c);
-        }
-        if (op.ln_g != nullptr) {                // K <= KC and K % 4 == 0 here
-          if (((reinterpret_cast<uintptr_t>(op.ln_g) | reinterpret_cast<uintptr_t>(op.ln_b)) & 15u) == 0) {
-            for (int i = threadIdx.x; i < 2 * q4; i += SM_THREADS)
-              cp_async16(sm.gb + (i < q4 ? 0 : KC) + 4 * (i < q4 ? i : i - q4), (i < q4 ? op.ln_g : op.ln_b) + 4 * (i < q4 ? i : i - q4));
-          } else {
-            for (int k = threadIdx.x; k < K; k += SM_THREADS) { sm.gb[k] = __ldg(op.ln_g + k); sm.gb[KC + k] = __ldg(op.ln_b + k); }
-          }
-        }
-        cp_async_commit();
-        if (kc8 != kc)
-          for (int r = threadIdx.x; r < B; r += SM_THREADS)
-            for (int k = kc; k < kc8; ++k) sm.xs[r * XS_PITCH + k] = 0.f;
-      } else {
-        for (int i = threadIdx.x; i < B * kc8; i += SM_THREADS) {
-          const int r = i / kc8, k = i - r * kc8;
-          sm.xs[r * XS_PITCH + k] = k < kc ? __ldcg(op.in + (size_t)r * op.ld_in + k0 + k) : 0.f;
-        }
-        if (op.ln_g != nullptr)
-          for (int k = threadIdx.x; k < K; k += SM_THREADS) { sm.gb[k] = __ldg(op.ln_g + k); sm.gb[KC + k] = __ldg(op.ln_b + k); }
+  const bool ln = op.ln_g != nullptr;
+#pragma unroll 1
+  for (int rr = 0; rr < 4; rr += R) {
+    float4 v[R][NJ];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int r = warp * 4 + rr + u;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int col = 4 * (lane + 32 * j);
+        v[u][j] = (r < B && col < kc) ? __ldcg(reinterpret_cast<const float4*>(op.in + (size_t)r * op.ld_in + k0 + col))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      cp_async_wait_all();                        // the chunk and this phase's weight rows have landed (own copies) ...
-      __syncthreads();                            // ... and everybody else's, and xs is complete
-      if (op.ln_g != nullptr) {
-        // LayerNorm in place (the whole row is in this chunk): 8 threads per row, two passes, eps 1e-5
-        // (rows >= B hold stale shared memory: normalised like the rest so the warp shuffles stay convergent, never used)
-        const int r = threadIdx.x >> 3, sub = threadIdx.x & 7;
-        {
-          float* xr = sm.xs + r * XS_PITCH;
-          float s = 0.f;
-          for (int k = sub; k < K; k += 8) s += xr[k];
-          s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-          const float mean = s / (float)K;
-          float q = 0.f;
-          for (int k = sub; k < K; k += 8) { const float d = xr[k] - mean; q = fmaf(d, d, q); }
-          q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
-          const float rstd = 1.0f / sqrtf(q / (float)K + 1e-5f);
-          for (int k = sub; k < K; k += 64) {       // eight elements per batch: loads first, then the in-place stores
-            float xv[8], gv[8], bv[8];
+    }
+    if (ln) {                                     // two passes over the registers, eps 1e-5 (nn.LayerNorm)
+      float4 g[NJ], bt[NJ];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int kk = k + 8 * u;
-              if (kk < K) { xv[u] = xr[kk]; gv[u] = sm.gb[kk]; bv[u] = sm.gb[KC + kk]; }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int kk = k + 8 * u;
-              if (kk < K) xr[kk] = (xv[u] - mean) * rstd * gv[u] + bv[u];
-            }
-          }
-        }
-        __syncthreads();
+      for (int j = 0; j < NJ; ++j) {
+        const int col = 4 * (lane + 32 * j);
+        g[j] = bt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < kc) { g[j] = __ldg(reinterpret_cast<const float4*>(op.ln_g + col)); bt[j] = __ldg(reinterpret_cast<const float4*>(op.ln_b + col)); }
       }
-      // lane = batch row, warp = K slice: every warp works on every column of the CTA (eight at a time, sharing each
-      // x load), the eight partial sums per (row, column) meet in shared memory.  (One warp per column left most
-      // warps idle and ran a dependent load -> FMA chain 64-256 steps long: 13-50 us per phase.)
-      const int kslice = ((kc8 / 8 + SM_WARPS - 1) / SM_WARPS) * 8;      // multiple of 8 columns per warp
-      const int kbeg = min(warp * kslice, kc8), kend = min(kbeg + kslice, kc8);
-      const float* xr = sm.xs + lane * XS_PITCH;
-      for (int cg = 0; cg < nc; cg += 8) {
-        const unsigned char* wr = wbase + (size_t)cg * row_bytes + 2 * k0;
-        float a0[8], a1[8];
+      float s[R], q[R];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
-        // warp c will finish column cg + c: fetch its bias and residual now, their L2 latency hides behind the FMAs
-        const bool fin = warp < 8 && cg + warp < nc && lane < B && k0 + KC >= K;
-        const int n_fin = (int)blockIdx.x + (cg + warp) * (int)gridDim.x;
-        float bias_v = 0.f, res_v = 0.f;
-        if (fin) {
-          if (op.bias != nullptr) bias_v = __ldg(op.bias + n_fin);
-          if (op.res != nullptr) res_v = __ldcg(op.res + (size_t)lane * op.ldr + n_fin);
-        }
-#pragma unroll 2
-        for (int k = kbeg; k < kend; k += 8) {
-          const float4 xa = *reinterpret_cast<const float4*>(xr + k), xb = *reinterpret_cast<const float4*>(xr + k + 4);
+      for (int u = 0; u < R; ++u) {
+        s[u] = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (cg + c < nc) {
-              const uint4 wv = *reinterpret_cast<const uint4*>(wr + (size_t)c * row_bytes + 2 * k);
-              a0[c] = fmaf(xa.x, bf16_bits_to_float(wv.x & 0xffffu), a0[c]); a1[c] = fmaf(xa.y, __uint_as_float(wv.x & 0xffff0000u), a1[c]);
-              a0[c] = fmaf(xa.z, bf16_bits_to_float(wv.y & 0xffffu), a0[c]); a1[c] = fmaf(xa.w, __uint_as_float(wv.y & 0xffff0000u), a1[c]);
-              a0[c] = fmaf(xb.x, bf16_bits_to_float(wv.z & 0xffffu), a0[c]); a1[c] = fmaf(xb.y, __uint_as_float(wv.z & 0xffff0000u), a1[c]);
-              a0[c] = fmaf(xb.z, bf16_bits_to_float(wv.w & 0xffffu), a0[c]); a1[c] = fmaf(xb.w, __uint_as_float(wv.w & 0xffff0000u), a1[c]);
-            }
+        for (int j = 0; j < NJ; ++j) s[u] += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < R; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        s[u] = s[u] / (float)kc;                  // mean
+        q[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (4 * (lane + 32 * j) < kc) {
+            const float d0 = v[u][j].x - s[u], d1 = v[u][j].y - s[u], d2 = v[u][j].z - s[u], d3 = v[u][j].w - s[u];
+            q[u] = fmaf(d0, d0, q[u]); q[u] = fmaf(d1, d1, q[u]); q[u] = fmaf(d2, d2, q[u]); q[u] = fmaf(d3, d3, q[u]);
           }
         }
-        if (cg > 0 || k0 > 0) __syncthreads();     // the previous group's partial sums have been consumed
+      }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sm.sc[(warp * 8 + c) * 32 + lane] = a0[c] + a1[c];
-        __syncthreads();
-        if (warp < 8 && cg + warp < nc) {          // warp c finishes column cg + c: lane = row
-          float t = 0.f;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-          for (int w2 = 0; w2 < SM_WARPS; ++w2) t += sm.sc[(w2 * 8 + warp) * 32 + lane];
-          if (multi_chunk) {
-            acc_mc += t;                           // K spans several chunks (nc <= 8): one column per warp, kept in a register
-          } else if (lane < B) {
-            float v = apply_act(t + bias_v, op.act);
-            if (op.res != nullptr) v += res_v;
-            __stcg(op.out + (size_t)lane * op.ldo + n_fin, v);
-          }
+        for (int u = 0; u < R; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const float mean = s[u], rstd = 1.0f / sqrtf(q[u] / (float)kc + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          v[u][j].x = (v[u][j].x - mean) * rstd * g[j].x + bt[j].x; v[u][j].y = (v[u][j].y - mean) * rstd * g[j].y + bt[j].y;
+          v[u][j].z = (v[u][j].z - mean) * rstd * g[j].z + bt[j].z; v[u][j].w = (v[u][j].w - mean) * rstd * g[j].w + bt[j].w;
         }
       }
     }
-    if (multi_chunk && warp < nc && lane < B) {
-      const int n = (int)blockIdx.x + warp * (int)gridDim.x;
-      float v = acc_mc;
-      if (op.bias != nullptr) v += __ldg(op.bias + n);
-      v = apply_act(v, op.act);
-      if (op.res != nullptr) v += __ldcg(op.res + (size_t)lane * op.ldr + n);
-      __stcg(op.out + (size_t)lane * op.ldo + n, v);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int r = warp * 4 + rr + u;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int col = 4 * (lane + 32 * j);
+        if (col < kc) {
+          const float4 x = v[u][j];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
+          const __nv_bfloat16 l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
+          *reinterpret_cast<uint2*>(sm.a_hi + r * A_PITCH + col) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+          *reinterpret_cast<uint2*>(sm.a_lo + r * A_PITCH + col) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+        }
+      }
     }
-    wbase += (size_t)nc * row_bytes;
   }
 }
 
-// One warp per (row, head); same operation order as attention_decode_kernel (q.k * scale -> softmax -> sum w v).
-__device__ void run_attention_phase(const AttnArgs& a_in, Smem& sm) {
+__device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int B) {
+  if (kc <= 512) stage_rows_t<4, 4>(op, sm, k0, kc, B);      // d_model-wide inputs: the warp's four rows in one round
+  else stage_rows_t<KC / 128, 2>(op, sm, k0, kc, B);
+}
+
+// One projection phase.  Per op: the CTA's nc <= 48 output columns for all 32 (padded) rows as mma.sync m16n8k16 tiles,
+// A = the staged rows (hi and lo against the same weight fragment, separate accumulators), B = the CTA's weight rows
+// [nc, K] (already k-contiguous = "col" operand).  Warp = (row tile, quarter of the k-steps); the four partial sums per
+// output meet in shared memory, then bias / activation / residual and nc contiguous floats per row go to global.
+__device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, unsigned long long* tdbg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp & 1, kq = warp >> 1;
+  const unsigned char* wbase = sm.w[buf];
+  float* red = reinterpret_cast<float*>(sm.a_hi);
+  for (int o = 0; o < ph.nops; ++o) {
+    const SmallOp op = ph.op[o];                  // by value: the descriptor lives in shared memory, the hot fields in registers
+    int n0, nc;
+    cols_of_cta(op, n0, nc);
+    if (nc == 0) continue;                        // CTA-uniform
+    const int K = op.K, wp = op.ldw * 2 + W_ROW_PAD;
+    const int ntiles = (nc + 7) >> 3;
+    // this thread's outputs of the epilogue: fetch bias and residual now, their latency hides behind the staging
+    constexpr int EP = (32 * NT_MAX * 8 + SM_THREADS - 1) / SM_THREADS;
+    float bias_v[EP], res_v[EP];
+#pragma unroll
+    for (int e = 0; e < EP; ++e) {
+      const int idx = threadIdx.x + e * SM_THREADS;
+      const int r = idx / nc, c = idx - r * nc;
+      bias_v[e] = 0.f; res_v[e] = 0.f;
+      if (r < B) {
+        if (op.bias != nullptr) bias_v[e] = __ldg(op.bias + n0 + c);
+        if (op.res != nullptr) res_v[e] = __ldcg(op.res + (size_t)r * op.ldr + n0 + c);
+      }
+    }
+    float acc_h[NT_MAX][4], acc_l[NT_MAX][4];
+#pragma unroll
+    for (int j = 0; j < NT_MAX; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc_h[j][i] = 0.f; acc_l[j][i] = 0.f; }
+    // ldmatrix row addresses: A x4 = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B x4 = (tile j | j+1) x (k 0-7 | 8-15)
+    const int mi = lane >> 3;
+    const int a_row = mt * 16 + (lane & 7) + (mi & 1) * 8, a_kofs = (mi >> 1) * 8;
+    const int b_kofs = (mi & 1) * 8;
+    const int chunk = K > KC ? KCH : KC;
+    for (int k0 = 0; k0 < K; k0 += chunk) {
+      const int kc = min(chunk, K - k0);
+      __syncthreads();                            // the previous chunk / op / phase is done with a_hi, a_lo
+      if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[0]));
+      stage_rows(op, sm, k0, kc, B);
+      cp_async_wait_all();                        // this phase's weight rows have landed (own copies) ...
+      __syncthreads();                            // ... and everybody else's; the staged rows are complete
+      if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[1]));
+      const int steps = kc >> 4;
+      for (int ks = kq; ks < steps; ks += 4) {
+        uint32_t ah[4], al[4];
+        ldmatrix_x4(ah, sm.a_hi + a_row * A_PITCH + ks * 16 + a_kofs);
+        ldmatrix_x4(al, sm.a_lo + a_row * A_PITCH + ks * 16 + a_kofs);
+#pragma unroll
+        for (int jp = 0; jp < NT_MAX / 2; ++jp) {
+          if (2 * jp < ntiles) {
+            const int wrow = min((2 * jp + (mi >> 1)) * 8 + (lane & 7), nc - 1);      // rows beyond nc: a duplicate, never stored
+            uint32_t b[4];
+            ldmatrix_x4(b, wbase + (size_t)wrow * wp + 2 * (k0 + ks * 16 + b_kofs));
+            mma_bf16(acc_h[2 * jp], ah, b[0], b[1]);
+            mma_bf16(acc_l[2 * jp], al, b[0], b[1]);
+            if (2 * jp + 1 < ntiles) {
+              mma_bf16(acc_h[2 * jp + 1], ah, b[2], b[3]);
+              mma_bf16(acc_l[2 * jp + 1], al, b[2], b[3]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                              // every warp is done reading a_hi: it becomes the partial-sum buffer
+    if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[2]));
+    {
+      const int g = lane >> 2, t = lane & 3;
+      float* r0 = red + ((size_t)kq * 32 + mt * 16 + g) * RED_PITCH + 2 * t;
+#pragma unroll
+      for (int j = 0; j < NT_MAX; ++j) {
+        if (j < ntiles) {
+          *reinterpret_cast<float2*>(r0 + 8 * j) = make_float2(acc_h[j][0] + acc_l[j][0], acc_h[j][1] + acc_l[j][1]);
+          *reinterpret_cast<float2*>(r0 + 8 * RED_PITCH + 8 * j) = make_float2(acc_h[j][2] + acc_l[j][2], acc_h[j][3] + acc_l[j][3]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EP; ++e) {
+      const int idx = threadIdx.x + e * SM_THREADS;
+      const int r = idx / nc, c = idx - r * nc;
+      if (r < B) {
+        const float* p = red + (size_t)r * RED_PITCH + c;
+        float v = (p[0] + p[32 * RED_PITCH]) + (p[64 * RED_PITCH] + p[96 * RED_PITCH]);
+        v = apply_act(v + bias_v[e], op.act);
+        if (op.res != nullptr) v += res_v[e];
+        __stcg(op.out + (size_t)r * op.ldo + n0 + c, v);
+      }
+    }
+    wbase += (size_t)nc * wp;
+  }
+}
+
+// Attention phase: pair p = (row, head) goes to CTA p % grid, warp p / grid (one pair per warp: B * nhead <= 8 * grid).
+// Cached K / V rows do not depend on this step's activations (self-attention: positions < step; cross-attention: the
+// projected memory tokens), so the pair's rows are copied into the idle weight buffer BEFORE the barrier that precedes
+// the phase, as many as fit; after the barrier only q and the step's new k, v row come through L2 (one round trip),
+// and the new row is used from registers.
+struct AttnPlan { int ppc, cap; };               // pairs per CTA, prefetchable positions per pair
+__device__ __forceinline__ AttnPlan attn_plan(const AttnArgs& a) {
+  AttnPlan pl;
+  pl.ppc = (a.B * a.nhead + (int)gridDim.x - 1) / (int)gridDim.x;
+  pl.cap = W_BUF_BYTES / (pl.ppc * 2 * a.hd * (int)sizeof(float));
+  return pl;
+}
+__device__ __forceinline__ size_t attn_row_off(const AttnArgs& a, int b, int h, int p) {
+  if (a.page_table != nullptr)
+    return (size_t)a.page_table[(size_t)b * a.pages_per_seq + (p >> kPageShift)] * a.page_stride +
+           (size_t)(p & (kPagePos - 1)) * a.row_stride + h * a.hd;
+  return (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * a.hd;
+}
+
+__device__ void prefetch_attention(const AttnArgs& a, Smem& sm, int buf, int step) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AttnPlan pl = attn_plan(a);
+  const int pair = (int)blockIdx.x + warp * (int)gridDim.x;
+  if (warp < pl.ppc && pair < a.B * a.nhead) {
+    const int b = pair / a.nhead, h = pair % a.nhead;
+    const int n = a.fixed_len >= 0 ? a.fixed_len : step + 1;
+    const int np = min(a.knew != nullptr ? n - 1 : n, pl.cap);          // self: the last row is produced in the phase itself
+    float* kv = reinterpret_cast<float*>(sm.w[buf]) + (size_t)warp * 2 * pl.cap * a.hd;
+    const int cpr = a.hd >> 2;                                           // 16-byte pieces per row
+    for (int i = lane; i < np * cpr; i += 32) {
+      const int p = i / cpr, c = i - p * cpr;
+      const size_t off = attn_row_off(a, b, h, p) + 4 * c;
+      cp_async16(kv + (size_t)p * a.hd + 4 * c, a.kcache + off);
+      cp_async16(kv + (size_t)(pl.cap + p) * a.hd + 4 * c, a.vcache + off);
+    }
+  }
+  cp_async_commit();
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+
+// One warp per (row, head): q.k * scale -> softmax -> sum w v (autoregressive_decoder.py:1270-1296, 1302-1307).  Eight
+// lanes share a cached row (16-byte pieces sub, sub + 8, ...), four rows per warp instruction.
+__device__ void run_attention_phase(const AttnArgs& a_in, Smem& sm, int buf, int step) {
   const AttnArgs a = a_in;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hd = a.hd;
-  const int n = a.fixed_len >= 0 ? a.fixed_len : a.st->step + 1;
-  float* sc = sm.sc + warp * MAX_N_SCORES;
-  const int pairs = a.B * a.nhead;
-  for (int gw = (int)blockIdx.x * SM_WARPS + warp; gw < pairs; gw += (int)gridDim.x * SM_WARPS) {
-    const int b = gw / a.nhead, h = gw % a.nhead;
-    const bool paged = a.page_table != nullptr;
-    const int* pt = paged ? a.page_table + (size_t)b * a.pages_per_seq : nullptr;
-    auto row_off = [&](int p) -> size_t {
-      if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
-      return (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * hd;
-    };
-    float qv[4];
+  const int sub = lane & 7, pg = lane >> 3;
+  const int hd = a.hd, cpr = hd >> 2;
+  const AttnPlan pl = attn_plan(a);
+  const int pair = (int)blockIdx.x + warp * (int)gridDim.x;
+  if (warp >= pl.ppc || pair >= a.B * a.nhead) { cp_async_wait_all(); return; }
+  const int b = pair / a.nhead, h = pair % a.nhead;
+  const bool self = a.knew != nullptr;
+  const int n = a.fixed_len >= 0 ? a.fixed_len : step + 1;
+  const int ncached = self ? n - 1 : n, np = min(ncached, pl.cap);
+  float* sc = reinterpret_cast<float*>(sm.a_hi) + warp * MAX_N_SCORES;
+  const float* kv = reinterpret_cast<const float*>(sm.w[buf]) + (size_t)warp * 2 * pl.cap * hd;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 q[4], kn[4], vn[4];
+  size_t new_off = 0;
+  if (self) new_off = attn_row_off(a, b, h, n - 1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = lane + 32 * j;
-      qv[j] = e < hd ? __ldcg(a.q + (size_t)b * a.ldq + h * hd + e) : 0.f;
-    }
-    if (a.knew != nullptr) {                       // append this step's key / value (:1266-1267)
-      const size_t off = row_off(n - 1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = lane + 32 * j;
-        if (e < hd) {
-          a.kcache[off + e] = __ldcg(a.knew + (size_t)b * a.ldn + h * hd + e);
-          a.vcache[off + e] = __ldcg(a.vnew + (size_t)b * a.ldn + h * hd + e);
-        }
-      }
-      __syncwarp();
-    }
-    for (int p0 = 0; p0 < n; p0 += 8) {           // eight cached rows in flight per warp
-      float kk[8][4];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float* kp = a.kcache + row_off(min(p0 + u, n - 1));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = lane + 32 * j;
-          kk[u][j] = e < hd ? kp[e] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float d = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d = fmaf(qv[j], kk[u][j], d);
-        d = warp_sum(d);
-        if (lane == 0 && p0 + u < n) sc[p0 + u] = d * a.scale;
+  for (int i = 0; i < 4; ++i) {
+    const int c = sub + 8 * i;
+    q[i] = kn[i] = vn[i] = zero4;
+    if (c < cpr) {
+      q[i] = __ldcg(reinterpret_cast<const float4*>(a.q + (size_t)b * a.ldq + h * hd) + c);
+      if (self) {
+        kn[i] = __ldcg(reinterpret_cast<const float4*>(a.knew + (size_t)b * a.ldn + h * hd) + c);
+        vn[i] = __ldcg(reinterpret_cast<const float4*>(a.vnew + (size_t)b * a.ldn + h * hd) + c);
       }
     }
-    __syncwarp();
-    float m = -INFINITY;
-    for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int p = lane; p < n; p += 32) { const float e = expf(sc[p] - m); sc[p] = e; sum += e; }
-    sum = warp_sum(sum);
-    __syncwarp();
-    for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
-    __syncwarp();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p0 = 0; p0 < n; p0 += 8) {
-      float vv[8][4];
+  }
+  cp_async_wait_all();                             // this warp's staged rows (its own copies) ...
+  __syncwarp();                                    // ... of every lane
+  if (self && pg == 0) {                           // append this step's key / value (:1266-1267)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float* vp = a.vcache + row_off(min(p0 + u, n - 1));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = lane + 32 * j;
-          vv[u][j] = e < hd ? vp[e] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (p0 + u < n) {
-          const float w = sc[p0 + u];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, vv[u][j], acc[j]);
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int c = sub + 8 * i;
+      if (c < cpr) {
+        *(reinterpret_cast<float4*>(a.kcache + new_off) + c) = kn[i];
+        *(reinterpret_cast<float4*>(a.vcache + new_off) + c) = vn[i];
       }
     }
+  }
+#pragma unroll 2
+  for (int p0 = 0; p0 < ncached; p0 += 4) {
+    const int p = min(p0 + pg, ncached - 1);
+    const float4* kp = reinterpret_cast<const float4*>(p < np ? kv + (size_t)p * hd : a.kcache + attn_row_off(a, b, h, p));
+    float d = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = lane + 32 * j;
-      if (e < hd) __stcg(a.out + (size_t)b * a.ldo + h * hd + e, acc[j]);
+    for (int i = 0; i < 4; ++i) {
+      const int c = sub + 8 * i;
+      if (c < cpr) d = dot4(q[i], kp[c], d);
     }
-    __syncwarp();
+    d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (sub == 0 && p0 + pg < ncached) sc[p0 + pg] = d * a.scale;
+  }
+  if (self) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d = dot4(q[i], kn[i], d);
+    d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (lane == 0) sc[n - 1] = d * a.scale;
+  }
+  __syncwarp();
+  float m = -INFINITY;
+  for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int p = lane; p < n; p += 32) { const float e = expf(sc[p] - m); sc[p] = e; sum += e; }
+  sum = warp_sum(sum);
+  __syncwarp();
+  for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
+  __syncwarp();
+  float4 acc[4] = {zero4, zero4, zero4, zero4};
+#pragma unroll 2
+  for (int p0 = 0; p0 < ncached; p0 += 4) {
+    const int p = min(p0 + pg, ncached - 1);
+    const float w = p0 + pg < ncached ? sc[p] : 0.f;
+    const float4* vp = reinterpret_cast<const float4*>(p < np ? kv + (size_t)(pl.cap + p) * hd : a.vcache + attn_row_off(a, b, h, p));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = sub + 8 * i;
+      if (c < cpr) {
+        const float4 v = vp[c];
+        acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y); acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+      }
+    }
+  }
+  if (self && pg == 0) {
+    const float w = sc[n - 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[i].x = fmaf(w, vn[i].x, acc[i].x); acc[i].y = fmaf(w, vn[i].y, acc[i].y); acc[i].z = fmaf(w, vn[i].z, acc[i].z); acc[i].w = fmaf(w, vn[i].w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                    // the four row groups meet
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o); acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+      acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o); acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
+    }
+  }
+  if (pg == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = sub + 8 * i;
+      if (c < cpr) __stcg(reinterpret_cast<float4*>(a.out + (size_t)b * a.ldo + h * hd) + c, acc[i]);
+    }
   }
 }
 
@@ -325,27 +471,34 @@ decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   if (st->done) return;                           // uniform: written by step_end_kernel of an earlier launch
+  const int step = st->step;
   unsigned target = 0;
-  // phase descriptors are read through shared memory (ph[p & 1]); the next one is copied while the current one runs
-  auto stage_desc = [&](int p) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(phases + p);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.ph[p & 1]);
-    for (int i = threadIdx.x; i < (int)(sizeof(SmallPhase) / 4); i += SM_THREADS) dst[i] = __ldg(src + i);
+  // phase descriptors are read through shared memory (ph[p & 1]); the next one travels through a register while the
+  // current phase runs (one word per thread), so its L2 latency is never waited for
+  constexpr int kDescWords = (int)(sizeof(SmallPhase) / 4);
+  static_assert(kDescWords <= SM_THREADS, "one descriptor word per thread");
+  auto desc_load = [&](int p) -> uint32_t {
+    return (int)threadIdx.x < kDescWords ? __ldg(reinterpret_cast<const uint32_t*>(phases + p) + threadIdx.x) : 0u;
   };
-  stage_desc(0);
+  auto desc_store = [&](int p, uint32_t v) {
+    if ((int)threadIdx.x < kDescWords) reinterpret_cast<uint32_t*>(&sm.ph[p & 1])[threadIdx.x] = v;
+  };
+  desc_store(0, desc_load(0));
   __syncthreads();
-  prefetch_weights(sm.ph[0], sm, 0);
+  prefetch_weights(sm.ph[0], sm, 0, step);
   for (int p = 0; p < n_phases; ++p) {
     const SmallPhase& ph = sm.ph[p & 1];
-    if (p + 1 < n_phases) stage_desc(p + 1);      // visible after the barriers inside / after this phase
+    uint32_t next_word = 0;
+    if (p + 1 < n_phases) next_word = desc_load(p + 1);
     unsigned long long t0 = 0, t1 = 0, t2 = 0;
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));   // SCV_SMALL_DEBUG
-    if (ph.kind == 0) run_gemv_phase(ph, sm, p & 1, B);
-    else run_attention_phase(ph.attn, sm);
+    if (ph.kind == 0) run_gemv_phase(ph, sm, p & 1, B, (dbg && blockIdx.x == 0) ? dbg + 2048 + 4 * p : nullptr);
+    else run_attention_phase(ph.attn, sm, p & 1, step);
     if (dbg && blockIdx.x == 0) { __syncthreads(); if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); }
     if (p + 1 < n_phases) {
+      desc_store(p + 1, next_word);                        // slot (p + 1) & 1 was last read in phase p - 1
       __syncthreads();                                     // the staged descriptor of phase p + 1 is complete
-      prefetch_weights(sm.ph[(p + 1) & 1], sm, (p + 1) & 1);   // weights do not depend on this phase's results
+      prefetch_weights(sm.ph[(p + 1) & 1], sm, (p + 1) & 1, step);   // weights / cached rows do not depend on this phase's results
       grid_barrier(bar, target);
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -360,16 +513,26 @@ decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, 
 
 size_t small_step_smem_bytes() { return sizeof(Smem); }
 
+int small_cols_per_cta(int N, int grid) {
+  // whole 8-column MMA tiles: rounding up never adds a tile to the busiest CTA, and fewer CTAs stage the input rows
+  // (every active CTA reads all of them through L2, which is what bounds a phase)
+  static const int min_cpc = [] { const char* e = getenv("SCV_SMALL_CPC"); return e ? atoi(e) : 8; }();
+  return std::max(round_up(ceil_div(N, grid), 8), std::min(round_up(min_cpc, 8), NT_MAX * 8));
+}
+
 bool small_phase_fits(const SmallPhase& ph, int grid) {
-  if (ph.kind != 0) return ph.attn.hd <= 128 && ph.attn.max_n <= MAX_N_SCORES;
+  if (ph.kind != 0)
+    return ph.attn.hd <= 128 && ph.attn.hd % 4 == 0 && ph.attn.max_n <= MAX_N_SCORES && ph.attn.B * ph.attn.nhead <= SM_WARPS * grid &&
+           ph.attn.ldq % 4 == 0 && ph.attn.ldn % 4 == 0 && ph.attn.ldo % 4 == 0 && ph.attn.row_stride % 4 == 0;
   size_t bytes = 0;
   for (int o = 0; o < ph.nops; ++o) {
     const SmallOp& op = ph.op[o];
-    const int nc = ceil_div(op.N, grid);
-    if (op.ldw % 8 != 0 || op.ldw < op.K) return false;
-    if (op.K > KC && nc > 8) return false;                    // several chunks: one register accumulator per warp
-    if (op.ln_g != nullptr && op.K > KC) return false;       // the LayerNorm needs the whole row in one chunk
-    bytes += (size_t)nc * op.ldw * 2;
+    if (op.K % 16 != 0 || op.ldw != op.K) return false;      // whole k16 MMA steps, rows copied in 16-byte pieces
+    if (op.ld_in % 4 != 0 || (reinterpret_cast<uintptr_t>(op.in) & 15u) != 0) return false;   // float4 staging
+    if (op.cpc % 8 != 0 || op.cpc > NT_MAX * 8 || (long long)op.cpc * grid < op.N) return false;   // accumulators: 6 tiles of 8 columns
+    if (op.ln_g != nullptr && (op.K > KC || ((reinterpret_cast<uintptr_t>(op.ln_g) | reinterpret_cast<uintptr_t>(op.ln_b)) & 15u) != 0))
+      return false;                                           // the LayerNorm needs the whole row in one chunk
+    bytes += (size_t)op.cpc * (op.ldw * 2 + W_ROW_PAD);
   }
   return bytes <= (size_t)W_BUF_BYTES;
 }
@@ -395,9 +558,13 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
   SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_kernel, phases_dev, n_phases, B, st, bar, dbg));
   if (dbg_env && ++dbg_calls == dbg_env) {
     SCV_CUDA(cudaStreamSynchronize(s));
-    std::vector<unsigned long long> h(2 * n_phases);
+    std::vector<unsigned long long> h(4096);
     SCV_CUDA(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
-    for (int p = 0; p < n_phases; ++p) fprintf(stderr, "phase %3d: run %6llu ns, prefetch+barrier %6llu ns\n", p, h[2 * p], h[2 * p + 1]);
+    for (int p = 0; p < n_phases; ++p) {
+      const unsigned long long* t = h.data() + 2048 + 4 * p;
+      fprintf(stderr, "phase %3d: run %6llu ns (stage %6llu, mma %6llu), prefetch+barrier %6llu ns\n", p, h[2 * p], t[1] - t[0],
+              t[2] - t[1], h[2 * p + 1]);
+    }
   }
   SCV_LAUNCH_CHECK();
   return 0;

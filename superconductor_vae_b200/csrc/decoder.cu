@@ -403,11 +403,12 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   float* t3 = D->t3.as<float>();
   std::vector<SmallPhase>& P = D->sm_host;
   P.clear();
-  auto op = [](const float* in, int ld_in, int K, const LNp* ln, const __nv_bfloat16* w, int ldw, const float* bias,
+  const int grid = D->sm_grid;
+  auto op = [grid](const float* in, int ld_in, int K, const LNp* ln, const __nv_bfloat16* w, int ldw, const float* bias,
                int N, int act, const float* res, int ldr, float* out, int ldo) {
     SmallOp o;
     o.in = in; o.ld_in = ld_in; o.K = K; o.ln_g = ln ? ln->g : nullptr; o.ln_b = ln ? ln->b : nullptr;
-    o.w = w; o.ldw = ldw; o.bias = bias; o.N = N; o.act = act; o.res = res; o.ldr = ldr; o.out = out; o.ldo = ldo;
+    o.w = w; o.ldw = ldw; o.bias = bias; o.N = N; o.act = act; o.cpc = small_cols_per_cta(N, grid); o.res = res; o.ldr = ldr; o.out = out; o.ldo = ldo;
     return o;
   };
   auto lin = [&](const float* in, int ld_in, const LNp* ln, const Lin& L, int act, const float* res, float* out, int ldo) {

@@ -16,11 +16,12 @@ for B in [int(a) for a in sys.argv[1:]] or [8, 32, 128]:
     for _ in range(2):
         t, _, _ = dec.generate_with_kv_cache(z, **kw)
     torch.cuda.synchronize()
+    n0 = S.launch_count()
     t0 = time.perf_counter()
     n = 5
     for _ in range(n):
         t, _, _ = dec.generate_with_kv_cache(z, **kw)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
-    print(f"B={B}: {dt*1e3:.2f} ms per decode of {t.shape[1]} steps -> {B/dt:.0f} formulas/s, {dt/t.shape[1]*1e6:.0f} us/step "
+    print(f"B={B}: {dt*1e3:.2f} ms per decode of {t.shape[1]} steps -> {B/dt:.0f} formulas/s, {dt/t.shape[1]*1e6:.0f} us/step, {(S.launch_count() - n0) / n / t.shape[1]:.1f} launches/step "
           f"(tc_min_rows={os.environ.get('SCV_TC_MIN_ROWS','64')}, graph={os.environ.get('SCV_GRAPH','1')})", flush=True)
