@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "decode_kernels.cuh"
+#include "sampler_device.cuh"
 
 namespace scv {
 
@@ -400,13 +401,6 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kSamplerThreads = 256;
 
-__device__ __forceinline__ bool arg_better(float a, int ia, float b, int ib) {
-  const bool an = isnan(a), bn = isnan(b);     // torch.argmax treats NaN as the maximum
-  if (an != bn) return an;
-  if (!an && a != b) return a > b;
-  return ia < ib;                              // first occurrence wins ties
-}
-
 __device__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -451,46 +445,6 @@ __device__ int block_argmax(const float* sl, int V, float* redv, int* redi) {
   return bi;
 }
 
-// Row context of the logit adjustments: type mask (:1416-1422), site-dup gate (:1426-1435), stop boost (:1438-1441),
-// hard stop (:1444-1448) and length boost (:1455-1457), applied per element in the reference's order.
-struct RowCtx {
-  const uint8_t* mk; const unsigned char* seen_row;
-  bool stop_on, force, dup_suppress, late;
-  float boost, length_boost;
-};
-__device__ __forceinline__ RowCtx make_row_ctx(const SamplerArgs& a, int b, int step) {
-  RowCtx c;
-  int pred_type = 0;
-  if (a.type_masks != nullptr) {
-    const float* tl = a.type_logits + (size_t)b * a.ldt;
-    float bv = tl[0];
-    for (int t = 1; t < 5; ++t)
-      if (arg_better(tl[t], t, bv, pred_type)) { bv = tl[t]; pred_type = t; }
-  }
-  c.stop_on = a.stop_boost > 0.f;
-  float sp = 0.f;
-  c.force = false;
-  if (c.stop_on) {
-    sp = sigmoidf_(a.stop_logits[b]);
-    c.force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
-  }
-  c.boost = a.stop_boost * sp;
-  c.late = c.stop_on && step > 10;
-  c.length_boost = c.late ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
-  c.dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(a.dup_logits[b]) < a.dup_threshold;
-  c.seen_row = c.dup_suppress ? a.seen + (size_t)b * a.V : nullptr;
-  c.mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
-  return c;
-}
-// allowed = type-mask byte of v (1 when no mask is given), seen = site-dup byte of v (0 when the gate is off)
-__device__ __forceinline__ float adjust_logit(const RowCtx& c, int v, float l, unsigned allowed, unsigned seen) {
-  if (allowed == 0) l = -INFINITY;
-  if (seen != 0) l = -30.0f;                                  // masked_fill(-30.0), even over a -inf
-  if (v == kEndIdx && c.stop_on) l = l + c.boost;
-  if (c.force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
-  if (v == kEndIdx && c.late) l = l + c.length_boost;
-  return l;
-}
 __device__ __forceinline__ int logit_flags(float l) {         // bit0: nan/+-inf, bit1: nan/+inf
   int bad = 0;
   if (isnan(l) || isinf(l)) bad |= 1;
@@ -510,20 +464,6 @@ __device__ int stage_logits(const SamplerArgs& a, int b, int step, float* sl) {
     bad |= logit_flags(l);
   }
   return bad;
-}
-
-__device__ void commit_token(const SamplerArgs& a, int b, int step, int token, float logprob) {
-  // single thread
-  if (a.forced != nullptr) token = (int)a.forced[(size_t)b * a.out_ld + step];
-  a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
-  if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
-  a.cur_tokens[b] = token;
-  // ids 20..137 are the element range of the pre-V13 vocabulary; the reference still uses it
-  if (a.seen != nullptr && token >= 20 && token <= 137 && a.finished[b] == 0) a.seen[(size_t)b * a.V + token] = 1;
-  if (token == kEndIdx && a.finished[b] == 0) {
-    a.finished[b] = 1;
-    atomicSub(&a.st->n_unfinished, 1);
-  }
 }
 
 // Phase 1: stage logits, publish the degenerate flag; when the call is plain greedy, also pick the token.
@@ -557,51 +497,11 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= a.B) return;
   const int step = a.st->step;
-  const RowCtx c = make_row_ctx(a, b, step);
-  const float4* lg = reinterpret_cast<const float4*>(a.logits + (size_t)b * a.ldl);
-  const uint32_t* mk4 = reinterpret_cast<const uint32_t*>(c.mk);
-  const uint32_t* sn4 = reinterpret_cast<const uint32_t*>(c.seen_row);
-  const bool scale = a.temperature != 1.0f;
-  float bv = -INFINITY;
-  int bi = INT_MAX;
-  const int n4 = a.V >> 2;
-  constexpr int UNR = 4;
-  for (int i0 = lane; i0 < n4; i0 += 32 * UNR) {
-    float4 x[UNR];
-    uint32_t m[UNR], sn[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int i = i0 + 32 * u;
-      const bool ok = i < n4;
-      x[u] = ok ? __ldcs(lg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      m[u] = (ok && mk4 != nullptr) ? mk4[i] : 0x01010101u;
-      sn[u] = (ok && sn4 != nullptr) ? sn4[i] : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int i = i0 + 32 * u;
-      if (i < n4) {
-        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int v = 4 * i + e;
-          float l = adjust_logit(c, v, xs[e], (m[u] >> (8 * e)) & 0xffu, (sn[u] >> (8 * e)) & 0xffu);
-          if (scale) l = l / a.temperature;                     // (:1485-1486)
-          if (arg_better(l, v, bv, bi)) { bv = l; bi = v; }
-        }
-      }
-    }
-  }
+  const int tok = greedy_row_token(a, b, step, lane);
   if (threadIdx.x == 0) pdl_launch_dependents();
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
   // (the batch-global degenerate flag, :1464-1466, only changes how probabilities are sampled; argmax ignores it,
   // and with a type mask every row would hit the same atomic: 4096 serialised updates cost ~75 us per step)
-  if (lane == 0) commit_token(a, b, step, bi, 0.f);             // (:1507)
+  if (lane == 0) commit_token(a, b, step, tok, 0.f);            // (:1507)
 }
 
 // Phase 2: entropy, temperature, multinomial (or argmax) and log-prob, given the batch-global flag.
@@ -788,6 +688,13 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
     const float p = sl[tok] / total;
     commit_token(a, b, step, tok, logf(fmaxf(p, 1e-8f)));                            // (:1518)
   }
+}
+
+bool sampler_plain_greedy(const SamplerArgs& a) {
+  const bool two_phase = !(a.temperature < 0.01f) || a.want_entropy;
+  const bool vec_ok = a.V % 4 == 0 && a.ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a.type_masks) & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.seen) & 3u) == 0;
+  return !two_phase && vec_ok;
 }
 
 int launch_sampler(const SamplerArgs& a_in, int which, cudaStream_t s) {

@@ -99,6 +99,19 @@ struct SamplerArgs {
 // which = 2: second kernel (entropy / temperature sampling / log-prob), only when sampling or entropy is requested
 int launch_sampler(const SamplerArgs& a, int which, cudaStream_t s);
 int launch_step_end(StepState* st, int max_steps, cudaStream_t s);
+// true when launch_sampler(a, 1, ...) is the warp-per-row greedy kernel and nothing else (no second sampler kernel)
+bool sampler_plain_greedy(const SamplerArgs& a);
+
+// Whole-decode persistent kernel (decode_small.cu): what the step loop needs besides the phase list
+struct SmallTail {
+  SamplerArgs sp;                                        // greedy sampling epilogue (sp.st = the call's StepState)
+  const __nv_bfloat16* emb; int ld_emb;                  // token_embedding.weight [V, ld_emb]
+  const float* pe; int d; float* x;                      // pos_encoding.pe [pe_len, d]; residual stream [B, d]
+  int* page_table; int pages_per_seq;
+  int max_steps;
+};
+int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int B, unsigned* bar, int grid, const SmallTail& tail,
+                                cudaStream_t s);
 int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
                      unsigned long long offset, cudaStream_t s);
 

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "decode_kernels.cuh"
+#include "sampler_device.cuh"
 
 namespace scv {
 
@@ -323,7 +324,7 @@ __device__ __forceinline__ AttnPlan attn_plan(const AttnArgs& a) {
 }
 __device__ __forceinline__ size_t attn_row_off(const AttnArgs& a, int b, int h, int p) {
   if (a.page_table != nullptr)
-    return (size_t)a.page_table[(size_t)b * a.pages_per_seq + (p >> kPageShift)] * a.page_stride +
+    return (size_t)__ldcg(a.page_table + (size_t)b * a.pages_per_seq + (p >> kPageShift)) * a.page_stride +
            (size_t)(p & (kPagePos - 1)) * a.row_stride + h * a.hd;
   return (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * a.hd;
 }
@@ -509,6 +510,77 @@ decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, 
   cp_async_wait_all();
 }
 
+// ---- the whole decode in ONE launch (plain greedy calls): the step loop, the sampling epilogue, the embedding of the
+// chosen token and the "every row has emitted END" exit run inside the kernel, so a decode costs two launches (the
+// embedding of the start token + this kernel) instead of five per step, and the host never polls.
+// Everything one step writes and a later step reads is read through L2 (ld.cg / cp.async.cg): L1 is not coherent
+// across SMs and is no longer flushed by kernel boundaries.
+__device__ __forceinline__ void embed_row(const SmallTail& t, int b, int tok, int pos, int lane) {
+  if (lane == 0 && (pos & (kPagePos - 1)) == 0)            // KV page of positions pos .. pos + 15 (embed_kernel)
+    t.page_table[b * t.pages_per_seq + (pos >> kPageShift)] = atomicAdd(&t.sp.st->next_free_page, 1);
+  const __nv_bfloat16* row = t.emb + (size_t)tok * t.ld_emb;
+  const float* pe = t.pe + (size_t)pos * t.d;
+  float* x = t.x + (size_t)b * t.d;
+  for (int i = lane; i < t.d; i += 32) __stcg(x + i, __bfloat162float(row[i]) + __ldg(pe + i));
+}
+
+__global__ void __launch_bounds__(SM_THREADS, 1)
+decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, unsigned* bar, SmallTail tail) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  StepState* st = tail.sp.st;
+  if (st->done) return;
+  int step = st->step;
+  unsigned target = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kDescWords = (int)(sizeof(SmallPhase) / 4);
+  auto desc_load = [&](int p) -> uint32_t {
+    return (int)threadIdx.x < kDescWords ? __ldg(reinterpret_cast<const uint32_t*>(phases + p) + threadIdx.x) : 0u;
+  };
+  auto desc_store = [&](int slot, uint32_t v) {
+    if ((int)threadIdx.x < kDescWords) reinterpret_cast<uint32_t*>(&sm.ph[slot])[threadIdx.x] = v;
+  };
+  desc_store(0, desc_load(0));
+  __syncthreads();
+  prefetch_weights(sm.ph[0], sm, 0, step);
+  int it = 0;                                      // phases executed so far: descriptor slot / weight buffer = it & 1
+  for (;;) {
+    for (int p = 0; p < n_phases; ++p, ++it) {
+      const int cur = it & 1, nxt = cur ^ 1;
+      const uint32_t next_word = desc_load(p + 1 < n_phases ? p + 1 : 0);
+      const SmallPhase& ph = sm.ph[cur];
+      if (ph.kind == 0) run_gemv_phase(ph, sm, cur, B, nullptr);
+      else run_attention_phase(ph.attn, sm, cur, step);
+      desc_store(nxt, next_word);                  // slot nxt was last read in the previous phase
+      __syncthreads();
+      // the next phase's weights / cached rows do not depend on this phase's results (after the last phase: the first
+      // projection of the next step, harmless if the decode ends here)
+      prefetch_weights(sm.ph[nxt], sm, nxt, step);
+      grid_barrier(bar, target);
+    }
+    // sampling epilogue (:1415-1548, plain greedy) + embedding of the chosen token at the next position: warp per row
+    for (int b = (int)blockIdx.x + warp * (int)gridDim.x; b < B; b += (int)gridDim.x * SM_WARPS) {
+      int tok = greedy_row_token(tail.sp, b, step, lane);
+      if (lane == 0) tok = commit_token(tail.sp, b, step, tok, 0.f);
+      tok = __shfl_sync(0xffffffffu, tok, 0);
+      if (step + 1 < tail.max_steps) embed_row(tail, b, tok, step + 1, lane);
+    }
+    grid_barrier(bar, target);
+    // step_end_kernel: every CTA takes the same decision from the same counter (nobody changes it before the next epilogue)
+    const int unfinished = (int)ld_acquire_u32(reinterpret_cast<const unsigned*>(&st->n_unfinished));
+    const int s1 = step + 1;
+    const bool done = unfinished <= 0 || s1 >= tail.max_steps;      // finished.all() -> break (:1547-1548)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->step = s1;
+      st->degenerate = 0;
+      if (done) { st->done = 1; st->out_len = s1; }
+    }
+    if (done) break;
+    step = s1;
+  }
+  cp_async_wait_all();
+}
+
 }  // namespace
 
 size_t small_step_smem_bytes() { return sizeof(Smem); }
@@ -566,6 +638,26 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
               t[2] - t[1], h[2 * p + 1]);
     }
   }
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int B, unsigned* bar, int grid, const SmallTail& tail,
+                                cudaStream_t s) {
+  SCV_REQUIRE(B >= 1 && B <= 32, "small-batch decode: %d rows (1..32 supported)", B);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCV_CUDA(cudaFuncSetAttribute(decode_small_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SM_THREADS); cfg.dynamicSmemBytes = sizeof(Smem); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident, or the launch fails: the barrier cannot hang
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_persist_kernel, phases_dev, n_phases, B, bar, tail));
+  count_launch();
   SCV_LAUNCH_CHECK();
   return 0;
 }

@@ -541,6 +541,14 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
   e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
   SCV_TRY(launch_embed(e, s));
+  if (D->small_active && phase == 3) {     // the whole decode in one launch (plain greedy): step loop inside the kernel
+    SCV_REQUIRE(sampler_plain_greedy(sp), "persistent decode: the call is not plain greedy");
+    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, sizeof(unsigned), s));
+    SmallTail t;
+    t.sp = sp; t.emb = D->emb; t.ld_emb = D->ld_emb; t.pe = D->pe; t.d = d; t.x = x; t.page_table = page_table; t.pages_per_seq = pps;
+    t.max_steps = steps_max;
+    return launch_decode_small_persist(D->sm_phases.as<SmallPhase>(), D->sm_n_phases, B, D->sm_bar.as<unsigned>(), D->sm_grid, t, s);
+  }
   if (D->small_active) {     // layers and heads in one persistent kernel (decode_small.cu); its barrier counter starts at 0
     SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, sizeof(unsigned), s));
     SCV_TRY(launch_decode_small(D->sm_phases.as<SmallPhase>(), D->sm_n_phases, B, st, D->sm_bar.as<unsigned>(), D->sm_grid, s));
@@ -756,7 +764,12 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   cudaGraphExec_t exec = nullptr;
   if (use_graph)
     for (auto& g : D->graphs) if (g.key == key) exec = g.exec;
-  for (int step = 0; step < steps_max; ++step) {
+  // Small batches, plain greedy: the step loop runs inside one persistent kernel (decode_small.cu), no host polling.
+  static const int persist_env = [] { const char* e = getenv("SCV_SMALL_PERSIST"); return e ? atoi(e) : 1; }();
+  const bool persist = D->small_active && persist_env != 0 && !two_phase && !sync_each && A->temperature < 0.01f &&
+                       c.vocab_size % 4 == 0 && (reinterpret_cast<uintptr_t>(A->type_masks) & 3u) == 0;   // sampler_plain_greedy
+  if (persist) SCV_TRY(decode_rows(D, A, steps_max, 0, 0, B, 3, s));
+  for (int step = 0; step < steps_max && !persist; ++step) {
     if (use_graph && step >= 1) {
       if (exec == nullptr) {
         cudaGraph_t graph = nullptr;

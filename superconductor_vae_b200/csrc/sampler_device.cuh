@@ -1,0 +1,123 @@
+// Device-side pieces of the sampling epilogue shared by the per-step sampler kernels (decode_kernels.cu) and the
+// persistent small-batch decode (decode_small.cu).  Everything a step writes and a later step reads (logits, head
+// outputs) is loaded through L2 (ld.cg), so the functions are also correct inside a kernel that spans several steps.
+#pragma once
+#include <limits.h>
+
+#include "decode_kernels.cuh"
+
+namespace scv {
+
+__device__ __forceinline__ bool arg_better(float a, int ia, float b, int ib) {
+  const bool an = isnan(a), bn = isnan(b);     // torch.argmax treats NaN as the maximum
+  if (an != bn) return an;
+  if (!an && a != b) return a > b;
+  return ia < ib;                              // first occurrence wins ties
+}
+
+
+// Row context of the logit adjustments: type mask (:1416-1422), site-dup gate (:1426-1435), stop boost (:1438-1441),
+// hard stop (:1444-1448) and length boost (:1455-1457), applied per element in the reference's order.
+struct RowCtx {
+  const uint8_t* mk; const unsigned char* seen_row;
+  bool stop_on, force, dup_suppress, late;
+  float boost, length_boost;
+};
+__device__ __forceinline__ RowCtx make_row_ctx(const SamplerArgs& a, int b, int step) {
+  RowCtx c;
+  int pred_type = 0;
+  if (a.type_masks != nullptr) {
+    const float* tl = a.type_logits + (size_t)b * a.ldt;
+    float bv = __ldcg(tl);
+    for (int t = 1; t < 5; ++t)
+      { const float v = __ldcg(tl + t); if (arg_better(v, t, bv, pred_type)) { bv = v; pred_type = t; } }
+  }
+  c.stop_on = a.stop_boost > 0.f;
+  float sp = 0.f;
+  c.force = false;
+  if (c.stop_on) {
+    sp = sigmoidf_(__ldcg(a.stop_logits + b));
+    c.force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
+  }
+  c.boost = a.stop_boost * sp;
+  c.late = c.stop_on && step > 10;
+  c.length_boost = c.late ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
+  c.dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(__ldcg(a.dup_logits + b)) < a.dup_threshold;
+  c.seen_row = c.dup_suppress ? a.seen + (size_t)b * a.V : nullptr;
+  c.mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
+  return c;
+}
+// allowed = type-mask byte of v (1 when no mask is given), seen = site-dup byte of v (0 when the gate is off)
+__device__ __forceinline__ float adjust_logit(const RowCtx& c, int v, float l, unsigned allowed, unsigned seen) {
+  if (allowed == 0) l = -INFINITY;
+  if (seen != 0) l = -30.0f;                                  // masked_fill(-30.0), even over a -inf
+  if (v == kEndIdx && c.stop_on) l = l + c.boost;
+  if (c.force) l = (v == kEndIdx) ? 100.0f : -INFINITY;
+  if (v == kEndIdx && c.late) l = l + c.length_boost;
+  return l;
+}
+
+__device__ __forceinline__ int commit_token(const SamplerArgs& a, int b, int step, int token, float logprob) {
+  // single thread
+  if (a.forced != nullptr) token = (int)a.forced[(size_t)b * a.out_ld + step];
+  a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
+  if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
+  a.cur_tokens[b] = token;
+  // ids 20..137 are the element range of the pre-V13 vocabulary; the reference still uses it
+  if (a.seen != nullptr && token >= 20 && token <= 137 && a.finished[b] == 0) a.seen[(size_t)b * a.V + token] = 1;
+  if (token == kEndIdx && a.finished[b] == 0) {
+    a.finished[b] = 1;
+    atomicSub(&a.st->n_unfinished, 1);
+  }
+  return token;
+}
+
+
+// Plain greedy choice of row b (temperature < 0.01, no entropy): one warp per row, 16-byte loads, the adjustments
+// applied per element, running first-occurrence argmax.  Every lane returns the token.
+__device__ __forceinline__ int greedy_row_token(const SamplerArgs& a, int b, int step, int lane) {
+  const RowCtx c = make_row_ctx(a, b, step);
+  const float4* lg = reinterpret_cast<const float4*>(a.logits + (size_t)b * a.ldl);
+  const uint32_t* mk4 = reinterpret_cast<const uint32_t*>(c.mk);
+  const uint32_t* sn4 = reinterpret_cast<const uint32_t*>(c.seen_row);
+  const bool scale = a.temperature != 1.0f;
+  float bv = -INFINITY;
+  int bi = INT_MAX;
+  const int n4 = a.V >> 2;
+  constexpr int UNR = 4;
+  for (int i0 = lane; i0 < n4; i0 += 32 * UNR) {
+    float4 x[UNR];
+    uint32_t m[UNR], sn[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + 32 * u;
+      const bool ok = i < n4;
+      x[u] = ok ? __ldcg(lg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      m[u] = (ok && mk4 != nullptr) ? mk4[i] : 0x01010101u;
+      sn[u] = (ok && sn4 != nullptr) ? sn4[i] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < n4) {
+        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int v = 4 * i + e;
+          float l = adjust_logit(c, v, xs[e], (m[u] >> (8 * e)) & 0xffu, (sn[u] >> (8 * e)) & 0xffu);
+          if (scale) l = l / a.temperature;                     // (:1485-1486)
+          if (arg_better(l, v, bv, bi)) { bv = l; bi = v; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
+}
+
+}  // namespace scv
