@@ -31,7 +31,9 @@ namespace scv {
 
 namespace {
 
-constexpr int SM_THREADS = 256, SM_WARPS = 8;
+constexpr int SM_THREADS = 512, SM_WARPS = 16;   // 4 warps per scheduler: the staging is issue / latency bound
+constexpr int KQ = SM_WARPS / 2;              // k-groups of the MMA loop (warp = row tile x k-group)
+constexpr int RPW = 32 / SM_WARPS;            // staged rows per warp
 constexpr int KC = 640;                       // widest input staged in one piece (a LayerNorm input must be: d_model <= 640)
 constexpr int KCH = 512;                      // wider inputs (the feed-forward width) are staged in chunks of 512 columns
 constexpr int A_PITCH = KC + 8;               // bf16 per staged row: 1296 B, consecutive rows 16 B apart in the banks
@@ -72,10 +74,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire_u32(bar) < target) { __nanosleep(32); }
-    __threadfence();
+    // release: the CTA's writes (ordered before this by the barrier above) are visible to whoever acquires the count
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    while (ld_acquire_u32(bar) < target) {}
   }
   __syncthreads();
 }
@@ -88,7 +89,7 @@ struct Smem {
   __align__(16) __nv_bfloat16 a_lo[32 * A_PITCH];
   __align__(16) unsigned char w[2][W_BUF_BYTES];
 };
-static_assert(4 * 32 * RED_PITCH * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi");
+static_assert(KQ * 32 * RED_PITCH * sizeof(float) <= 2 * 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi + a_lo");
 static_assert(SM_WARPS * MAX_N_SCORES * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "scores alias a_hi");
 
 // Output columns are dealt to the CTAs in contiguous blocks of op.cpc (a multiple of 8 = whole MMA column tiles, see
@@ -114,28 +115,32 @@ __device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf, int st
       cp_async16(dst + (size_t)j * wp + 16 * c, reinterpret_cast<const unsigned char*>(op.w + (size_t)(n0 + j) * op.ldw) + 16 * c);
     }
     dst += (size_t)nc * wp;
+    if (op.ln_g != nullptr && nc > 0) {           // LayerNorm weight and bias of the input rows: K floats each
+      const int q4 = op.K >> 2;
+      for (int i = threadIdx.x; i < 2 * q4; i += SM_THREADS)
+        cp_async16(dst + 16 * i, (i < q4 ? op.ln_g : op.ln_b) + 4 * (i < q4 ? i : i - q4));
+      dst += (size_t)op.K * 8;
+    }
   }
   cp_async_commit();
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
+__device__ __forceinline__ uint32_t bf162_bits(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 // Stage columns [k0, k0 + kc) of the B input rows as bf16 hi / lo, LayerNorm applied on the way (then the chunk is the
-// whole row).  Warp w owns rows 4w .. 4w+3, R rows at a time, a row spread over the lanes as NJ float4s; every load of
+// whole row).  Warp w owns rows RPW * w .. RPW * w + RPW - 1, R rows at a time, a row spread over the lanes as NJ float4s; every load of
 // a round (and the LayerNorm weights) is in flight at once: the input was written by other CTAs in the previous phase
 // and comes through L2, so a round costs one L2 round trip.
 template <int NJ, int R>
-__device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0, int kc, int B) {
+__device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0, int kc, int B, const float* gb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool ln = op.ln_g != nullptr;
 #pragma unroll 1
-  for (int rr = 0; rr < 4; rr += R) {
+  for (int rr = 0; rr < RPW; rr += R) {
     float4 v[R][NJ];
 #pragma unroll
     for (int u = 0; u < R; ++u) {
-      const int r = warp * 4 + rr + u;
+      const int r = warp * RPW + rr + u;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int col = 4 * (lane + 32 * j);
@@ -144,13 +149,6 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
       }
     }
     if (ln) {                                     // two passes over the registers, eps 1e-5 (nn.LayerNorm)
-      float4 g[NJ], bt[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int col = 4 * (lane + 32 * j);
-        g[j] = bt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < kc) { g[j] = __ldg(reinterpret_cast<const float4*>(op.ln_g + col)); bt[j] = __ldg(reinterpret_cast<const float4*>(op.ln_b + col)); }
-      }
       float s[R], q[R];
 #pragma unroll
       for (int u = 0; u < R; ++u) {
@@ -179,37 +177,44 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
 #pragma unroll
         for (int u = 0; u < R; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
 #pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const float mean = s[u], rstd = 1.0f / sqrtf(q[u] / (float)kc + 1e-5f);
+      for (int u = 0; u < R; ++u) q[u] = 1.0f / sqrtf(q[u] / (float)kc + 1e-5f);      // rstd
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          v[u][j].x = (v[u][j].x - mean) * rstd * g[j].x + bt[j].x; v[u][j].y = (v[u][j].y - mean) * rstd * g[j].y + bt[j].y;
-          v[u][j].z = (v[u][j].z - mean) * rstd * g[j].z + bt[j].z; v[u][j].w = (v[u][j].w - mean) * rstd * g[j].w + bt[j].w;
+      for (int j = 0; j < NJ; ++j) {
+        const int col = 4 * (lane + 32 * j);
+        if (col < kc) {
+          const float4 g = *reinterpret_cast<const float4*>(gb + col), bt = *reinterpret_cast<const float4*>(gb + kc + col);
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const float mean = s[u], rstd = q[u];
+            v[u][j].x = (v[u][j].x - mean) * rstd * g.x + bt.x; v[u][j].y = (v[u][j].y - mean) * rstd * g.y + bt.y;
+            v[u][j].z = (v[u][j].z - mean) * rstd * g.z + bt.z; v[u][j].w = (v[u][j].w - mean) * rstd * g.w + bt.w;
+          }
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < R; ++u) {
-      const int r = warp * 4 + rr + u;
+      const int r = warp * RPW + rr + u;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int col = 4 * (lane + 32 * j);
         if (col < kc) {
           const float4 x = v[u][j];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
-          const __nv_bfloat16 l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
-          *reinterpret_cast<uint2*>(sm.a_hi + r * A_PITCH + col) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-          *reinterpret_cast<uint2*>(sm.a_lo + r * A_PITCH + col) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+          // hi = bf16(x), lo = bf16(x - hi): packed converts, two values per instruction
+          const uint32_t h01 = bf162_bits(__floats2bfloat162_rn(x.x, x.y)), h23 = bf162_bits(__floats2bfloat162_rn(x.z, x.w));
+          const uint32_t l01 = bf162_bits(__floats2bfloat162_rn(x.x - __uint_as_float(h01 << 16), x.y - __uint_as_float(h01 & 0xffff0000u)));
+          const uint32_t l23 = bf162_bits(__floats2bfloat162_rn(x.z - __uint_as_float(h23 << 16), x.w - __uint_as_float(h23 & 0xffff0000u)));
+          *reinterpret_cast<uint2*>(sm.a_hi + r * A_PITCH + col) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(sm.a_lo + r * A_PITCH + col) = make_uint2(l01, l23);
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int B) {
-  if (kc <= 512) stage_rows_t<4, 4>(op, sm, k0, kc, B);      // d_model-wide inputs: the warp's four rows in one round
-  else stage_rows_t<KC / 128, 2>(op, sm, k0, kc, B);
+__device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int B, const float* gb) {
+  if (kc <= 512) stage_rows_t<4, RPW>(op, sm, k0, kc, B, gb);    // d_model-wide inputs: the warp's rows in one round
+  else stage_rows_t<KC / 128, RPW>(op, sm, k0, kc, B, gb);
 }
 
 // One projection phase.  Per op: the CTA's nc <= 48 output columns for all 32 (padded) rows as mma.sync m16n8k16 tiles,
@@ -218,7 +223,7 @@ __device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, 
 // output meet in shared memory, then bias / activation / residual and nc contiguous floats per row go to global.
 __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, unsigned long long* tdbg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = warp & 1, kq = warp >> 1;
+  const int mt = warp & 1, kq = warp >> 1;      // row tile, k-group
   const unsigned char* wbase = sm.w[buf];
   float* red = reinterpret_cast<float*>(sm.a_hi);
   for (int o = 0; o < ph.nops; ++o) {
@@ -241,11 +246,12 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
         if (op.res != nullptr) res_v[e] = __ldcg(op.res + (size_t)r * op.ldr + n0 + c);
       }
     }
-    float acc_h[NT_MAX][4], acc_l[NT_MAX][4];
+    float acc[NT_MAX][4];                         // hi and lo products of a k-step go to the same accumulator
 #pragma unroll
     for (int j = 0; j < NT_MAX; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc_h[j][i] = 0.f; acc_l[j][i] = 0.f; }
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    const float* gb = reinterpret_cast<const float*>(wbase + (size_t)nc * wp);   // staged LayerNorm weight | bias
     // ldmatrix row addresses: A x4 = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B x4 = (tile j | j+1) x (k 0-7 | 8-15)
     const int mi = lane >> 3;
     const int a_row = mt * 16 + (lane & 7) + (mi & 1) * 8, a_kofs = (mi >> 1) * 8;
@@ -253,14 +259,14 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
     const int chunk = K > KC ? KCH : KC;
     for (int k0 = 0; k0 < K; k0 += chunk) {
       const int kc = min(chunk, K - k0);
-      __syncthreads();                            // the previous chunk / op / phase is done with a_hi, a_lo
+      cp_async_wait_all();                        // this phase's weight rows and LayerNorm weights, copied before the barrier ...
+      __syncthreads();                            // ... by every thread; the previous chunk / op / phase is done with a_hi, a_lo
       if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[0]));
-      stage_rows(op, sm, k0, kc, B);
-      cp_async_wait_all();                        // this phase's weight rows have landed (own copies) ...
-      __syncthreads();                            // ... and everybody else's; the staged rows are complete
+      stage_rows(op, sm, k0, kc, B, gb);
+      __syncthreads();                            // the staged rows are complete
       if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[1]));
       const int steps = kc >> 4;
-      for (int ks = kq; ks < steps; ks += 4) {
+      for (int ks = kq; ks < steps; ks += KQ) {
         uint32_t ah[4], al[4];
         ldmatrix_x4(ah, sm.a_hi + a_row * A_PITCH + ks * 16 + a_kofs);
         ldmatrix_x4(al, sm.a_lo + a_row * A_PITCH + ks * 16 + a_kofs);
@@ -270,12 +276,10 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
             const int wrow = min((2 * jp + (mi >> 1)) * 8 + (lane & 7), nc - 1);      // rows beyond nc: a duplicate, never stored
             uint32_t b[4];
             ldmatrix_x4(b, wbase + (size_t)wrow * wp + 2 * (k0 + ks * 16 + b_kofs));
-            mma_bf16(acc_h[2 * jp], ah, b[0], b[1]);
-            mma_bf16(acc_l[2 * jp], al, b[0], b[1]);
-            if (2 * jp + 1 < ntiles) {
-              mma_bf16(acc_h[2 * jp + 1], ah, b[2], b[3]);
-              mma_bf16(acc_l[2 * jp + 1], al, b[2], b[3]);
-            }
+            mma_bf16(acc[2 * jp], ah, b[0], b[1]);
+            if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], ah, b[2], b[3]);
+            mma_bf16(acc[2 * jp], al, b[0], b[1]);
+            if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], al, b[2], b[3]);
           }
         }
       }
@@ -288,8 +292,8 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
 #pragma unroll
       for (int j = 0; j < NT_MAX; ++j) {
         if (j < ntiles) {
-          *reinterpret_cast<float2*>(r0 + 8 * j) = make_float2(acc_h[j][0] + acc_l[j][0], acc_h[j][1] + acc_l[j][1]);
-          *reinterpret_cast<float2*>(r0 + 8 * RED_PITCH + 8 * j) = make_float2(acc_h[j][2] + acc_l[j][2], acc_h[j][3] + acc_l[j][3]);
+          *reinterpret_cast<float2*>(r0 + 8 * j) = make_float2(acc[j][0], acc[j][1]);
+          *reinterpret_cast<float2*>(r0 + 8 * RED_PITCH + 8 * j) = make_float2(acc[j][2], acc[j][3]);
         }
       }
     }
@@ -300,13 +304,16 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
       const int r = idx / nc, c = idx - r * nc;
       if (r < B) {
         const float* p = red + (size_t)r * RED_PITCH + c;
-        float v = (p[0] + p[32 * RED_PITCH]) + (p[64 * RED_PITCH] + p[96 * RED_PITCH]);
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < KQ; ++g) v += p[g * 32 * RED_PITCH];
         v = apply_act(v + bias_v[e], op.act);
         if (op.res != nullptr) v += res_v[e];
         __stcg(op.out + (size_t)r * op.ldo + n0 + c, v);
       }
     }
-    wbase += (size_t)nc * wp;
+    if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[3]));
+    wbase += (size_t)nc * wp + (op.ln_g != nullptr ? (size_t)op.K * 8 : 0);
   }
 }
 
@@ -319,7 +326,7 @@ struct AttnPlan { int ppc, cap; };               // pairs per CTA, prefetchable 
 __device__ __forceinline__ AttnPlan attn_plan(const AttnArgs& a) {
   AttnPlan pl;
   pl.ppc = (a.B * a.nhead + (int)gridDim.x - 1) / (int)gridDim.x;
-  pl.cap = W_BUF_BYTES / (pl.ppc * 2 * a.hd * (int)sizeof(float));
+  pl.cap = min(W_BUF_BYTES / (pl.ppc * 2 * a.hd * (int)sizeof(float)), 4 * kPagePos);   // four page indices in registers
   return pl;
 }
 __device__ __forceinline__ size_t attn_row_off(const AttnArgs& a, int b, int h, int p) {
@@ -339,9 +346,27 @@ __device__ void prefetch_attention(const AttnArgs& a, Smem& sm, int buf, int ste
     const int np = min(a.knew != nullptr ? n - 1 : n, pl.cap);          // self: the last row is produced in the phase itself
     float* kv = reinterpret_cast<float*>(sm.w[buf]) + (size_t)warp * 2 * pl.cap * a.hd;
     const int cpr = a.hd >> 2;                                           // 16-byte pieces per row
+    // paged cache: the (<= 4, cap <= 64 positions) page indices of the row, all in flight at once, instead of one
+    // dependent L2 round trip per copy
+    int pg0 = 0, pg1 = 0, pg2 = 0, pg3 = 0;
+    if (a.page_table != nullptr) {
+      const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
+      if (np > 0) pg0 = __ldcg(pt);
+      if (np > kPagePos) pg1 = __ldcg(pt + 1);
+      if (np > 2 * kPagePos) pg2 = __ldcg(pt + 2);
+      if (np > 3 * kPagePos) pg3 = __ldcg(pt + 3);
+    }
+    const bool pow2 = cpr == 16;
     for (int i = lane; i < np * cpr; i += 32) {
-      const int p = i / cpr, c = i - p * cpr;
-      const size_t off = attn_row_off(a, b, h, p) + 4 * c;
+      const int p = pow2 ? i >> 4 : i / cpr, c = pow2 ? i & 15 : i - p * cpr;
+      size_t off;
+      if (a.page_table != nullptr) {
+        const int q = p >> kPageShift;
+        const int pg = q == 0 ? pg0 : q == 1 ? pg1 : q == 2 ? pg2 : pg3;
+        off = (size_t)pg * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * a.hd + 4 * c;
+      } else {
+        off = (size_t)b * a.seq_stride + (size_t)p * a.row_stride + h * a.hd + 4 * c;
+      }
       cp_async16(kv + (size_t)p * a.hd + 4 * c, a.kcache + off);
       cp_async16(kv + (size_t)(pl.cap + p) * a.hd + 4 * c, a.vcache + off);
     }
@@ -604,7 +629,7 @@ bool small_phase_fits(const SmallPhase& ph, int grid) {
     if (op.cpc % 8 != 0 || op.cpc > NT_MAX * 8 || (long long)op.cpc * grid < op.N) return false;   // accumulators: 6 tiles of 8 columns
     if (op.ln_g != nullptr && (op.K > KC || ((reinterpret_cast<uintptr_t>(op.ln_g) | reinterpret_cast<uintptr_t>(op.ln_b)) & 15u) != 0))
       return false;                                           // the LayerNorm needs the whole row in one chunk
-    bytes += (size_t)op.cpc * (op.ldw * 2 + W_ROW_PAD);
+    bytes += (size_t)op.cpc * (op.ldw * 2 + W_ROW_PAD) + (op.ln_g != nullptr ? (size_t)op.K * 8 : 0);
   }
   return bytes <= (size_t)W_BUF_BYTES;
 }
@@ -634,8 +659,8 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
     SCV_CUDA(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
     for (int p = 0; p < n_phases; ++p) {
       const unsigned long long* t = h.data() + 2048 + 4 * p;
-      fprintf(stderr, "phase %3d: run %6llu ns (stage %6llu, mma %6llu), prefetch+barrier %6llu ns\n", p, h[2 * p], t[1] - t[0],
-              t[2] - t[1], h[2 * p + 1]);
+      fprintf(stderr, "phase %3d: run %6llu ns (stage %6llu, mma %6llu, epilogue %6llu), prefetch+barrier %6llu ns\n", p, h[2 * p],
+              t[1] - t[0], t[2] - t[1], t[3] - t[2], h[2 * p + 1]);
     }
   }
   SCV_LAUNCH_CHECK();

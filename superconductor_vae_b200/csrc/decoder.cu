@@ -383,7 +383,7 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   const scv_decoder_config& c = D->cfg;
   const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward, pps = ceil_div(c.pe_len, kPagePos);
   D->small_active = false;
-  static const int env = [] { const char* e = getenv("SCV_SMALL"); return e ? atoi(e) : 0; }();   // opt-in, see decode_small.cu
+  static const int env = [] { const char* e = getenv("SCV_SMALL"); return e ? atoi(e) : 1; }();   // SCV_SMALL=0: per-projection path
   if (!env || B > 32 || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
   if (D->sm_grid == 0) {
     int dev = 0, sms = 0;
