@@ -53,10 +53,11 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; started before the warm-up (nvidia-smi needs a few
+    hundred ms to come up), reported over the timed region only (samples are time-stamped by the reader thread)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,clocks.mem")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -64,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -72,24 +73,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is not None:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        in_window = len(rows)
+        if not rows:                                   # region shorter than a sampling period: everything under load
+            rows = [r for _, r in self.rows]
+        sm, mx, mem, reasons = [], [], [], set()
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
+            try:
+                mem.append(float(r[8]))
+            except Exception:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         hot = [v for v in sm if v >= 0.5 * (max(sm) if sm else 0)]
         return {"sm_mhz": hot[len(hot) // 2] if hot else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "mem_mhz": sorted(mem)[len(mem) // 2] if mem else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": in_window}
 
 
 def algorithmic_bytes(B, executed_steps, kv_bytes_per_pos=49152, weight_bytes=107_091_244):
@@ -234,20 +244,21 @@ def run_engine(args, rank, local_rank, world):
                           "launches_per_decode": _lib.launch_count() // (args.warmup + 1)}))
         return
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step_resident()
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    t_region0 = time.time()
     n0 = _lib.launch_count()
     ms_total, toks = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
     barrier()
     ms_e2e, _ = timed(step_e2e, args.steps)
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop(t_region0, time.time())
     L = int(toks.shape[1])
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -311,6 +322,32 @@ def run_engine(args, rank, local_rank, world):
             cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_rows} latents of the same workload ({cL} executed steps, {cdt:.1f} s), "
                              f"CPU oracle port, torch fp32, {threads} threads"}
+        # small-batch regime (BASELINE config 1 shape: 32 latents, max_len 64): one persistent kernel per decode
+        small = None
+        if world == 1:
+            Bs = 32
+            zs, sts = z[:Bs].contiguous(), st[:Bs].contiguous()
+            hps = {k: v[:Bs].contiguous() for k, v in hp.items()}
+            kws = dict(temperature=0.001, max_len=max_len)          # no masks / stop head: all max_len - 1 steps run
+            for _ in range(2):
+                dec.generate_with_kv_cache(zs, stoich_pred=sts, heads_pred=hps, **kws)
+            n1 = _lib.launch_count()
+            reps = 5
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                ts, _, _ = dec.generate_with_kv_cache(zs, stoich_pred=sts, heads_pred=hps, **kws)
+            b.record()
+            b.synchronize()
+            ms_s = a.elapsed_time(b) / reps
+            Ls = int(ts.shape[1])
+            small = {"workload": f"{Bs} latents, greedy, max_len {max_len}, no masks / stop head ({Ls} executed steps), "
+                                 "whole decode in one persistent cooperative kernel (csrc/decode_small.cu)",
+                     "ms_per_decode": ms_s, "us_per_step": 1e3 * ms_s / Ls, "formulas_per_s": Bs / (ms_s / 1e3),
+                     "launches_per_decode": (_lib.launch_count() - n1) / reps,
+                     "hbm_algorithmic_gbs": algorithmic_bytes(Bs, Ls) / (ms_s * 1e6),
+                     "hbm_frac": algorithmic_bytes(Bs, Ls) / (ms_s * 1e6) / pk["hbm_gbs"],
+                     "note": "bound by the ~100 dependent grid-wide phases of a step (8 per layer), not by HBM: see DESIGN.md section 4"}
         per_gpu_ms = ms_total / args.steps
         step_roof = {
             "hbm_algorithmic_gbs": algorithmic_bytes(B, L) / (per_gpu_ms * 1e6),
@@ -329,7 +366,7 @@ def run_engine(args, rank, local_rank, world):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": B * L * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm_kernel": roof_hbm,
-            "step_roofline": step_roof,
+            "step_roofline": step_roof, "small_batch": small,
             "kernels": kernels, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
@@ -343,7 +380,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="latents per GPU")
     ap.add_argument("--max-len", type=int, default=64)
-    ap.add_argument("--cpu-rows", type=int, default=64, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=1536, help="rows of the bounded CPU-baseline sample (10-20 s of CPU work)")
     ap.add_argument("--ncu", action="store_true", help="short run for ncu: warm-up decodes + one decode, no timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -68,15 +68,27 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Grid-wide barrier over co-resident CTAs (the launch is cooperative: one CTA per SM).  `bar` counts arrivals and is
-// reset to zero by a memset before the launch.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+// Grid-wide barrier over co-resident CTAs (the launch is cooperative: one CTA per SM).  The arrivals are spread over
+// kBarShards counters in separate 128-byte lines (atomics on one address are serialised by the L2); CTA b adds to
+// counter b % kBarShards and lanes 0 .. kBarShards-1 of warp 0 poll one counter each.  `bar` is zeroed by a memset
+// before the launch; the counters only grow (epoch * CTAs of the shard).  Measured at 32 rows: 1, 4 and 8 shards are
+// within 1 % of each other (782 / 781 / 789 us per step), so the default is one counter (SCV_SMALL_BAR_SHARDS): the
+// barrier's ~2 us are the release fence plus two L2 round trips, not the serialised atomics.  One release-store flag
+// per CTA polled by every CTA was also tried: 148 x 148 acquire loads per poll round on five lines, 1190 us per step.
+constexpr int kBarWords = 256;                    // 8 counters, 32 words (128 B) apart
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, int shards) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    // release: the CTA's writes (ordered before this by the barrier above) are visible to whoever acquires the count
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    while (ld_acquire_u32(bar) < target) {}
+  epoch += 1;
+  if (threadIdx.x < 32) {
+    const int lane = (int)threadIdx.x;
+    if (lane == 0)                                // release: the CTA's writes (ordered before this by the barrier above)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 32 * ((int)blockIdx.x % shards)) : "memory");
+    const unsigned members = lane < shards ? ((unsigned)gridDim.x - (unsigned)lane + (unsigned)shards - 1u) / (unsigned)shards : 0u;
+    const unsigned want = members * epoch;
+    for (;;) {
+      const bool ok = lane >= shards || ld_acquire_u32(bar + 32 * lane) >= want;
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
   }
   __syncthreads();
 }
@@ -493,12 +505,12 @@ __device__ void run_attention_phase(const AttnArgs& a_in, Smem& sm, int buf, int
 
 __global__ void __launch_bounds__(SM_THREADS, 1)
 decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, const StepState* st, unsigned* bar,
-                    unsigned long long* dbg) {
+                    int bar_shards, unsigned long long* dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   if (st->done) return;                           // uniform: written by step_end_kernel of an earlier launch
   const int step = st->step;
-  unsigned target = 0;
+  unsigned target = 0;                            // barrier epoch
   // phase descriptors are read through shared memory (ph[p & 1]); the next one travels through a register while the
   // current phase runs (one word per thread), so its L2 latency is never waited for
   constexpr int kDescWords = (int)(sizeof(SmallPhase) / 4);
@@ -525,7 +537,7 @@ decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, 
       desc_store(p + 1, next_word);                        // slot (p + 1) & 1 was last read in phase p - 1
       __syncthreads();                                     // the staged descriptor of phase p + 1 is complete
       prefetch_weights(sm.ph[(p + 1) & 1], sm, (p + 1) & 1, step);   // weights / cached rows do not depend on this phase's results
-      grid_barrier(bar, target);
+      grid_barrier(bar, target, bar_shards);
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
@@ -550,13 +562,13 @@ __device__ __forceinline__ void embed_row(const SmallTail& t, int b, int tok, in
 }
 
 __global__ void __launch_bounds__(SM_THREADS, 1)
-decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, unsigned* bar, SmallTail tail) {
+decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, unsigned* bar, int bar_shards, SmallTail tail) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   StepState* st = tail.sp.st;
   if (st->done) return;
   int step = st->step;
-  unsigned target = 0;
+  unsigned target = 0;                            // barrier epoch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kDescWords = (int)(sizeof(SmallPhase) / 4);
   auto desc_load = [&](int p) -> uint32_t {
@@ -581,7 +593,7 @@ decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases,
       // the next phase's weights / cached rows do not depend on this phase's results (after the last phase: the first
       // projection of the next step, harmless if the decode ends here)
       prefetch_weights(sm.ph[nxt], sm, nxt, step);
-      grid_barrier(bar, target);
+      grid_barrier(bar, target, bar_shards);
     }
     // sampling epilogue (:1415-1548, plain greedy) + embedding of the chosen token at the next position: warp per row
     for (int b = (int)blockIdx.x + warp * (int)gridDim.x; b < B; b += (int)gridDim.x * SM_WARPS) {
@@ -590,7 +602,7 @@ decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases,
       tok = __shfl_sync(0xffffffffu, tok, 0);
       if (step + 1 < tail.max_steps) embed_row(tail, b, tok, step + 1, lane);
     }
-    grid_barrier(bar, target);
+    grid_barrier(bar, target, bar_shards);
     // step_end_kernel: every CTA takes the same decision from the same counter (nobody changes it before the next epilogue)
     const int unfinished = (int)ld_acquire_u32(reinterpret_cast<const unsigned*>(&st->n_unfinished));
     const int s1 = step + 1;
@@ -609,6 +621,11 @@ decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases,
 }  // namespace
 
 size_t small_step_smem_bytes() { return sizeof(Smem); }
+
+static int bar_shards_env() {
+  static const int v = [] { const char* e = getenv("SCV_SMALL_BAR_SHARDS"); return std::max(1, std::min(e ? atoi(e) : 1, kBarWords / 32)); }();
+  return v;
+}
 
 int small_cols_per_cta(int N, int grid) {
   // whole 8-column MMA tiles: rounding up never adds a tile to the busiest CTA, and fewer CTAs stage the input rows
@@ -652,7 +669,7 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
   static int dbg_calls = 0;
   static const int dbg_env = [] { const char* e = getenv("SCV_SMALL_DEBUG"); return e ? atoi(e) : 0; }();
   if (dbg_env && dbg == nullptr) { SCV_CUDA(cudaMalloc(&dbg, 4096 * 8)); SCV_CUDA(cudaMemset(dbg, 0, 4096 * 8)); }
-  SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_kernel, phases_dev, n_phases, B, st, bar, dbg));
+  SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_kernel, phases_dev, n_phases, B, st, bar, bar_shards_env(), dbg));
   if (dbg_env && ++dbg_calls == dbg_env) {
     SCV_CUDA(cudaStreamSynchronize(s));
     std::vector<unsigned long long> h(4096);
@@ -681,7 +698,7 @@ int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int 
   attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident, or the launch fails: the barrier cannot hang
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_persist_kernel, phases_dev, n_phases, B, bar, tail));
+  SCV_CUDA(cudaLaunchKernelEx(&cfg, decode_small_persist_kernel, phases_dev, n_phases, B, bar, bar_shards_env(), tail));
   count_launch();
   SCV_LAUNCH_CHECK();
   return 0;

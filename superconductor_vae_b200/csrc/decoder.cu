@@ -391,8 +391,9 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
     SCV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     D->sm_grid = sms;
   }
+  if (D->sm_grid > 256) return 0;               // one barrier flag per CTA, 256 flags (decode_small.cu)
   // fixed sizes: a captured step holds these pointers, so they must never be reallocated
-  SCV_TRY(D->sm_bar.ensure(sizeof(unsigned)));
+  SCV_TRY(D->sm_bar.ensure(256 * sizeof(unsigned)));      // one barrier flag per CTA (decode_small.cu kBarWords)
   SCV_TRY(D->sm_h2b.ensure((size_t)32 * d * sizeof(float)));
   SCV_TRY(D->sm_t3s.ensure((size_t)32 * d * sizeof(float)));
   SCV_TRY(D->sm_t3d.ensure((size_t)32 * d * sizeof(float)));
@@ -543,14 +544,14 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   SCV_TRY(launch_embed(e, s));
   if (D->small_active && phase == 3) {     // the whole decode in one launch (plain greedy): step loop inside the kernel
     SCV_REQUIRE(sampler_plain_greedy(sp), "persistent decode: the call is not plain greedy");
-    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, sizeof(unsigned), s));
+    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, 256 * sizeof(unsigned), s));
     SmallTail t;
     t.sp = sp; t.emb = D->emb; t.ld_emb = D->ld_emb; t.pe = D->pe; t.d = d; t.x = x; t.page_table = page_table; t.pages_per_seq = pps;
     t.max_steps = steps_max;
     return launch_decode_small_persist(D->sm_phases.as<SmallPhase>(), D->sm_n_phases, B, D->sm_bar.as<unsigned>(), D->sm_grid, t, s);
   }
   if (D->small_active) {     // layers and heads in one persistent kernel (decode_small.cu); its barrier counter starts at 0
-    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, sizeof(unsigned), s));
+    SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, 256 * sizeof(unsigned), s));
     SCV_TRY(launch_decode_small(D->sm_phases.as<SmallPhase>(), D->sm_n_phases, B, st, D->sm_bar.as<unsigned>(), D->sm_grid, s));
     return launch_sampler(sp, 1, s);
   }
