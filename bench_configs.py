@@ -75,6 +75,21 @@ def main():
                           "entropy and mask (stop_boost 10, no hard masks so the reference's H2 fallback cannot trip)",
                           "rows": B * k, "executed_decode_steps": int(t.shape[1]), "ms": ms,
                           "formulas_per_s": B * k / (ms / 1e3), "mean_len": float(mk.sum(1).mean())}))
+        # f1: the token-level reward of those rollouts (compute_reward_gpu_native, V14 continuous reward + semantic
+        # fraction values, as scripts/train_v12_clean.py:2745-2752 calls it): one kernel
+        from superconductor_vae_b200 import reward as R
+        L = int(t.shape[1])
+        _, targets, _ = Sy.make_reward_rows(B, L, 4752, 11)
+        targets = targets.to(dev).repeat(k, 1)
+        fv = Sy.make_fraction_values(4752, 143, 7).to(dev)
+        cfg = R.GPURewardConfigV14()
+        rfn = lambda: R.compute_reward_gpu_native(t, targets, mk.bool(), config=cfg, use_semantic_fractions=True,
+                                                  fraction_token_start=143, fraction_values=fv)
+        rms, rew = timed(rfn, warmup=2, iters=20)
+        emit(({"config": "f1", "what": "token-level rollout reward (V14 continuous + semantic fraction penalty) of the "
+                          "config-3 rollouts: one warp-per-row kernel", "rows": B * k, "seq_len": L, "us": 1e3 * rms,
+                          "rows_per_s": B * k / (rms / 1e3), "algorithmic_bytes": B * k * L * 17,
+                          "gbs": B * k * L * 17 / (rms * 1e6), "mean_reward": float(rew.mean())}))
 
     if 5 in todo and rank == 0:
         n = 52800

@@ -178,6 +178,32 @@ int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const i
 int scv_tokens_canonical_hash(const int64_t* tokens, int64_t n_rows, int32_t row_len, int16_t* canonical,
                               uint64_t* hash, int32_t* length, void* stream);
 
+/* Token-level rollout reward (replaces compute_reward_gpu_native,
+ * src/superconductor/losses/reward_gpu_native.py:448-722, called after every rollout at
+ * scripts/train_v12_clean.py:2745-2752, 2829-2836, 2942-2950).  The struct carries the fields of GPURewardConfig
+ * (:42-79) and GPURewardConfigV14 (:82-131) under their reference names; `v14` = "the caller passed a
+ * GPURewardConfigV14" (the reference branches on isinstance, :564). */
+typedef struct scv_reward_config {
+  float exact_match, near_exact_1, near_exact_2, near_exact_3, token_correct, token_penalty, length_mismatch_penalty;
+  float fraction_digit_penalty, fraction_structure_penalty;
+  int32_t use_semantic_digit_penalty;
+  float semantic_digit_scale, length_only_base_reward, length_only_per_extra, length_only_floor;
+  int32_t v14, use_continuous_reward;
+  float max_reward, sharpness, element_error_penalty, integer_error_penalty, fraction_error_penalty, special_error_penalty;
+  float too_short_base_reward, too_short_per_missing, too_short_floor;
+  int32_t use_phased_curriculum, reward_phase;
+  float phase3_sharpness;
+  int32_t v14_element_start, v14_element_end, v14_integer_start, v14_integer_end, v14_fraction_start;
+} scv_reward_config;
+/* sampled, target: int64 [batch, seq_len] with `row_stride` elements between rows; mask: one byte per position
+ * (nonzero = valid), same stride; fraction_values: float [n_fraction_values] or NULL (then, as in the reference, the
+ * digit-level penalties of the pre-V13 vocabulary apply even if use_semantic_fractions is set); rewards: float [batch].
+ * All pointers are device pointers. */
+int scv_reward_tokens(const int64_t* sampled, const int64_t* target, const uint8_t* mask, int32_t batch,
+                      int32_t seq_len, int64_t row_stride, const scv_reward_config* config, int32_t end_idx,
+                      int32_t use_semantic_fractions, int32_t fraction_token_start, const float* fraction_values,
+                      int32_t n_fraction_values, float* rewards, void* stream);
+
 /* ---------------------------------------------------------------- kernel-level taps (tests) */
 /* y[M,N] = act(x[M,K] * w[N,K]^T + bias) (+ residual); w is bf16 with row stride ldw (elements).
  * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 1 SIMT fp32 (w_bf16 row-major), 2 tcgen05 hi/lo bf16

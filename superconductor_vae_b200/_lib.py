@@ -53,6 +53,24 @@ class EncoderConfig(C.Structure):
         ("n_decoder_hidden", C.c_int32), ("decoder_hidden", C.c_int32 * 4)]
 
 
+class RewardConfig(C.Structure):
+    """scv_reward_config (include/scvae_b200.h): GPURewardConfig + GPURewardConfigV14 fields under their reference names."""
+    _fields_ = (
+        [(n, C.c_float) for n in ("exact_match", "near_exact_1", "near_exact_2", "near_exact_3", "token_correct",
+                                  "token_penalty", "length_mismatch_penalty", "fraction_digit_penalty",
+                                  "fraction_structure_penalty")]
+        + [("use_semantic_digit_penalty", C.c_int32)]
+        + [(n, C.c_float) for n in ("semantic_digit_scale", "length_only_base_reward", "length_only_per_extra",
+                                    "length_only_floor")]
+        + [("v14", C.c_int32), ("use_continuous_reward", C.c_int32)]
+        + [(n, C.c_float) for n in ("max_reward", "sharpness", "element_error_penalty", "integer_error_penalty",
+                                    "fraction_error_penalty", "special_error_penalty", "too_short_base_reward",
+                                    "too_short_per_missing", "too_short_floor")]
+        + [("use_phased_curriculum", C.c_int32), ("reward_phase", C.c_int32), ("phase3_sharpness", C.c_float)]
+        + [(n, C.c_int32) for n in ("v14_element_start", "v14_element_end", "v14_integer_start", "v14_integer_end",
+                                    "v14_fraction_start")])
+
+
 HEADS_OUT_FIELDS = (
     "tc_pred", "magpie_pred", "attended_input", "tc_class_logits", "competence", "fraction_pred",
     "element_count_pred", "hp_pred", "sc_pred", "family_coarse_logits", "family_cuprate_sub_logits",
@@ -95,6 +113,8 @@ SIGNATURES = {
     "scv_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "scv_tokens_canonical_hash": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
+    "scv_reward_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scv_op_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p]),

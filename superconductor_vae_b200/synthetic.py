@@ -287,3 +287,75 @@ def make_compositions(n: int, seed: int = 1234, max_elements: int = 12, n_elemen
     magpie = torch.randn((n, magpie_dim), generator=g)
     tc = torch.randn((n,), generator=g)
     return idx, frac, mask, magpie, tc
+
+
+# ------------------------------------------------------------------------------------------------ reward inputs (f1)
+def make_fraction_values(vocab: int = 4752, fraction_token_start: int = 143, seed: int = 4242) -> torch.Tensor:
+    """Per-token float value table of the semantic fraction tokens (scripts/train_v12_clean.py:2556-2564): zero below
+    `fraction_token_start`, here uniform in [0, 25) so that the 20.0 clamp of the value penalty is reached."""
+    g = torch.Generator().manual_seed(seed)
+    fv = torch.zeros(vocab)
+    fv[fraction_token_start:] = torch.rand(vocab - fraction_token_start, generator=g) * 25.0
+    return fv
+
+
+def make_reward_rows(n: int, seq_len: int, vocab: int = 4752, seed: int = 4242, old_vocab: bool = False):
+    """Seeded (sampled, target, mask) rows for the rollout reward, built to reach every branch of
+    `compute_reward_gpu_native`: exact copies, 1-6 substitutions, samples that stop early / run on after a correct
+    prefix, samples without END, fully random rows, and masks both "up to the sample's END" (what
+    sample_for_reinforce returns) and all-ones.  Targets are START-less formulas `tokens... END PAD...`
+    (PAD=0, END=2).  old_vocab=True draws from the pre-V13 ids the digit-level penalties look at
+    (parentheses 4/5, slash 16, digits 138-147)."""
+    g = torch.Generator().manual_seed(seed)
+    if old_vocab:
+        pool = torch.tensor([4, 5, 16] * 6 + list(range(138, 148)) * 3 + list(range(20, 60)))
+    else:
+        pool = torch.cat([torch.arange(5, 123), torch.arange(123, 143), torch.randint(143, vocab, (160,), generator=g)])
+
+    def draw(k):
+        return pool[torch.randint(0, pool.numel(), (k,), generator=g)]
+
+    sampled = torch.zeros((n, seq_len), dtype=torch.long)
+    target = torch.zeros((n, seq_len), dtype=torch.long)
+    mask = torch.zeros((n, seq_len), dtype=torch.bool)
+    for b in range(n):
+        tl = int(torch.randint(3, seq_len - 2, (1,), generator=g))        # formula tokens before END
+        t = torch.zeros(seq_len, dtype=torch.long)
+        t[:tl] = draw(tl)
+        t[tl] = 2
+        s = t.clone()
+        kind = b % 10
+        if kind in (1, 2, 3):                                              # a few substitutions
+            for p in torch.randperm(tl, generator=g)[: int(torch.randint(1, 7, (1,), generator=g))]:
+                s[p] = draw(1)[0]
+        elif kind == 4:                                                    # correct prefix, stops early
+            cut = int(torch.randint(1, tl, (1,), generator=g))
+            s[cut] = 2
+            s[cut + 1:] = 0
+        elif kind == 5:                                                    # correct formula, runs on
+            ext = int(torch.randint(1, seq_len - tl - 1, (1,), generator=g)) if seq_len - tl - 1 > 1 else 1
+            s[tl:tl + ext] = draw(ext)
+            if tl + ext < seq_len:
+                s[tl + ext] = 2
+        elif kind == 6:                                                    # never emits END
+            s[:] = draw(seq_len)
+            s[s == 2] = 7
+        elif kind == 7:                                                    # unrelated sample
+            sl = int(torch.randint(1, seq_len - 1, (1,), generator=g))
+            s[:] = 0
+            s[:sl] = draw(sl)
+            s[sl] = 2
+        elif kind == 8:                                                    # substitutions + wrong length
+            for p in torch.randperm(tl, generator=g)[:2]:
+                s[p] = draw(1)[0]
+            s[tl] = draw(1)[0]
+            if tl + 1 < seq_len:
+                s[tl + 1] = 2
+        # kinds 0 and 9: exact copies
+        sampled[b], target[b] = s, t
+        if b % 3 == 0:
+            mask[b] = True
+        else:                                                              # 1 up to and including the sample's first END
+            e = (s == 2).nonzero()
+            mask[b, : (int(e[0]) + 1 if e.numel() else seq_len)] = True
+    return sampled, target, mask
