@@ -90,6 +90,19 @@ def main():
                           "config-3 rollouts: one warp-per-row kernel", "rows": B * k, "seq_len": L, "us": 1e3 * rms,
                           "rows_per_s": B * k / (rms / 1e3), "algorithmic_bytes": B * k * L * 17,
                           "gbs": B * k * L * 17 / (rms * 1e6), "mean_reward": float(rew.mean())}))
+        # the chemistry-constraint rewards added to it (compute_constraint_rewards, :2754-2766): the reference walks every
+        # row on the host with Python loops; here one kernel.  Formula-like rows of the rollout's shape.
+        from superconductor_vae_b200 import constraints as K
+        ctok, cmask = Sy.make_constraint_rows(B * k, L, 31, True)
+        ctok, cmask = ctok.to(dev), cmask.to(dev)
+        fam = Sy.make_family_probs(B * k, 32).to(dev)
+        K.set_vocab_config(K.make_v13_vocab_config(143, Sy.make_constraint_fraction_values().to(dev)))
+        kfn = lambda: K.compute_constraint_rewards(ctok, cmask, K.ConstraintRewardConfig(), fam, K.FamilyConstraintConfig())
+        kms, kr = timed(kfn, warmup=2, iters=20)
+        K.set_vocab_config(K.VocabConfig())
+        emit(({"config": "f1-constraints", "what": "chemistry-constraint rewards (A1, A2, A4, A7, B1-B8) of 8192 formula-like "
+                          "rows: one thread-per-row kernel over rows staged in shared memory", "rows": B * k, "seq_len": L,
+                          "us": 1e3 * kms, "rows_per_s": B * k / (kms / 1e3), "rows_penalised": int((kr != 0).sum())}))
 
     if 5 in todo and rank == 0:
         n = 52800

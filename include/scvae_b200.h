@@ -204,6 +204,26 @@ int scv_reward_tokens(const int64_t* sampled, const int64_t* target, const uint8
                       int32_t use_semantic_fractions, int32_t fraction_token_start, const float* fraction_values,
                       int32_t n_fraction_values, float* rewards, void* stream);
 
+/* Chemistry-constraint rewards of a rollout (replaces compute_constraint_rewards,
+ * src/superconductor/losses/constraint_rewards.py:629-676 = A1 :270-303 + A2 :306-379 + A4 :382-459 + A7 :462-507 +
+ * B1-B8 :510-626 over the parser :172-267; call sites scripts/train_v12_clean.py:2754-2766, 2990-3007).  The struct
+ * carries VocabConfig (:29-56), ConstraintRewardConfig (:132-149) and FamilyConstraintConfig (:152-167) under their
+ * reference names; penalties and the threshold are doubles like the Python floats they replace; b_penalty[i] = b{i+1}. */
+typedef struct scv_constraint_config {
+  int32_t element_start, element_end, digit_start, digit_end, lparen_idx, rparen_idx, slash_idx, pad_idx, end_idx;
+  int32_t use_semantic_fractions, fraction_token_start;
+  int32_t a1_enabled, a2_enabled, a4_enabled, a7_enabled, family_enabled;
+  double a1_penalty, a2_penalty_per_violation, a4_penalty, a7_penalty, confidence_threshold;
+  double b_penalty[8];
+} scv_constraint_config;
+/* sampled: int64 [batch, seq_len] (non-negative ids), mask: one byte per position, both with `row_stride` elements
+ * between rows; fraction_values: float [n_fraction_values] or NULL; family_probs: float [batch, n_families] or NULL (no
+ * family rules); rewards: float [batch].  Device pointers. */
+int scv_constraint_rewards(const int64_t* sampled, const uint8_t* mask, int32_t batch, int32_t seq_len,
+                           int64_t row_stride, const scv_constraint_config* config, const float* fraction_values,
+                           int32_t n_fraction_values, const float* family_probs, int32_t n_families, float* rewards,
+                           void* stream);
+
 /* ---------------------------------------------------------------- kernel-level taps (tests) */
 /* y[M,N] = act(x[M,K] * w[N,K]^T + bias) (+ residual); w is bf16 with row stride ldw (elements).
  * act: 0 none, 1 gelu(erf), 2 relu, 3 sigmoid.  impl: 1 SIMT fp32 (w_bf16 row-major), 2 tcgen05 hi/lo bf16

@@ -71,6 +71,17 @@ class RewardConfig(C.Structure):
                                     "v14_fraction_start")])
 
 
+class ConstraintConfig(C.Structure):
+    """scv_constraint_config (include/scvae_b200.h): VocabConfig + ConstraintRewardConfig + FamilyConstraintConfig."""
+    _fields_ = (
+        [(n, C.c_int32) for n in ("element_start", "element_end", "digit_start", "digit_end", "lparen_idx", "rparen_idx",
+                                  "slash_idx", "pad_idx", "end_idx", "use_semantic_fractions", "fraction_token_start",
+                                  "a1_enabled", "a2_enabled", "a4_enabled", "a7_enabled", "family_enabled")]
+        + [(n, C.c_double) for n in ("a1_penalty", "a2_penalty_per_violation", "a4_penalty", "a7_penalty",
+                                     "confidence_threshold")]
+        + [("b_penalty", C.c_double * 8)])
+
+
 HEADS_OUT_FIELDS = (
     "tc_pred", "magpie_pred", "attended_input", "tc_class_logits", "competence", "fraction_pred",
     "element_count_pred", "hp_pred", "sc_pred", "family_coarse_logits", "family_cuprate_sub_logits",
@@ -115,6 +126,8 @@ SIGNATURES = {
                                             C.c_void_p]),
     "scv_reward_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "scv_constraint_rewards": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "scv_op_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p]),

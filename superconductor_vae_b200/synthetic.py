@@ -359,3 +359,76 @@ def make_reward_rows(n: int, seq_len: int, vocab: int = 4752, seed: int = 4242, 
             e = (s == 2).nonzero()
             mask[b, : (int(e[0]) + 1 if e.numel() else seq_len)] = True
     return sampled, target, mask
+
+
+# ------------------------------------------------------------------------------------------------ constraint inputs (f1)
+_RULE_ELEMENTS = (3, 5, 6, 8, 9, 12, 13, 14, 20, 23, 25, 26, 27, 28, 29, 32, 38, 39, 41, 50, 56, 57, 80, 81, 82, 83)
+
+
+def make_constraint_rows(n: int, seq_len: int, seed: int = 777, semantic: bool = True, vocab: int = 4752,
+                         fraction_token_start: int = 143):
+    """Seeded formula-like token rows `El sub El sub ... END PAD...` for the chemistry-constraint rewards, in the V13
+    layout (elements 5-122, integer tokens 123-142, fraction tokens 143+) or the pre-V13 one (elements 20-137,
+    digits 138-147, '(' 4, ')' 5, '/' 16).  Elements are drawn mostly from the ones the rules name (O, Cu, Sr, ...),
+    so duplicates, F+Tl, Cu next to magnetic metals, reducible integer formulas and every family rule occur; some rows
+    have malformed groups, no END, or an unmasked position in the middle.  Returns (tokens int64 [n, L], mask bool)."""
+    g = torch.Generator().manual_seed(seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))
+    e0 = 5 if semantic else 20
+    tokens = torch.zeros((n, seq_len), dtype=torch.long)
+    mask = torch.zeros((n, seq_len), dtype=torch.bool)
+    for b in range(n):
+        row = []
+        n_el = ri(1, 7)
+        all_int = ri(0, 3) == 0                                    # integer-only formulas reach the A4 rule
+        for _ in range(n_el):
+            z = _RULE_ELEMENTS[ri(0, len(_RULE_ELEMENTS))] if ri(0, 5) else ri(1, 119)
+            row.append(e0 - 1 + z)
+            kind = ri(0, 6)
+            if semantic:
+                if kind <= 1 or all_int:
+                    if kind != 5:
+                        row.append(123 + (2 * ri(0, 5) + 1 if all_int and ri(0, 2) else ri(0, 20)))
+                elif kind <= 4:
+                    row.append(ri(fraction_token_start, vocab))
+            else:
+                if all_int or kind <= 1:
+                    if kind != 5:
+                        row.extend(138 + int(c) for c in str(ri(1, 40) * (2 if all_int and ri(0, 2) else 1)))
+                elif kind <= 3:
+                    num, den = ri(1, 60), ri(1, 60)
+                    row.append(4)
+                    row.extend(138 + int(c) for c in str(num))
+                    row.append(16)
+                    row.extend(138 + int(c) for c in str(den))
+                    if ri(0, 8):                                   # sometimes the group is left open
+                        row.append(5)
+                elif kind == 4:
+                    row.extend([4, 138 + ri(0, 10), 138 + ri(0, 10), 5] if ri(0, 2) else [4, 16, 5])    # malformed groups
+        if b % 11 != 7:
+            row.append(2)                                          # END (missing in a few rows)
+        row = row[:seq_len]
+        tokens[b, :len(row)] = torch.tensor(row, dtype=torch.long)
+        if b % 4 == 0:
+            mask[b] = True                                         # PAD positions masked in (id 0 is no element)
+        else:
+            mask[b, :len(row)] = True
+        if b % 13 == 5 and len(row) > 4:
+            mask[b, ri(2, len(row))] = False                       # a hole: the scans stop there, A1 does not
+    return tokens, mask
+
+
+def make_family_probs(n: int, seed: int = 778) -> torch.Tensor:
+    """[n, 14] composed family probabilities, about half of the rows above the 0.8 confidence threshold."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.softmax(torch.randn((n, 14), generator=g) * 4.0, dim=1)
+
+
+def make_constraint_fraction_values(vocab: int = 4752, fraction_token_start: int = 143, seed: int = 779) -> torch.Tensor:
+    """Fraction-token value table for the constraint inputs: amounts in [0, 8) so that the family windows
+    (0.055-0.27, 0.3, 0.7, 6.35 ...) are hit from both sides."""
+    g = torch.Generator().manual_seed(seed)
+    fv = torch.zeros(vocab)
+    u = torch.rand(vocab - fraction_token_start, generator=g)
+    fv[fraction_token_start:] = torch.where(u < 0.5, u * 1.0, (u - 0.5) * 16.0)
+    return fv
