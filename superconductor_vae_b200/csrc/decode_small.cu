@@ -1,24 +1,26 @@
-// Small-batch decode step (B <= 32 rows): ONE persistent kernel per step instead of ~140 launches.
+// Small-batch decode (<= 64 rows): ONE persistent cooperative kernel for the whole decode (plain greedy calls) or per
+// step (sampling calls) instead of ~140 launches per step.
 //
-// At a few dozen rows a decode step is bound by streaming the 107 MB of bf16 weights once (16 us of
-// HBM time) but the per-projection kernels spend ~7 us each on launch, prologue and drain: 1.05 ms per step.  Here
-// one CTA per SM stays resident for the whole step and walks a list of phases separated by grid-wide barriers:
-//   GEMV phase  : up to four projections of the same dependency level (y = act(LN?(x) W^T + b) (+ residual)); the
-//                 output columns are dealt round-robin to the CTAs, the input rows ([B, K] fp32, a few KB) are staged
-//                 in shared memory with the LayerNorm applied on the fly, lane r of every warp owns batch row r, so a
-//                 warp produces one output column for all rows with no cross-lane reduction.  The CTA's weight rows
-//                 (bf16, <= 40 KB) are fetched with cp.async BEFORE the barrier that precedes the phase: they do not
-//                 depend on activations, so the weight stream overlaps the barrier and the previous phase's tail.
-//   attention   : one warp per (row, head), same arithmetic as attention_decode_kernel (decode_kernels.cu).
-// Arithmetic: bf16 weights, fp32 activations / accumulate, like linear_simt.cu (every product exact in the FMA).
+// At a few dozen rows a decode step is bound by streaming the 107 MB of bf16 weights once (16 us of HBM
+// time) but the per-projection kernels spend ~7 us each on launch, prologue and drain: 1.17 ms per step.  Here one CTA
+// per SM (16 warps) stays resident and walks a list of phases separated by grid-wide barriers:
+//   projection phase: up to four projections of the same dependency level (y = act(LN?(x) W^T + b) (+ residual)).  A
+//                 CTA owns 8-48 contiguous output columns; per group of 32 rows it reads the input rows ([32, K] fp32)
+//                 through L2 into registers (a warp = two rows, every load in flight at once), applies the LayerNorm
+//                 there, writes them as bf16 hi / lo (x = hi + lo, the split of the tcgen05 path) into shared memory
+//                 and multiplies with mma.sync.m16n8k16 (warp = row tile x k-group, partial sums meet in shared
+//                 memory), then bias / activation / residual.  The CTA's weight rows and LayerNorm weights are copied
+//                 with cp.async BEFORE the barrier that precedes the phase: they do not depend on activations.
+//   attention   : one warp per (row, head); cached K / V rows are copied before the barrier too, the step's new row is
+//                 used from registers.
+//   sampling    : (whole-decode kernel) greedy epilogue, END bookkeeping, embedding of the chosen token.
+// Arithmetic: bf16 weights, activations as bf16 hi + lo (16 significant bits), fp32 accumulate; LayerNorm, softmax,
+// residual stream and KV cache fp32.
 //
-// STATUS: opt-in (SCV_SMALL=1).  Measured on B200 at 32 rows: 1.33 ms per step against 1.05 ms for the per-projection
-// path (CUDA graph + PDL): with ~100 dependent phases per step, each phase pays a grid barrier (1.5-2.5 us), an L2
-// round trip to stage its input (2.4 us) and a latency-bound compute / epilogue tail (3-5 us; two warps per scheduler
-// cannot hide the shared-memory and L2 latencies).  Per-phase times are printed with SCV_SMALL_DEBUG=<launch index>.
-// What it needs to win (next round): fewer, fatter phases (q projection fused into the out-projection phase, both
-// attention phases overlapped with the next weight stream), mma.sync on the hi/lo split instead of scalar FMAs.
-// Reference call sites: models/autoregressive_decoder.py:1244-1313 (layer), :1413-1441 (heads).
+// Measured on B200: 0.75 ms per step at 32 rows against 1.17 ms for the per-projection path.  A
+// step is ~99 dependent phases; a barrier costs ~2 us, staging 1-2 us, MMA + epilogue ~1.2 us.  Per-phase times of
+// the per-step kernel are printed with SCV_GRAPH=0 SCV_SMALL_PERSIST=0 SCV_SMALL_DEBUG=<launch index>.
+// Reference call sites: models/autoregressive_decoder.py:1244-1313 (layer), :1413-1441 (heads), :1505-1548 (sampling).
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
@@ -144,7 +146,7 @@ __device__ __forceinline__ uint32_t bf162_bits(__nv_bfloat162 v) { return *reint
 // a round (and the LayerNorm weights) is in flight at once: the input was written by other CTAs in the previous phase
 // and comes through L2, so a round costs one L2 round trip.
 template <int NJ, int R>
-__device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0, int kc, int B, const float* gb) {
+__device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0, int kc, int rg, int B, const float* gb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool ln = op.ln_g != nullptr;
 #pragma unroll 1
@@ -156,7 +158,7 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int col = 4 * (lane + 32 * j);
-        v[u][j] = (r < B && col < kc) ? __ldcg(reinterpret_cast<const float4*>(op.in + (size_t)r * op.ld_in + k0 + col))
+        v[u][j] = (rg + r < B && col < kc) ? __ldcg(reinterpret_cast<const float4*>(op.in + (size_t)(rg + r) * op.ld_in + k0 + col))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -224,9 +226,9 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
   }
 }
 
-__device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int B, const float* gb) {
-  if (kc <= 512) stage_rows_t<4, RPW>(op, sm, k0, kc, B, gb);    // d_model-wide inputs: the warp's rows in one round
-  else stage_rows_t<KC / 128, RPW>(op, sm, k0, kc, B, gb);
+__device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int rg, int B, const float* gb) {
+  if (kc <= 512) stage_rows_t<4, RPW>(op, sm, k0, kc, rg, B, gb);    // d_model-wide inputs: the warp's rows in one round
+  else stage_rows_t<KC / 128, RPW>(op, sm, k0, kc, rg, B, gb);
 }
 
 // One projection phase.  Per op: the CTA's nc <= 48 output columns for all 32 (padded) rows as mma.sync m16n8k16 tiles,
@@ -245,83 +247,85 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
     if (nc == 0) continue;                        // CTA-uniform
     const int K = op.K, wp = op.ldw * 2 + W_ROW_PAD;
     const int ntiles = (nc + 7) >> 3;
-    // this thread's outputs of the epilogue: fetch bias and residual now, their latency hides behind the staging
-    constexpr int EP = (32 * NT_MAX * 8 + SM_THREADS - 1) / SM_THREADS;
-    float bias_v[EP], res_v[EP];
+    for (int rg = 0; rg < B; rg += 32) {            // groups of 32 rows: the staged weights serve every group
+      // this thread's outputs of the epilogue: fetch bias and residual now, their latency hides behind the staging
+      constexpr int EP = (32 * NT_MAX * 8 + SM_THREADS - 1) / SM_THREADS;
+      float bias_v[EP], res_v[EP];
 #pragma unroll
-    for (int e = 0; e < EP; ++e) {
-      const int idx = threadIdx.x + e * SM_THREADS;
-      const int r = idx / nc, c = idx - r * nc;
-      bias_v[e] = 0.f; res_v[e] = 0.f;
-      if (r < B) {
-        if (op.bias != nullptr) bias_v[e] = __ldg(op.bias + n0 + c);
-        if (op.res != nullptr) res_v[e] = __ldcg(op.res + (size_t)r * op.ldr + n0 + c);
+      for (int e = 0; e < EP; ++e) {
+        const int idx = threadIdx.x + e * SM_THREADS;
+        const int r = idx / nc, c = idx - r * nc;
+        bias_v[e] = 0.f; res_v[e] = 0.f;
+        if (r < 32 && rg + r < B) {
+          if (op.bias != nullptr) bias_v[e] = __ldg(op.bias + n0 + c);
+          if (op.res != nullptr) res_v[e] = __ldcg(op.res + (size_t)(rg + r) * op.ldr + n0 + c);
+        }
       }
-    }
-    float acc[NT_MAX][4];                         // hi and lo products of a k-step go to the same accumulator
+      float acc[NT_MAX][4];                         // hi and lo products of a k-step go to the same accumulator
 #pragma unroll
-    for (int j = 0; j < NT_MAX; ++j)
+      for (int j = 0; j < NT_MAX; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-    const float* gb = reinterpret_cast<const float*>(wbase + (size_t)nc * wp);   // staged LayerNorm weight | bias
-    // ldmatrix row addresses: A x4 = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B x4 = (tile j | j+1) x (k 0-7 | 8-15)
-    const int mi = lane >> 3;
-    const int a_row = mt * 16 + (lane & 7) + (mi & 1) * 8, a_kofs = (mi >> 1) * 8;
-    const int b_kofs = (mi & 1) * 8;
-    const int chunk = K > KC ? KCH : KC;
-    for (int k0 = 0; k0 < K; k0 += chunk) {
-      const int kc = min(chunk, K - k0);
-      cp_async_wait_all();                        // this phase's weight rows and LayerNorm weights, copied before the barrier ...
-      __syncthreads();                            // ... by every thread; the previous chunk / op / phase is done with a_hi, a_lo
-      if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[0]));
-      stage_rows(op, sm, k0, kc, B, gb);
-      __syncthreads();                            // the staged rows are complete
-      if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[1]));
-      const int steps = kc >> 4;
-      for (int ks = kq; ks < steps; ks += KQ) {
-        uint32_t ah[4], al[4];
-        ldmatrix_x4(ah, sm.a_hi + a_row * A_PITCH + ks * 16 + a_kofs);
-        ldmatrix_x4(al, sm.a_lo + a_row * A_PITCH + ks * 16 + a_kofs);
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+      const float* gb = reinterpret_cast<const float*>(wbase + (size_t)nc * wp);   // staged LayerNorm weight | bias
+      // ldmatrix row addresses: A x4 = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B x4 = (tile j | j+1) x (k 0-7 | 8-15)
+      const int mi = lane >> 3;
+      const int a_row = mt * 16 + (lane & 7) + (mi & 1) * 8, a_kofs = (mi >> 1) * 8;
+      const int b_kofs = (mi & 1) * 8;
+      const int chunk = K > KC ? KCH : KC;
+      for (int k0 = 0; k0 < K; k0 += chunk) {
+        const int kc = min(chunk, K - k0);
+        cp_async_wait_all();                        // this phase's weight rows and LayerNorm weights, copied before the barrier ...
+        __syncthreads();                            // ... by every thread; the previous chunk / op / phase is done with a_hi, a_lo
+        if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[0]));
+        stage_rows(op, sm, k0, kc, rg, B, gb);
+        __syncthreads();                            // the staged rows are complete
+        if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[1]));
+        const int steps = kc >> 4;
+        for (int ks = kq; ks < steps; ks += KQ) {
+          uint32_t ah[4], al[4];
+          ldmatrix_x4(ah, sm.a_hi + a_row * A_PITCH + ks * 16 + a_kofs);
+          ldmatrix_x4(al, sm.a_lo + a_row * A_PITCH + ks * 16 + a_kofs);
 #pragma unroll
-        for (int jp = 0; jp < NT_MAX / 2; ++jp) {
-          if (2 * jp < ntiles) {
-            const int wrow = min((2 * jp + (mi >> 1)) * 8 + (lane & 7), nc - 1);      // rows beyond nc: a duplicate, never stored
-            uint32_t b[4];
-            ldmatrix_x4(b, wbase + (size_t)wrow * wp + 2 * (k0 + ks * 16 + b_kofs));
-            mma_bf16(acc[2 * jp], ah, b[0], b[1]);
-            if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], ah, b[2], b[3]);
-            mma_bf16(acc[2 * jp], al, b[0], b[1]);
-            if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], al, b[2], b[3]);
+          for (int jp = 0; jp < NT_MAX / 2; ++jp) {
+            if (2 * jp < ntiles) {
+              const int wrow = min((2 * jp + (mi >> 1)) * 8 + (lane & 7), nc - 1);      // rows beyond nc: a duplicate, never stored
+              uint32_t b[4];
+              ldmatrix_x4(b, wbase + (size_t)wrow * wp + 2 * (k0 + ks * 16 + b_kofs));
+              mma_bf16(acc[2 * jp], ah, b[0], b[1]);
+              if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], ah, b[2], b[3]);
+              mma_bf16(acc[2 * jp], al, b[0], b[1]);
+              if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], al, b[2], b[3]);
+            }
           }
         }
       }
-    }
-    __syncthreads();                              // every warp is done reading a_hi: it becomes the partial-sum buffer
-    if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[2]));
-    {
-      const int g = lane >> 2, t = lane & 3;
-      float* r0 = red + ((size_t)kq * 32 + mt * 16 + g) * RED_PITCH + 2 * t;
+      __syncthreads();                              // every warp is done reading a_hi: it becomes the partial-sum buffer
+      if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[2]));
+      {
+        const int g = lane >> 2, t = lane & 3;
+        float* r0 = red + ((size_t)kq * 32 + mt * 16 + g) * RED_PITCH + 2 * t;
 #pragma unroll
-      for (int j = 0; j < NT_MAX; ++j) {
-        if (j < ntiles) {
-          *reinterpret_cast<float2*>(r0 + 8 * j) = make_float2(acc[j][0], acc[j][1]);
-          *reinterpret_cast<float2*>(r0 + 8 * RED_PITCH + 8 * j) = make_float2(acc[j][2], acc[j][3]);
+        for (int j = 0; j < NT_MAX; ++j) {
+          if (j < ntiles) {
+            *reinterpret_cast<float2*>(r0 + 8 * j) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(r0 + 8 * RED_PITCH + 8 * j) = make_float2(acc[j][2], acc[j][3]);
+          }
         }
       }
-    }
-    __syncthreads();
+      __syncthreads();
 #pragma unroll
-    for (int e = 0; e < EP; ++e) {
-      const int idx = threadIdx.x + e * SM_THREADS;
-      const int r = idx / nc, c = idx - r * nc;
-      if (r < B) {
-        const float* p = red + (size_t)r * RED_PITCH + c;
-        float v = 0.f;
+      for (int e = 0; e < EP; ++e) {
+        const int idx = threadIdx.x + e * SM_THREADS;
+        const int r = idx / nc, c = idx - r * nc;
+        if (r < 32 && rg + r < B) {
+          const float* p = red + (size_t)r * RED_PITCH + c;
+          float v = 0.f;
 #pragma unroll
-        for (int g = 0; g < KQ; ++g) v += p[g * 32 * RED_PITCH];
-        v = apply_act(v + bias_v[e], op.act);
-        if (op.res != nullptr) v += res_v[e];
-        __stcg(op.out + (size_t)r * op.ldo + n0 + c, v);
+          for (int g = 0; g < KQ; ++g) v += p[g * 32 * RED_PITCH];
+          v = apply_act(v + bias_v[e], op.act);
+          if (op.res != nullptr) v += res_v[e];
+          __stcg(op.out + (size_t)(rg + r) * op.ldo + n0 + c, v);
+        }
       }
     }
     if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[3]));
@@ -653,7 +657,7 @@ bool small_phase_fits(const SmallPhase& ph, int grid) {
 
 int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const StepState* st, unsigned* bar, int grid,
                         cudaStream_t s) {
-  SCV_REQUIRE(B >= 1 && B <= 32, "small-batch step: %d rows (1..32 supported)", B);
+  SCV_REQUIRE(B >= 1 && B <= kSmallMaxRows, "small-batch step: %d rows (1..%d supported)", B, kSmallMaxRows);
   static bool attr_set = false;
   if (!attr_set) {
     SCV_CUDA(cudaFuncSetAttribute(decode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -686,7 +690,7 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
 
 int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int B, unsigned* bar, int grid, const SmallTail& tail,
                                 cudaStream_t s) {
-  SCV_REQUIRE(B >= 1 && B <= 32, "small-batch decode: %d rows (1..32 supported)", B);
+  SCV_REQUIRE(B >= 1 && B <= kSmallMaxRows, "small-batch decode: %d rows (1..%d supported)", B, kSmallMaxRows);
   static bool attr_set = false;
   if (!attr_set) {
     SCV_CUDA(cudaFuncSetAttribute(decode_small_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));

@@ -384,7 +384,8 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward, pps = ceil_div(c.pe_len, kPagePos);
   D->small_active = false;
   static const int env = [] { const char* e = getenv("SCV_SMALL"); return e ? atoi(e) : 1; }();   // SCV_SMALL=0: per-projection path
-  if (!env || B > 32 || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
+  static const int max_rows = [] { const char* e = getenv("SCV_SMALL_MAX_ROWS"); return std::min(e ? atoi(e) : kSmallMaxRows, kSmallMaxRows); }();
+  if (!env || B > max_rows || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
   if (D->sm_grid == 0) {
     int dev = 0, sms = 0;
     SCV_CUDA(cudaGetDevice(&dev));
@@ -394,9 +395,9 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   if (D->sm_grid > 256) return 0;               // one barrier flag per CTA, 256 flags (decode_small.cu)
   // fixed sizes: a captured step holds these pointers, so they must never be reallocated
   SCV_TRY(D->sm_bar.ensure(256 * sizeof(unsigned)));      // one barrier flag per CTA (decode_small.cu kBarWords)
-  SCV_TRY(D->sm_h2b.ensure((size_t)32 * d * sizeof(float)));
-  SCV_TRY(D->sm_t3s.ensure((size_t)32 * d * sizeof(float)));
-  SCV_TRY(D->sm_t3d.ensure((size_t)32 * d * sizeof(float)));
+  SCV_TRY(D->sm_h2b.ensure((size_t)kSmallMaxRows * d * sizeof(float)));
+  SCV_TRY(D->sm_t3s.ensure((size_t)kSmallMaxRows * d * sizeof(float)));
+  SCV_TRY(D->sm_t3d.ensure((size_t)kSmallMaxRows * d * sizeof(float)));
   SCV_TRY(D->sm_phases.ensure((size_t)(8 * c.num_layers + 3) * sizeof(SmallPhase)));
   StepState* st = D->state.as<StepState>();
   float* x = D->x.as<float>(); float* qkv = D->qkv.as<float>(); float* attn = D->attn.as<float>();
