@@ -194,6 +194,9 @@ int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
 bool tc_persistent_ok(const LinearArgs& a);
 int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s);
+// CTA-pair variant for wide projections (gemm_tcgen05_2cta.cu, SCV_GEMM_2CTA)
+bool tc_2cta_ok(const LinearArgs& a);
+int launch_linear_tcgen05_2cta(const LinearArgs& a, cudaStream_t s);
 bool tc_shape_ok(const LinearArgs& a);
 bool tc_res_ln_ok(const LinearArgs& a);
 int launch_linear_res_ln(const LinearArgs& a, cudaStream_t s);

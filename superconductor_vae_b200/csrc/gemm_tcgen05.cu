@@ -318,6 +318,7 @@ bool tc_shape_ok(const LinearArgs& a) {
 
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
+  if (tc_2cta_ok(a)) return launch_linear_tcgen05_2cta(a, s);
   if (tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
   static bool attr_set = false;
   if (!attr_set) {

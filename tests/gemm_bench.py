@@ -33,13 +33,17 @@ def bench(M, name, N, K, residual, split_out, iters=50):
     for _ in range(5):
         run()
     torch.cuda.synchronize()
+    err = None
+    if not split_out and not residual and K <= 1024:      # check against fp64 with the bf16-rounded weights
+        ref = (x.double() @ w.to(torch.bfloat16).double().t() + b.double())
+        err = float((y.double() - ref).abs().max())
     a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
         run()
     e.record(); e.synchronize()
     us = a.elapsed_time(e) * 1e3 / iters
-    return us, 2.0 * M * N * K / (us * 1e6)
+    return us, 2.0 * M * N * K / (us * 1e6), err
 
 
 if __name__ == "__main__":
@@ -47,9 +51,9 @@ if __name__ == "__main__":
     for M in Ms:
         tot = 0.0
         for (name, N, K, res, so) in SHAPES:
-            us, tf = bench(M, name, N, K, res, so)
+            us, tf, err = bench(M, name, N, K, res, so)
             w = {"q": 1, "o+res": 2}.get(name, 1)
             tot += us * w
-            print(f"M={M:5d} {name:11s} N={N:5d} K={K:5d}: {us:7.2f} us  {tf:7.1f} TFLOP/s(alg)", flush=True)
+            print(f"M={M:5d} {name:11s} N={N:5d} K={K:5d}: {us:7.2f} us  {tf:7.1f} TFLOP/s(alg)" + (f"  max|err| {err:.2e}" if err is not None else ""), flush=True)
         print(f"M={M}: one layer (qkv + q + 2*o + ff1 + ff2) + logits/12 ~ {tot - bench(M, *SHAPES[5])[0] * 11 / 12:7.1f} us "
               f"[BN={os.environ.get('SCV_GEMM_BN', '128')}]", flush=True)

@@ -1,6 +1,6 @@
 """Helper of test_optin_kernels_match (run in a subprocess because the switches are read once per process):
 prints a digest of greedy tokens for a 32-row batch (golden-checked), a 64-row batch (two row groups of the
-persistent small-batch kernel) and a 640-row batch."""
+persistent small-batch kernel) and a 768-row batch (six row tiles: multi-wave projections, whole CTA pairs)."""
 import hashlib
 import os
 import sys
@@ -19,7 +19,7 @@ sd = W.make_decoder_state_dict(shape, 0)
 dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=dev)
 masks = OV.type_masks().to(dev)
 out = []
-for B in (32, 64, 640):
+for B in (32, 64, 768):
     z = W.make_latents(B, shape.latent_dim, 1234).to(dev)
     st, hp = W.make_conditioning(B, shape.stoich_input_dim, 1234)
     st, hp = st.to(dev), {k: v.to(dev) for k, v in hp.items()}
