@@ -71,7 +71,7 @@ struct SmallPhase {
   SmallOp op[4];
   AttnArgs attn;
 };
-constexpr int kSmallMaxRows = 64;                // beyond that the per-projection (tcgen05) path is faster
+constexpr int kSmallMaxRows = 64;                // what the kernel can take (row groups of 32); the default limit is 32
 size_t small_step_smem_bytes();
 int small_cols_per_cta(int N, int grid);
 bool small_phase_fits(const SmallPhase& ph, int grid);

@@ -1,4 +1,4 @@
-// Small-batch decode (<= 64 rows): ONE persistent cooperative kernel for the whole decode (plain greedy calls) or per
+// Small-batch decode (<= 32 rows by default, <= 64 with SCV_SMALL_MAX_ROWS): ONE persistent cooperative kernel for the whole decode (plain greedy calls) or per
 // step (sampling calls) instead of ~140 launches per step.
 //
 // At a few dozen rows a decode step is bound by streaming the 107 MB of bf16 weights once (16 us of HBM
@@ -7,17 +7,19 @@
 //   projection phase: up to four projections of the same dependency level (y = act(LN?(x) W^T + b) (+ residual)).  A
 //                 CTA owns 8-48 contiguous output columns; per group of 32 rows it reads the input rows ([32, K] fp32)
 //                 through L2 into registers (a warp = two rows, every load in flight at once), applies the LayerNorm
-//                 there, writes them as bf16 hi / lo (x = hi + lo, the split of the tcgen05 path) into shared memory
+//                 there, writes them as three bf16 terms (x = hi + mid + lo exactly) into shared memory
 //                 and multiplies with mma.sync.m16n8k16 (warp = row tile x k-group, partial sums meet in shared
 //                 memory), then bias / activation / residual.  The CTA's weight rows and LayerNorm weights are copied
 //                 with cp.async BEFORE the barrier that precedes the phase: they do not depend on activations.
 //   attention   : one warp per (row, head); cached K / V rows are copied before the barrier too, the step's new row is
 //                 used from registers.
 //   sampling    : (whole-decode kernel) greedy epilogue, END bookkeeping, embedding of the chosen token.
-// Arithmetic: bf16 weights, activations as bf16 hi + lo (16 significant bits), fp32 accumulate; LayerNorm, softmax,
+// Arithmetic: bf16 weights, activations as three bf16 terms (all 24 significant bits: every product exact), fp32
+// accumulate; LayerNorm, softmax,
 // residual stream and KV cache fp32.
 //
-// Measured on B200: 0.75 ms per step at 32 rows against 1.17 ms for the per-projection path.  A
+// Measured on B200: 0.80-0.85 ms per step at 8-32 rows against 1.17-1.20 ms for the per-projection
+// path, 2048 of 2048 rows token-identical to the fp32 oracle when decoded 32 at a time (tests/kv_probe.py).  A
 // step is ~99 dependent phases; a barrier costs ~2 us, staging 1-2 us, MMA + epilogue ~1.2 us.  Per-phase times of
 // the per-step kernel are printed with SCV_GRAPH=0 SCV_SMALL_PERSIST=0 SCV_SMALL_DEBUG=<launch index>.
 // Reference call sites: models/autoregressive_decoder.py:1244-1313 (layer), :1413-1441 (heads), :1505-1548 (sampling).
@@ -36,10 +38,10 @@ namespace {
 constexpr int SM_THREADS = 512, SM_WARPS = 16;   // 4 warps per scheduler: the staging is issue / latency bound
 constexpr int KQ = SM_WARPS / 2;              // k-groups of the MMA loop (warp = row tile x k-group)
 constexpr int RPW = 32 / SM_WARPS;            // staged rows per warp
-constexpr int KC = 640;                       // widest input staged in one piece (a LayerNorm input must be: d_model <= 640)
+constexpr int KC = 512;                       // widest input staged in one piece (a LayerNorm input must be: d_model <= 512)
 constexpr int KCH = 512;                      // wider inputs (the feed-forward width) are staged in chunks of 512 columns
-constexpr int A_PITCH = KC + 8;               // bf16 per staged row: 1296 B, consecutive rows 16 B apart in the banks
-constexpr int W_BUF_BYTES = 64 * 1024;        // weight rows of one phase for one CTA
+constexpr int A_PITCH = KC + 8;               // bf16 per staged row: 1040 B, consecutive rows 16 B apart in the banks
+constexpr int W_BUF_BYTES = 56 * 1024;        // weight rows of one phase for one CTA
 constexpr int W_ROW_PAD = 16;                 // bytes added to every staged weight row (same bank rotation as A)
 constexpr int NT_MAX = 6;                     // 8-column MMA tiles per CTA and projection (<= 48 output columns)
 constexpr int RED_PITCH = NT_MAX * 8;         // floats per row of the cross-warp partial sums
@@ -97,13 +99,17 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, int
 
 struct Smem {
   SmallPhase ph[2];                               // descriptors of the running and of the next phase (copied from global)
-  // the staged input rows as bf16 hi / lo (x = hi + lo to 16 significant bits, the split of the tcgen05 path);
+  // the staged input rows as three bf16 terms, x = hi + mid + lo EXACTLY (3 x 8 significant bits = the 24 of an fp32):
+  // with bf16 weights every product is exact and only the fp32 accumulation rounds, like the fp32 CUDA-core path.
+  // (Two terms, the split of the tcgen05 path, measured 2046 of 2048 rows token-identical to the fp32 oracle when
+  // decoded 32 at a time, tests/kv_probe.py; the per-projection path these batch sizes used before is fp32-exact.)
   // a_hi doubles as the cross-warp partial-sum buffer of a projection and as the score buffer of an attention phase
   __align__(16) __nv_bfloat16 a_hi[32 * A_PITCH];
+  __align__(16) __nv_bfloat16 a_mid[32 * A_PITCH];
   __align__(16) __nv_bfloat16 a_lo[32 * A_PITCH];
   __align__(16) unsigned char w[2][W_BUF_BYTES];
 };
-static_assert(KQ * 32 * RED_PITCH * sizeof(float) <= 2 * 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi + a_lo");
+static_assert(KQ * 32 * RED_PITCH * sizeof(float) <= 3 * 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi .. a_lo");
 static_assert(SM_WARPS * MAX_N_SCORES * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "scores alias a_hi");
 
 // Output columns are dealt to the CTAs in contiguous blocks of op.cpc (a multiple of 8 = whole MMA column tiles, see
@@ -141,7 +147,7 @@ __device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf, int st
 
 __device__ __forceinline__ uint32_t bf162_bits(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
-// Stage columns [k0, k0 + kc) of the B input rows as bf16 hi / lo, LayerNorm applied on the way (then the chunk is the
+// Stage columns [k0, k0 + kc) of the B input rows as bf16 hi / mid / lo, LayerNorm applied on the way (then the chunk is the
 // whole row).  Warp w owns rows RPW * w .. RPW * w + RPW - 1, R rows at a time, a row spread over the lanes as NJ float4s; every load of
 // a round (and the LayerNorm weights) is in flight at once: the input was written by other CTAs in the previous phase
 // and comes through L2, so a round costs one L2 round trip.
@@ -214,11 +220,15 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
         const int col = 4 * (lane + 32 * j);
         if (col < kc) {
           const float4 x = v[u][j];
-          // hi = bf16(x), lo = bf16(x - hi): packed converts, two values per instruction
+          // hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) (both differences exact in fp32): packed converts
           const uint32_t h01 = bf162_bits(__floats2bfloat162_rn(x.x, x.y)), h23 = bf162_bits(__floats2bfloat162_rn(x.z, x.w));
-          const uint32_t l01 = bf162_bits(__floats2bfloat162_rn(x.x - __uint_as_float(h01 << 16), x.y - __uint_as_float(h01 & 0xffff0000u)));
-          const uint32_t l23 = bf162_bits(__floats2bfloat162_rn(x.z - __uint_as_float(h23 << 16), x.w - __uint_as_float(h23 & 0xffff0000u)));
+          const float r0 = x.x - __uint_as_float(h01 << 16), r1 = x.y - __uint_as_float(h01 & 0xffff0000u);
+          const float r2 = x.z - __uint_as_float(h23 << 16), r3 = x.w - __uint_as_float(h23 & 0xffff0000u);
+          const uint32_t m01 = bf162_bits(__floats2bfloat162_rn(r0, r1)), m23 = bf162_bits(__floats2bfloat162_rn(r2, r3));
+          const uint32_t l01 = bf162_bits(__floats2bfloat162_rn(r0 - __uint_as_float(m01 << 16), r1 - __uint_as_float(m01 & 0xffff0000u)));
+          const uint32_t l23 = bf162_bits(__floats2bfloat162_rn(r2 - __uint_as_float(m23 << 16), r3 - __uint_as_float(m23 & 0xffff0000u)));
           *reinterpret_cast<uint2*>(sm.a_hi + r * A_PITCH + col) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(sm.a_mid + r * A_PITCH + col) = make_uint2(m01, m23);
           *reinterpret_cast<uint2*>(sm.a_lo + r * A_PITCH + col) = make_uint2(l01, l23);
         }
       }
@@ -227,12 +237,11 @@ __device__ __forceinline__ void stage_rows_t(const SmallOp& op, Smem& sm, int k0
 }
 
 __device__ __forceinline__ void stage_rows(const SmallOp& op, Smem& sm, int k0, int kc, int rg, int B, const float* gb) {
-  if (kc <= 512) stage_rows_t<4, RPW>(op, sm, k0, kc, rg, B, gb);    // d_model-wide inputs: the warp's rows in one round
-  else stage_rows_t<KC / 128, RPW>(op, sm, k0, kc, rg, B, gb);
+  stage_rows_t<KC / 128, RPW>(op, sm, k0, kc, rg, B, gb);        // kc <= KC = 512: the warp's rows in one round
 }
 
 // One projection phase.  Per op: the CTA's nc <= 48 output columns for all 32 (padded) rows as mma.sync m16n8k16 tiles,
-// A = the staged rows (hi and lo against the same weight fragment, separate accumulators), B = the CTA's weight rows
+// A = the staged rows (hi, mid and lo against the same weight fragment, one accumulator), B = the CTA's weight rows
 // [nc, K] (already k-contiguous = "col" operand).  Warp = (row tile, quarter of the k-steps); the four partial sums per
 // output meet in shared memory, then bias / activation / residual and nc contiguous floats per row go to global.
 __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, unsigned long long* tdbg) {
@@ -261,7 +270,7 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
           if (op.res != nullptr) res_v[e] = __ldcg(op.res + (size_t)(rg + r) * op.ldr + n0 + c);
         }
       }
-      float acc[NT_MAX][4];                         // hi and lo products of a k-step go to the same accumulator
+      float acc[NT_MAX][4];                         // the three terms' products of a k-step go to the same accumulator
 #pragma unroll
       for (int j = 0; j < NT_MAX; ++j)
 #pragma unroll
@@ -282,8 +291,9 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
         if (tdbg && threadIdx.x == 0 && o == 0 && k0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[1]));
         const int steps = kc >> 4;
         for (int ks = kq; ks < steps; ks += KQ) {
-          uint32_t ah[4], al[4];
+          uint32_t ah[4], am[4], al[4];
           ldmatrix_x4(ah, sm.a_hi + a_row * A_PITCH + ks * 16 + a_kofs);
+          ldmatrix_x4(am, sm.a_mid + a_row * A_PITCH + ks * 16 + a_kofs);
           ldmatrix_x4(al, sm.a_lo + a_row * A_PITCH + ks * 16 + a_kofs);
 #pragma unroll
           for (int jp = 0; jp < NT_MAX / 2; ++jp) {
@@ -291,10 +301,12 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
               const int wrow = min((2 * jp + (mi >> 1)) * 8 + (lane & 7), nc - 1);      // rows beyond nc: a duplicate, never stored
               uint32_t b[4];
               ldmatrix_x4(b, wbase + (size_t)wrow * wp + 2 * (k0 + ks * 16 + b_kofs));
+              mma_bf16(acc[2 * jp], al, b[0], b[1]);                  // smallest term first
+              if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], al, b[2], b[3]);
+              mma_bf16(acc[2 * jp], am, b[0], b[1]);
+              if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], am, b[2], b[3]);
               mma_bf16(acc[2 * jp], ah, b[0], b[1]);
               if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], ah, b[2], b[3]);
-              mma_bf16(acc[2 * jp], al, b[0], b[1]);
-              if (2 * jp + 1 < ntiles) mma_bf16(acc[2 * jp + 1], al, b[2], b[3]);
             }
           }
         }

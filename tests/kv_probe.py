@@ -1,7 +1,9 @@
 """Probe (not a test): how many rows of a large greedy batch equal the fp32 CPU oracle token for token (config 2
 settings).  Measured on B200 with 2048 rows: 2048/2048 for the tensor-core path (bf16 hi/lo activations, fp32 K/V) and
 for the CUDA-core path (SCV_LINEAR_IMPL=1); an experimental 3-byte K/V cache format (fp32 rounded to 16 significant
-bits) gave 2046/2048 and was dropped.  usage: python tests/kv_probe.py [rows] [seed]"""
+bits) gave 2046/2048 and was dropped.  usage: python tests/kv_probe.py [rows] [seed] [chunk]
+chunk > 0 decodes the rows `chunk` at a time (chunk <= 64: every call goes through the persistent small-batch kernel,
+csrc/decode_small.cu), compared against the same oracle rows."""
 import os
 import sys
 import time
@@ -16,6 +18,7 @@ from oracle import vocab as OV                          # noqa: E402
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1234
+chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 shape = W.C512
 sd = W.make_decoder_state_dict(shape, 0)
 dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device="cuda:0")
@@ -29,7 +32,16 @@ def cu(t):
 
 
 kw = dict(temperature=0.001, max_len=64, stop_boost=10.0, hard_stop_threshold=0.8)
-t, _, _ = dec.generate_with_kv_cache(cu(z), stoich_pred=cu(stoich), heads_pred=cu(heads), type_masks=cu(masks), **kw)
+if chunk <= 0:
+    t, _, _ = dec.generate_with_kv_cache(cu(z), stoich_pred=cu(stoich), heads_pred=cu(heads), type_masks=cu(masks), **kw)
+else:
+    t = torch.zeros((rows, 63), dtype=torch.long, device="cuda:0")
+    zc, sc, hc, mc = cu(z), cu(stoich), cu(heads), cu(masks)
+    for r0 in range(0, rows, chunk):
+        sl = slice(r0, min(rows, r0 + chunk))
+        tt, _, _ = dec.generate_with_kv_cache(zc[sl], stoich_pred=sc[sl], heads_pred={k: v[sl] for k, v in hc.items()},
+                                              type_masks=mc, **kw)
+        t[sl, : tt.shape[1]] = tt
 t0 = time.time()
 torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
 rt, _, _ = DO.generate_with_kv_cache(sd, 8, z, stoich_pred=stoich, heads_pred=heads, type_masks=masks, **kw)
@@ -38,5 +50,5 @@ lens = DO.first_end_lengths(rt)
 tc = t.cpu()
 bad = [r for r in range(rows) if not torch.equal(tc[r, : int(lens[r])], rt[r, : int(lens[r])])]
 print(f"SCV_LINEAR_IMPL={os.environ.get('SCV_LINEAR_IMPL', '0')} "
-      f"rows={rows} seed={seed}: {rows - len(bad)}/{rows} rows equal to the oracle up to their END "
+      f"rows={rows} seed={seed} chunk={chunk}: {rows - len(bad)}/{rows} rows equal to the oracle up to their END "
       f"(oracle {dt:.1f} s); differing rows: {bad[:16]}")

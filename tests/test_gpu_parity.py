@@ -522,7 +522,7 @@ def test_config2_4096_latents_properties(golden_dir):
 def test_optin_kernels_match_default_tokens():
     """The alternative kernels must decode the same greedy tokens as the default path: 32 rows (default: the whole decode
     in the persistent small-batch kernel; SCV_SMALL=0: per-projection kernels; SCV_SMALL_PERSIST=0: one persistent kernel
-    per step) and 768 rows (multi-wave projections; opt-in fused residual + LayerNorm cluster projection, persistent
+    per step), 64 rows (SCV_SMALL_MAX_ROWS=64: two row groups per phase of the persistent kernel) and 768 rows (multi-wave projections; opt-in fused residual + LayerNorm cluster projection, persistent
     tcgen05 projection and CTA-pair (cta_group::2) projection), with and without masks / stop head."""
     import subprocess
     import sys as _sys
@@ -538,6 +538,6 @@ def test_optin_kernels_match_default_tokens():
         return line[0]
 
     base = digest({})
-    for extra in ({"SCV_SMALL": "0"}, {"SCV_SMALL_PERSIST": "0"}, {"SCV_FUSE_LN": "1"}, {"SCV_GEMM_PERSISTENT": "1"},
-                  {"SCV_GEMM_2CTA": "1"}):
+    for extra in ({"SCV_SMALL": "0"}, {"SCV_SMALL_PERSIST": "0"}, {"SCV_SMALL_MAX_ROWS": "64"}, {"SCV_FUSE_LN": "1"},
+                  {"SCV_GEMM_PERSISTENT": "1"}, {"SCV_GEMM_2CTA": "1"}):
         assert digest(extra) == base, f"{extra} decodes different tokens"
