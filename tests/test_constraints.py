@@ -104,3 +104,22 @@ def test_kernel_matches_oracle_rollout_shape(semantic):
         K.set_vocab_config(K.VocabConfig())
     assert r.shape == (B,) and np.array_equal(r[:1024].cpu().numpy(), ref)
     assert int((r != 0).sum()) > B // 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("semantic", [True, False])
+def test_kernel_long_rows_partial_cta(semantic):
+    """130 rows of 131 positions: a partial second CTA and rows wider than the default 48 KB of shared memory."""
+    dev = "cuda:0"
+    B, L = 130, 131
+    tok, m = Sy.make_constraint_rows(B, L, 41, semantic)
+    fv = Sy.make_constraint_fraction_values()
+    fam = Sy.make_family_probs(B, 42)
+    v = OC.Vocab.v13(143, fv.numpy()) if semantic else OC.Vocab()
+    ref = OC.compute_constraint_rewards(tok.numpy(), m.numpy(), OC.Rules(), v, fam.numpy())
+    try:
+        K.set_vocab_config(K.make_v13_vocab_config(143, fv.to(dev)) if semantic else K.VocabConfig())
+        r = K.compute_constraint_rewards(tok.to(dev), m.to(dev), K.ConstraintRewardConfig(), fam.to(dev), K.FamilyConstraintConfig())
+    finally:
+        K.set_vocab_config(K.VocabConfig())
+    assert np.array_equal(r.cpu().numpy(), ref)

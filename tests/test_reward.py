@@ -129,3 +129,17 @@ def test_reward_of_engine_rollout_rlo_shape():
     ref = OR.compute_reward(sampled[:64].cpu().numpy(), targets[:64].cpu().numpy(), mask[:64].cpu().numpy(),
                             OR.RewardConfig(v14=True), 2, True, 143, fv.cpu().numpy())
     assert np.abs(r[0, :64].cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.gpu
+def test_kernel_rows_longer_than_three_chunks():
+    """70 rows of 100 positions (four 32-position chunks, ragged last one), V14 continuous and tiered digit-level paths."""
+    dev = "cuda:0"
+    B, L, V = 70, 100, 4752
+    fv = Sy.make_fraction_values(V, 143, 7)
+    for semantic, cfg_o, cfg_s in ((True, OR.RewardConfig(v14=True), R.GPURewardConfigV14()), (False, OR.RewardConfig(), R.GPURewardConfig())):
+        s, t, m = Sy.make_reward_rows(B, L, V, 123, old_vocab=not semantic)
+        ref = OR.compute_reward(s.numpy(), t.numpy(), m.numpy(), cfg_o, 2, semantic, 143 if semantic else 0, fv.numpy() if semantic else None)
+        r = R.compute_reward_gpu_native(s.to(dev), t.to(dev), m.to(dev), config=cfg_s, use_semantic_fractions=semantic,
+                                        fraction_token_start=143 if semantic else 0, fraction_values=fv.to(dev) if semantic else None)
+        assert np.abs(r.cpu().numpy() - ref).max() <= TOL, semantic
