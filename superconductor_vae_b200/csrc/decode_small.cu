@@ -45,6 +45,9 @@ constexpr int W_BUF_BYTES = 56 * 1024;        // weight rows of one phase for on
 constexpr int W_ROW_PAD = 16;                 // bytes added to every staged weight row (same bank rotation as A)
 constexpr int NT_MAX = 6;                     // 8-column MMA tiles per CTA and projection (<= 48 output columns)
 constexpr int RED_PITCH = NT_MAX * 8;         // floats per row of the cross-warp partial sums
+constexpr int FF2_PITCH = 48;                 // bytes per staged linear2 row slice (16 hidden units = 32 B + pad)
+constexpr int FFH_PITCH = 24;                 // bf16 per row of the staged hidden activations (16 + pad: 48 B)
+constexpr int FFH_OFFSET = 64 * 1024;         // byte offset of the hidden-activation terms inside the a_hi.. region
 constexpr int MAX_N_SCORES = 256;             // positions per (row, head) the score buffer can hold
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -111,6 +114,7 @@ struct Smem {
 };
 static_assert(KQ * 32 * RED_PITCH * sizeof(float) <= 3 * 32 * A_PITCH * sizeof(__nv_bfloat16), "partial sums alias a_hi .. a_lo");
 static_assert(SM_WARPS * MAX_N_SCORES * sizeof(float) <= 32 * A_PITCH * sizeof(__nv_bfloat16), "scores alias a_hi");
+static_assert(KQ * 32 * RED_PITCH * sizeof(float) <= FFH_OFFSET && FFH_OFFSET + 3 * 32 * FFH_PITCH * 2 <= 3 * 32 * A_PITCH * 2, "hidden terms sit behind the partial sums");
 
 // Output columns are dealt to the CTAs in contiguous blocks of op.cpc (a multiple of 8 = whole MMA column tiles, see
 // small_cols_per_cta): CTA c owns [c * cpc, c * cpc + nc); CTAs beyond N / cpc skip the projection (and its staging).
@@ -123,9 +127,11 @@ __device__ void prefetch_attention(const AttnArgs& a, Smem& sm, int buf, int ste
 
 // Issue the cp.async copies of this CTA's weight rows of every op of `ph` into buffer `buf`.
 __device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf, int step) {
-  if (ph.kind != 0) { prefetch_attention(ph.attn, sm, buf, step); return; }
+  if (ph.kind == 1) { prefetch_attention(ph.attn, sm, buf, step); return; }
+  if (ph.kind == 3) { cp_async_commit(); return; }             // partial-sum reduction: nothing to stage
   unsigned char* dst = sm.w[buf];
-  for (int o = 0; o < ph.nops; ++o) {
+  const int nops = ph.kind == 2 ? 1 : ph.nops;                  // fused feed-forward: op[0] = linear1, op[1] = linear2
+  for (int o = 0; o < nops; ++o) {
     const SmallOp& op = ph.op[o];
     int n0, nc;
     cols_of_cta(op, n0, nc);
@@ -141,6 +147,19 @@ __device__ void prefetch_weights(const SmallPhase& ph, Smem& sm, int buf, int st
         cp_async16(dst + 16 * i, (i < q4 ? op.ln_g : op.ln_b) + 4 * (i < q4 ? i : i - q4));
       dst += (size_t)op.K * 8;
     }
+  }
+  if (ph.kind == 2) {
+    // linear2's weights for this CTA's hidden units: W2[n, h0 .. h0 + 15] = 32 contiguous bytes of every output row n
+    // (the k-contiguous "col" operand of the second MMA), staged at a 48-byte pitch (bank rotation)
+    const SmallOp& f1 = ph.op[0];
+    const SmallOp& f2 = ph.op[1];
+    int h0, nh;
+    cols_of_cta(f1, h0, nh);
+    if (nh > 0)
+      for (int i = threadIdx.x; i < 2 * f2.N; i += SM_THREADS) {
+        const int n = i >> 1, c = i & 1;
+        cp_async16(dst + (size_t)n * FF2_PITCH + 16 * c, reinterpret_cast<const unsigned char*>(f2.w + (size_t)n * f2.ldw + h0) + 16 * c);
+      }
   }
   cp_async_commit();
 }
@@ -249,7 +268,8 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
   const int mt = warp & 1, kq = warp >> 1;      // row tile, k-group
   const unsigned char* wbase = sm.w[buf];
   float* red = reinterpret_cast<float*>(sm.a_hi);
-  for (int o = 0; o < ph.nops; ++o) {
+  const bool fused = ph.kind == 2;                // feed-forward block: linear1 + GELU here, linear2 as partial sums
+  for (int o = 0; o < (fused ? 1 : ph.nops); ++o) {
     const SmallOp op = ph.op[o];                  // by value: the descriptor lives in shared memory, the hot fields in registers
     int n0, nc;
     cols_of_cta(op, n0, nc);
@@ -329,19 +349,96 @@ __device__ void run_gemv_phase(const SmallPhase& ph, Smem& sm, int buf, int B, u
       for (int e = 0; e < EP; ++e) {
         const int idx = threadIdx.x + e * SM_THREADS;
         const int r = idx / nc, c = idx - r * nc;
-        if (r < 32 && rg + r < B) {
+        if (r < 32 && (fused || rg + r < B)) {
           const float* p = red + (size_t)r * RED_PITCH + c;
           float v = 0.f;
 #pragma unroll
           for (int g = 0; g < KQ; ++g) v += p[g * 32 * RED_PITCH];
           v = apply_act(v + bias_v[e], op.act);
-          if (op.res != nullptr) v += res_v[e];
-          __stcg(op.out + (size_t)(rg + r) * op.ldo + n0 + c, v);
+          if (fused) {                             // hidden activation -> three bf16 terms, the A operand of linear2
+            if (rg + r >= B) v = 0.f;
+            __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sm.a_hi) + FFH_OFFSET);
+            const __nv_bfloat16 t0 = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(t0);
+            const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
+            hb[r * FFH_PITCH + c] = t0; hb[(32 + r) * FFH_PITCH + c] = t1; hb[(64 + r) * FFH_PITCH + c] = t2;
+          } else {
+            if (op.res != nullptr) v += res_v[e];
+            __stcg(op.out + (size_t)(rg + r) * op.ldo + n0 + c, v);
+          }
+        }
+      }
+      if (fused) {
+        // linear2 on the CTA's 16 hidden units: partial[32, d] = h[32, 16] * W2[:, h0 .. h0 + 15]^T, one k16 step, warp =
+        // (row tile, eighth of the output columns); the partial sums go to this CTA's slab, summed by the next phase
+        __syncthreads();
+        const SmallOp f2 = ph.op[1];
+        const unsigned char* w2s = wbase + (size_t)nc * wp + (op.ln_g != nullptr ? (size_t)op.K * 8 : 0);
+        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const unsigned char*>(sm.a_hi) + FFH_OFFSET);
+        const int ng = warp >> 1, tiles = f2.N >> 6;            // n-tiles of this warp (d / 64 <= 8)
+        uint32_t h_t[3][4];
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3) ldmatrix_x4(h_t[t3], hb + (t3 * 32 + a_row) * FFH_PITCH + a_kofs);
+        float* pslab = f2.out + ((size_t)blockIdx.x * 32) * f2.ldo;
+        const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          if (2 * jp < tiles) {
+            float c2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            const int nrow = (ng * tiles + 2 * jp + (mi >> 1)) * 8 + (lane & 7);
+            uint32_t b[4];
+            ldmatrix_x4(b, w2s + (size_t)nrow * FF2_PITCH + 2 * b_kofs);
+#pragma unroll
+            for (int t3 = 2; t3 >= 0; --t3) {                   // smallest term first
+              mma_bf16(c2[0], h_t[t3], b[0], b[1]);
+              mma_bf16(c2[1], h_t[t3], b[2], b[3]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = (ng * tiles + 2 * jp + u) * 8 + 2 * t4;
+              const int r_lo = mt * 16 + g4;
+              if (rg + r_lo < B) __stcg(reinterpret_cast<float2*>(pslab + (size_t)r_lo * f2.ldo + col), make_float2(c2[u][0], c2[u][1]));
+              if (rg + r_lo + 8 < B) __stcg(reinterpret_cast<float2*>(pslab + (size_t)(r_lo + 8) * f2.ldo + col), make_float2(c2[u][2], c2[u][3]));
+            }
+          }
         }
       }
     }
     if (tdbg && threadIdx.x == 0 && o == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tdbg[3]));
     wbase += (size_t)nc * wp + (op.ln_g != nullptr ? (size_t)op.K * 8 : 0);
+  }
+}
+
+// Second half of the fused feed-forward block: x[r, n] += b2[n] + sum over the hidden-unit slabs of partial[slab][r, n].
+// A CTA owns four output columns; thread = (row, sixteenth of the slabs): 16-byte loads all in flight, a sequential sum
+// per thread, then a fixed shuffle tree over the 16 threads of a row (deterministic order).
+__device__ void run_reduce_phase(const SmallPhase& ph, int B) {
+  const SmallOp op = ph.op[0];                    // in = slabs [K][32][ld_in], K = number of slabs, N = d, res = out = x
+  const int c0 = (int)blockIdx.x * 4;
+  if (c0 >= op.N) return;
+  const int r = threadIdx.x >> 4, q = threadIdx.x & 15;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < B) {
+    float4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int p = q + 16 * i;
+      v[i] = p < op.K ? __ldcg(reinterpret_cast<const float4*>(op.in + ((size_t)p * 32 + r) * op.ld_in + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (q == 0 && r < B) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(op.bias + c0));
+    const float4 xv = __ldcg(reinterpret_cast<const float4*>(op.res + (size_t)r * op.ldr + c0));
+    __stcg(reinterpret_cast<float4*>(op.out + (size_t)r * op.ldo + c0),
+           make_float4(acc.x + bv.x + xv.x, acc.y + bv.y + xv.y, acc.z + bv.z + xv.z, acc.w + bv.w + xv.w));
   }
 }
 
@@ -546,7 +643,8 @@ decode_small_kernel(const SmallPhase* __restrict__ phases, int n_phases, int B, 
     if (p + 1 < n_phases) next_word = desc_load(p + 1);
     unsigned long long t0 = 0, t1 = 0, t2 = 0;
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));   // SCV_SMALL_DEBUG
-    if (ph.kind == 0) run_gemv_phase(ph, sm, p & 1, B, (dbg && blockIdx.x == 0) ? dbg + 2048 + 4 * p : nullptr);
+    if (ph.kind == 0 || ph.kind == 2) run_gemv_phase(ph, sm, p & 1, B, (dbg && blockIdx.x == 0) ? dbg + 2048 + 4 * p : nullptr);
+    else if (ph.kind == 3) run_reduce_phase(ph, B);
     else run_attention_phase(ph.attn, sm, p & 1, step);
     if (dbg && blockIdx.x == 0) { __syncthreads(); if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); }
     if (p + 1 < n_phases) {
@@ -602,7 +700,8 @@ decode_small_persist_kernel(const SmallPhase* __restrict__ phases, int n_phases,
       const int cur = it & 1, nxt = cur ^ 1;
       const uint32_t next_word = desc_load(p + 1 < n_phases ? p + 1 : 0);
       const SmallPhase& ph = sm.ph[cur];
-      if (ph.kind == 0) run_gemv_phase(ph, sm, cur, B, nullptr);
+      if (ph.kind == 0 || ph.kind == 2) run_gemv_phase(ph, sm, cur, B, nullptr);
+      else if (ph.kind == 3) run_reduce_phase(ph, B);
       else run_attention_phase(ph.attn, sm, cur, step);
       desc_store(nxt, next_word);                  // slot nxt was last read in the previous phase
       __syncthreads();
@@ -651,6 +750,20 @@ int small_cols_per_cta(int N, int grid) {
 }
 
 bool small_phase_fits(const SmallPhase& ph, int grid) {
+  if (ph.kind == 3) {                                           // partial-sum reduction of the fused feed-forward block
+    const SmallOp& op = ph.op[0];
+    return op.N % 4 == 0 && op.N <= 4 * grid && op.K <= 256 && op.ld_in % 4 == 0 && op.ldr % 4 == 0 && op.ldo % 4 == 0 &&
+           op.bias != nullptr && op.res != nullptr;
+  }
+  if (ph.kind == 2) {                                           // linear1 (+ LayerNorm, GELU) and linear2 partial sums
+    const SmallOp& f1 = ph.op[0];
+    const SmallOp& f2 = ph.op[1];
+    if (f1.cpc != 16 || f1.N % 16 != 0 || f1.N > 16 * grid || f1.K > KC || f1.K % 16 != 0 || f1.ldw != f1.K) return false;
+    if (f1.ld_in % 4 != 0 || (reinterpret_cast<uintptr_t>(f1.in) & 15u) != 0) return false;
+    if (f2.N % 64 != 0 || f2.N > 512 || f2.K != f1.N || f2.ldw % 8 != 0 || f2.ldo % 2 != 0) return false;
+    const size_t bytes = (size_t)16 * (f1.ldw * 2 + W_ROW_PAD) + (f1.ln_g != nullptr ? (size_t)f1.K * 8 : 0) + (size_t)f2.N * FF2_PITCH;
+    return bytes <= (size_t)W_BUF_BYTES;
+  }
   if (ph.kind != 0)
     return ph.attn.hd <= 128 && ph.attn.hd % 4 == 0 && ph.attn.max_n <= MAX_N_SCORES && ph.attn.B * ph.attn.nhead <= SM_WARPS * grid &&
            ph.attn.ldq % 4 == 0 && ph.attn.ldn % 4 == 0 && ph.attn.ldo % 4 == 0 && ph.attn.row_stride % 4 == 0;

@@ -90,6 +90,7 @@ struct scv_decoder {
   DevBuf fw_skip;                          // teacher-forced forward: [B, L] key padding bytes
   DevBuf sm_phases, sm_bar, sm_h2b, sm_t3s, sm_t3d;
   std::vector<SmallPhase> sm_host;
+  DevBuf sm_part;                          // per-CTA partial sums of the fused feed-forward block
   int sm_n_phases = 0, sm_grid = 0;
   bool small_active = false;               // this call decodes through the persistent small-batch kernel
 
@@ -401,6 +402,11 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   SCV_TRY(D->sm_t3s.ensure((size_t)kSmallMaxRows * d * sizeof(float)));
   SCV_TRY(D->sm_t3d.ensure((size_t)kSmallMaxRows * d * sizeof(float)));
   SCV_TRY(D->sm_phases.ensure((size_t)(8 * c.num_layers + 3) * sizeof(SmallPhase)));
+  // SCV_SMALL_FUSE_FFN=1 (opt-in, NOT yet validated on hardware): fused feed-forward phases (decode_small.cu, kinds 2 and
+  // 3), one row group only
+  static const int fuse_env = [] { const char* e = getenv("SCV_SMALL_FUSE_FFN"); return e ? atoi(e) : 0; }();
+  const bool fuse_ffn = fuse_env != 0 && B <= 32;
+  if (fuse_ffn) SCV_TRY(D->sm_part.ensure((size_t)D->sm_grid * 32 * d * sizeof(float)));
   StepState* st = D->state.as<StepState>();
   float* x = D->x.as<float>(); float* qkv = D->qkv.as<float>(); float* attn = D->attn.as<float>();
   float* q2 = D->q2.as<float>(); float* ff = D->ff.as<float>(); float* h2 = D->h2.as<float>();
@@ -448,8 +454,24 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
     ca.attn.scale = scale; ca.attn.fixed_len = M; ca.attn.max_n = std::max(c.pe_len, M); ca.attn.st = st;
     P.push_back(ca);
     gemv({lin(attn, d, nullptr, L.ca_out, ACT_NONE, x, x, d)});
-    gemv({lin(x, d, &L.n3, L.ff1, ACT_GELU, nullptr, ff, dff)});
-    gemv({lin(ff, dff, nullptr, L.ff2, ACT_NONE, x, x, d)});
+    if (fuse_ffn) {
+      // feed-forward block as two phases without the [B, dff] round trip: linear1 + GELU on 16 hidden units per CTA and
+      // linear2's partial sums over them (one slab per CTA), then the sum of the slabs + bias + residual
+      SmallPhase f;
+      f.kind = 2; f.nops = 2;
+      f.op[0] = lin(x, d, &L.n3, L.ff1, ACT_GELU, nullptr, ff, dff);
+      f.op[0].cpc = 16;
+      f.op[1] = lin(ff, dff, nullptr, L.ff2, ACT_NONE, nullptr, D->sm_part.as<float>(), d);
+      P.push_back(f);
+      SmallPhase r;
+      r.kind = 3; r.nops = 1;
+      r.op[0] = op(D->sm_part.as<float>(), d, ceil_div(dff, 16), nullptr, nullptr, 0, L.ff2.b, d, ACT_NONE, x, d, x, d);
+      r.op[0].cpc = 4;
+      P.push_back(r);
+    } else {
+      gemv({lin(x, d, &L.n3, L.ff1, ACT_GELU, nullptr, ff, dff)});
+      gemv({lin(ff, dff, nullptr, L.ff2, ACT_NONE, x, x, d)});
+    }
   }
   const bool type = A->type_masks != nullptr, stop = A->stop_boost > 0.f, dup = A->site_dup_threshold > 0.f;
   float* h2b = D->sm_h2b.as<float>(); float* t3s = D->sm_t3s.as<float>(); float* t3d = D->sm_t3d.as<float>();
