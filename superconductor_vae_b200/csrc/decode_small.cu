@@ -760,7 +760,7 @@ bool small_phase_fits(const SmallPhase& ph, int grid) {
     const SmallOp& f2 = ph.op[1];
     if (f1.cpc != 16 || f1.N % 16 != 0 || f1.N > 16 * grid || f1.K > KC || f1.K % 16 != 0 || f1.ldw != f1.K) return false;
     if (f1.ld_in % 4 != 0 || (reinterpret_cast<uintptr_t>(f1.in) & 15u) != 0) return false;
-    if (f2.N % 64 != 0 || f2.N > 512 || f2.K != f1.N || f2.ldw % 8 != 0 || f2.ldo % 2 != 0) return false;
+    if (f2.N % 128 != 0 || f2.N > 512 || f2.K != f1.N || f2.ldw % 8 != 0 || f2.ldo % 2 != 0) return false;   // whole tile pairs per warp
     const size_t bytes = (size_t)16 * (f1.ldw * 2 + W_ROW_PAD) + (f1.ln_g != nullptr ? (size_t)f1.K * 8 : 0) + (size_t)f2.N * FF2_PITCH;
     return bytes <= (size_t)W_BUF_BYTES;
   }
