@@ -11,6 +11,10 @@
 //                 and multiplies with mma.sync.m16n8k16 (warp = row tile x k-group, partial sums meet in shared
 //                 memory), then bias / activation / residual.  The CTA's weight rows and LayerNorm weights are copied
 //                 with cp.async BEFORE the barrier that precedes the phase: they do not depend on activations.
+//   feed-forward: (opt-in, SCV_SMALL_FUSE_FFN=1) linear1 (+ LayerNorm, GELU) as a projection phase on 16 hidden units per CTA whose epilogue keeps the
+//                 hidden activations in shared memory (three bf16 terms again) and multiplies them with the matching
+//                 16 columns of linear2: a [32, d] slab of partial sums per CTA; the next phase adds up the slabs
+//                 (fixed order) + bias + residual.  The [32, dff] activations never travel.
 //   attention   : one warp per (row, head); cached K / V rows are copied before the barrier too, the step's new row is
 //                 used from registers.
 //   sampling    : (whole-decode kernel) greedy epilogue, END bookkeeping, embedding of the chosen token.

@@ -538,6 +538,6 @@ def test_optin_kernels_match_default_tokens():
         return line[0]
 
     base = digest({})
-    for extra in ({"SCV_SMALL": "0"}, {"SCV_SMALL_PERSIST": "0"}, {"SCV_SMALL_MAX_ROWS": "64"}, {"SCV_FUSE_LN": "1"},
+    for extra in ({"SCV_SMALL": "0"}, {"SCV_SMALL_PERSIST": "0"}, {"SCV_SMALL_MAX_ROWS": "64"}, {"SCV_SMALL_FUSE_FFN": "1"}, {"SCV_FUSE_LN": "1"},
                   {"SCV_GEMM_PERSISTENT": "1"}, {"SCV_GEMM_2CTA": "1"}):
         assert digest(extra) == base, f"{extra} decodes different tokens"
