@@ -33,6 +33,19 @@ const char* scv_last_error(void);
 /* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
 int64_t scv_launch_count(void);
 
+/* Run-time tunables of the launch configuration (no reference counterpart: the reference has no launch configuration).
+ * Keys: "attn_ctas_per_sm" (0 = one CTA per 8 (row, head) items; k > 0 = persistent attention grid of k CTAs per SM so
+ * that another sub-batch's projections can run on the same SMs), "gemm_stages" (0 auto / 2 / 4), "subbatches"
+ * (0 auto; row ranges decoded on separate streams), "sub_min_rows", "graph" (0 / 1: CUDA-graph step replay).
+ * Defaults come from the SCV_* environment variables read at load.  Unknown keys return 1. */
+int scv_tune(const char* key, int32_t value);
+
+/* Debug: CTA residency trace of the step kernels (projection and attention CTAs log kernel id, SM, start and end time).
+ * scv_trace_begin arms it for up to max_records CTAs; scv_trace_read synchronises the device, disarms it and copies the
+ * records (32 bytes each: u64 t0_ns, u64 t1_ns, u32 sm, u32 kernel id, u32 blockIdx.x, u32 blockIdx.y) to HOST memory. */
+int scv_trace_begin(int32_t max_records);
+int scv_trace_read(void* records_host, int32_t max_records, int32_t* n_out);
+
 /* Per-category kernel timing with CUDA events on the launch stream (bench.py roofline pass; adds overhead,
  * never enabled inside a timed region).  Categories are indexed 0..n-1, see scv_profile_category_name. */
 int scv_profile_begin(void);

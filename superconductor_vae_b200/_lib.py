@@ -100,6 +100,9 @@ SIGNATURES = {
     "scv_abi_version": (C.c_int, []),
     "scv_last_error": (C.c_char_p, []),
     "scv_launch_count": (C.c_int64, []),
+    "scv_tune": (C.c_int, [C.c_char_p, C.c_int32]),
+    "scv_trace_begin": (C.c_int, [C.c_int32]),
+    "scv_trace_read": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "scv_profile_begin": (C.c_int, []),
     "scv_profile_end": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double)]),
@@ -174,6 +177,26 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().scv_last_error().decode("utf-8", "replace")
         raise EngineError(f"{what}: {msg}" if what else msg)
+
+
+def tune(**kv) -> None:
+    """Set run-time launch tunables (include/scvae_b200.h scv_tune), e.g. tune(attn_ctas_per_sm=3, subbatches=2)."""
+    for k, v in kv.items():
+        check(lib().scv_tune(k.encode(), int(v)), f"tune({k})")
+
+
+def trace_begin(max_records: int = 1 << 20) -> None:
+    check(lib().scv_trace_begin(int(max_records)), "trace_begin")
+
+
+def trace_read(max_records: int = 1 << 20):
+    """numpy structured array (t0, t1 in ns, sm, kid, bx, by) of the CTAs traced since trace_begin()."""
+    import numpy as np
+    dt = np.dtype([("t0", "<u8"), ("t1", "<u8"), ("sm", "<u4"), ("kid", "<u4"), ("bx", "<u4"), ("by", "<u4")])
+    buf = np.zeros(max_records, dtype=dt)
+    n = C.c_int32(0)
+    check(lib().scv_trace_read(buf.ctypes.data_as(C.c_void_p), int(max_records), C.byref(n)), "trace_read")
+    return buf[:n.value]
 
 
 def launch_count() -> int:

@@ -1,8 +1,10 @@
 // Error reporting, launch accounting, weight store and the kernel-level C-ABI taps.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/scvae_b200.h"
@@ -33,6 +35,33 @@ bool pdl_enabled() {
   static const int forced = [] { const char* e = getenv("SCV_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
   return forced >= 0 ? forced == 1 : g_pdl_call;
 }
+
+// ------------------------------------------------------------------ tunables
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static unsigned g_tune_epoch = 0;
+Tunables& tun() {
+  static Tunables t = {env_int("SCV_ATTN_CTAS", 0), env_int("SCV_GEMM_STAGES", 0), env_int("SCV_SUBBATCHES", 0),
+                       env_int("SCV_GRAPH", 1), env_int("SCV_SUB_MIN_ROWS", 2048)};
+  return t;
+}
+unsigned tune_epoch() { return g_tune_epoch; }
+int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ------------------------------------------------------------------ CTA residency trace
+static void* g_trace_dev = nullptr;
+static unsigned g_trace_cap = 0;
+static bool g_trace_on = false;
+void* trace_ptr() { return g_trace_on ? g_trace_dev : nullptr; }
 
 // ------------------------------------------------------------------ profiling
 struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };
@@ -192,6 +221,46 @@ extern "C" {
 int scv_abi_version(void) { return SCV_ABI_VERSION; }
 const char* scv_last_error(void) { return g_err; }
 int64_t scv_launch_count(void) { return g_launches.load(); }
+
+int scv_tune(const char* key, int32_t value) {
+  SCV_REQUIRE(key != nullptr, "tune: null key");
+  Tunables& t = tun();
+  const std::string k(key);
+  int* slot = k == "attn_ctas_per_sm" ? &t.attn_ctas_per_sm : k == "gemm_stages" ? &t.gemm_stages :
+              k == "subbatches" ? &t.subbatches : k == "graph" ? &t.graph : k == "sub_min_rows" ? &t.sub_min_rows : nullptr;
+  SCV_REQUIRE(slot != nullptr, "tune: unknown key '%s'", key);
+  if (*slot != value) { *slot = value; ++g_tune_epoch; }
+  return 0;
+}
+
+int scv_trace_begin(int32_t max_records) {
+  SCV_REQUIRE(max_records > 0, "trace_begin: max_records must be positive");
+  if (g_trace_dev == nullptr || g_trace_cap < (unsigned)max_records) {
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    g_trace_dev = nullptr;
+    SCV_CUDA(cudaMalloc(&g_trace_dev, sizeof(TraceBuf) + (size_t)max_records * sizeof(TraceRec)));
+    g_trace_cap = (unsigned)max_records;
+  }
+  TraceBuf h{0u, g_trace_cap, 0ull};
+  SCV_CUDA(cudaMemcpy(g_trace_dev, &h, sizeof(h), cudaMemcpyHostToDevice));
+  g_trace_on = true;
+  ++g_tune_epoch;             // captured graphs hold the old (null) trace pointer
+  return 0;
+}
+
+int scv_trace_read(void* records_host, int32_t max_records, int32_t* n_out) {
+  SCV_REQUIRE(g_trace_dev != nullptr && records_host != nullptr && n_out != nullptr, "trace_read: nothing traced");
+  SCV_CUDA(cudaDeviceSynchronize());
+  g_trace_on = false;
+  ++g_tune_epoch;
+  TraceBuf h;
+  SCV_CUDA(cudaMemcpy(&h, g_trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+  const unsigned n = std::min(std::min(h.n, h.cap), (unsigned)max_records);
+  SCV_CUDA(cudaMemcpy(records_host, static_cast<char*>(g_trace_dev) + sizeof(TraceBuf), (size_t)n * sizeof(TraceRec),
+                      cudaMemcpyDeviceToHost));
+  *n_out = (int32_t)n;
+  return 0;
+}
 
 int scv_profile_begin(void) {
   for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }

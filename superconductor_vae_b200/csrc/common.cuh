@@ -65,6 +65,28 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 bool pdl_enabled();
 void set_pdl_for_call(bool on);
 
+// Run-time tunables (scv_tune in the C ABI; defaults from SCV_* environment variables read once at load).  A change bumps
+// tune_epoch(), which makes every decoder drop its captured step graphs.
+struct Tunables {
+  int attn_ctas_per_sm;    // SCV_ATTN_CTAS: 0 = one CTA per 8 (row, head) items; > 0 = persistent grid, that many CTAs per SM
+  int gemm_stages;         // SCV_GEMM_STAGES: 0 = by grid size (4 stages up to one CTA per SM, else 2 x 2 CTAs per SM); 2 / 4 forces
+  int subbatches;          // SCV_SUBBATCHES: 0 = automatic
+  int graph;               // SCV_GRAPH: replay one captured CUDA graph per step
+  int sub_min_rows;        // SCV_SUB_MIN_ROWS: batches at least this large are decoded as sub-batches on separate streams
+};
+Tunables& tun();
+unsigned tune_epoch();
+int sm_count();            // multiprocessors of the current device (cached per device)
+// cudaFuncSetAttribute is per DEVICE: launchers keep one flag per device ordinal and set their attributes the first time
+// they run on each (a process-wide flag would leave a second GPU of the same process without the opt-in shared memory).
+inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -75,6 +97,29 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// ---- CTA residency trace (debug; scv_trace_begin / scv_trace_read): thread 0 of every CTA of the big step kernels logs
+// (kernel id, SM, start, end) with %globaltimer, which shows which kernels of the sub-batch streams really share SMs.
+struct TraceBuf { unsigned n, cap; unsigned long long pad; };
+struct TraceRec { unsigned long long t0, t1; unsigned smid, kid, bx, by; };
+void* trace_ptr();         // device TraceBuf* while tracing, else nullptr
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ TraceRec* trace_begin(void* tb, unsigned kid) {
+  if (tb == nullptr) return nullptr;
+  TraceBuf* b = static_cast<TraceBuf*>(tb);
+  const unsigned i = atomicAdd(&b->n, 1u);
+  if (i >= b->cap) return nullptr;
+  TraceRec* r = reinterpret_cast<TraceRec*>(b + 1) + i;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  r->smid = smid; r->kid = kid; r->bx = blockIdx.x; r->by = blockIdx.y; r->t0 = globaltimer_ns(); r->t1 = 0;
+  return r;
+}
+__device__ __forceinline__ void trace_end(TraceRec* r) { if (r != nullptr) r->t1 = globaltimer_ns(); }
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
 

@@ -217,8 +217,12 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   if (a.st != nullptr && a.st->done) return;
   constexpr int PPI = 32 / LPP;
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (gw >= a.B * a.nhead) return;
+  // The grid may be smaller than the work (a few CTAs per SM, launch_attention): CTAs walk the (row, head) items with a
+  // grid stride, so this HBM-bound kernel leaves registers / shared memory on every SM for the tensor-core projections of
+  // another sub-batch's stream to run beside it ("co-residency").
+  const int n_items = a.B * a.nhead, wpb = blockDim.x >> 5;
+  TraceRec* trc = threadIdx.x == 0 ? trace_begin(a.trace, a.fixed_len >= 0 ? 2u : 1u) : nullptr;
+  for (int gw = blockIdx.x * wpb + warp_in_block; gw < n_items; gw += gridDim.x * wpb) {
   const int b = gw / a.nhead, h = gw % a.nhead;
   const int hd = a.hd;
   const int sb = a.rows_per_seq > 0 ? b / a.rows_per_seq : b;          // sequence whose K / V this query row attends to
@@ -336,7 +340,8 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
       acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
     }
   }
-  if (threadIdx.x == 0) pdl_launch_dependents();   // all K / V of this CTA's first warp are in: let the next kernel ramp up
+  // all K / V of this CTA's first warp are in: let the next kernel ramp up (a grid-stride CTA triggers in its last round)
+  if (threadIdx.x == 0 && gw + gridDim.x * wpb >= n_items) pdl_launch_dependents();
 #pragma unroll
   for (int o = LPP; o < 32; o <<= 1) {       // combine the PPI position groups
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
@@ -358,6 +363,9 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
       *reinterpret_cast<uint2*>(dst + 16384) = make_uint2(lo0, lo1);
     }
   }
+  __syncwarp();          // the warp's score buffer is reused by its next item
+  }
+  trace_end(trc);
 }
 
 int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
@@ -365,9 +373,12 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a_in.max_n >= 1, "attention: max_n must be positive");
   SCV_REQUIRE(a_in.out_split == nullptr || a_in.hd % 8 == 0, "attention: SplitTile output needs head_dim %% 8 == 0");
   AttnArgs a = a_in;
+  a.trace = trace_ptr();
   a.max_n = std::max(a_in.max_n, a_in.hd);     // the score buffer doubles as the staging row of the split output
   const int warps = 8;
-  const int blocks = ceil_div(a.B * a.nhead, warps);
+  int blocks = ceil_div(a.B * a.nhead, warps);
+  const int blocks_v1 = blocks;
+  if (tun().attn_ctas_per_sm > 0) blocks = std::min(blocks, tun().attn_ctas_per_sm * sm_count());
   const size_t smem = (size_t)warps * a.max_n * sizeof(float);
   const int epl = ceil_div(a.hd, 32);
   const bool v4 = a.hd % 4 == 0 && a.ldq % 4 == 0 && a.row_stride % 4 == 0 && a.seq_stride % 4 == 0 && a.page_stride % 4 == 0 &&
@@ -387,10 +398,10 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
     return 0;
   }
   switch (epl) {
-    case 1: SCV_CUDA(launch_k(attention_decode_kernel<1>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
-    case 2: SCV_CUDA(launch_k(attention_decode_kernel<2>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
-    case 3: SCV_CUDA(launch_k(attention_decode_kernel<3>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
-    default: SCV_CUDA(launch_k(attention_decode_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a)); break;
+    case 1: SCV_CUDA(launch_k(attention_decode_kernel<1>, dim3(blocks_v1), dim3(warps * 32), smem, s, a)); break;
+    case 2: SCV_CUDA(launch_k(attention_decode_kernel<2>, dim3(blocks_v1), dim3(warps * 32), smem, s, a)); break;
+    case 3: SCV_CUDA(launch_k(attention_decode_kernel<3>, dim3(blocks_v1), dim3(warps * 32), smem, s, a)); break;
+    default: SCV_CUDA(launch_k(attention_decode_kernel<4>, dim3(blocks_v1), dim3(warps * 32), smem, s, a)); break;
   }
   SCV_LAUNCH_CHECK();
   return 0;
@@ -705,11 +716,10 @@ int launch_sampler(const SamplerArgs& a_in, int which, cudaStream_t s) {
   if (filter) { a.sort_n = kSamplerThreads; while (a.sort_n < a.V) a.sort_n <<= 1; }
   const size_t smem = (size_t)a.V * sizeof(float) + (size_t)a.sort_n * 8;
   ProfScope prof(PC_SAMPLER, s, 4.0 * a.B * a.V, 4.0 * a.B * a.V * (two_phase ? 2 : 1));
-  static bool attr_set = false;
-  if (!attr_set && smem > 40 * 1024) {
+  static bool attr_dev[64] = {};
+  if (smem > 40 * 1024 && first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(sampler_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SCV_CUDA(cudaFuncSetAttribute(sampler_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   SCV_REQUIRE(smem <= 200 * 1024, "sampler: vocabulary of %d tokens does not fit in shared memory", a.V);
   const bool vec_ok = a.V % 4 == 0 && a.ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15u) == 0 &&

@@ -52,6 +52,7 @@ struct AttnArgs {
   int rows_per_seq = 0;
   const unsigned char* key_skip = nullptr;
   const StepState* st = nullptr;                         // null: no done flag / step counter (forward)
+  void* trace = nullptr;                                 // CTA residency trace (common.cuh), normally null
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 

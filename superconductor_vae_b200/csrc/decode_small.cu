@@ -787,10 +787,9 @@ bool small_phase_fits(const SmallPhase& ph, int grid) {
 int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const StepState* st, unsigned* bar, int grid,
                         cudaStream_t s) {
   SCV_REQUIRE(B >= 1 && B <= kSmallMaxRows, "small-batch step: %d rows (1..%d supported)", B, kSmallMaxRows);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(decode_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SM_THREADS); cfg.dynamicSmemBytes = sizeof(Smem); cfg.stream = s;
@@ -820,10 +819,9 @@ int launch_decode_small(const SmallPhase* phases_dev, int n_phases, int B, const
 int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int B, unsigned* bar, int grid, const SmallTail& tail,
                                 cudaStream_t s) {
   SCV_REQUIRE(B >= 1 && B <= kSmallMaxRows, "small-batch decode: %d rows (1..%d supported)", B, kSmallMaxRows);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(decode_small_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SM_THREADS); cfg.dynamicSmemBytes = sizeof(Smem); cfg.stream = s;

@@ -78,6 +78,7 @@ struct scv_decoder {
   DevBuf o_tok, o_lp, o_ent, masks_buf, forced_buf;   // engine-owned I/O so that a captured step never bakes caller pointers
   std::vector<GraphEntry> graphs;    // one instantiated CUDA graph of a decode step per call configuration
   size_t ws_signature = 0;
+  unsigned tune_epoch_seen = 0;
   int* pinned = nullptr;              // host-pinned: [0..1] done polls, [2..9] StepState copy
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaStream_t main = nullptr;             // the decode loop's own stream
@@ -332,7 +333,7 @@ static bool use_tensor_cores(const scv_decoder_config& c, int B) {
          c.vocab_size % 4 == 0 && c.d_model <= 1024;
 }
 
-static int ensure_workspace(scv_decoder* D, int B, int M) {
+static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = false) {
   const scv_decoder_config& c = D->cfg;
   const size_t d = c.d_model, f = sizeof(float);
   const int pps = ceil_div(c.pe_len, kPagePos);
@@ -369,13 +370,20 @@ static int ensure_workspace(scv_decoder* D, int B, int M) {
   SCV_TRY(D->o_ent.ensure(io * f));
   SCV_TRY(D->forced_buf.ensure(io * sizeof(long long)));
   SCV_TRY(D->masks_buf.ensure((size_t)5 * c.vocab_size));
+  if (need_site_dup) {      // captured steps bake these pointers in as well, so they belong to the signature below
+    SCV_TRY(D->seen.ensure((size_t)B * c.vocab_size));
+    SCV_TRY(D->dlog.ensure((size_t)B * sizeof(float)));
+  }
   // captured steps hold raw workspace pointers: drop them whenever any buffer was reallocated
   size_t sig = 0;
   for (const DevBuf* b : {&D->x, &D->xn, &D->qkv, &D->attn, &D->q2, &D->ff, &D->h1, &D->h2, &D->t3, &D->logits, &D->tlog,
                           &D->slog, &D->ckv, &D->kvpool, &D->cur, &D->fin, &D->ptab, &D->state, &D->xn_s, &D->attn_s,
-                          &D->ff_s, &D->h2_s, &D->o_tok, &D->o_lp, &D->o_ent, &D->masks_buf, &D->forced_buf})
+                          &D->ff_s, &D->h2_s, &D->o_tok, &D->o_lp, &D->o_ent, &D->masks_buf, &D->forced_buf, &D->seen,
+                          &D->dlog, &D->sm_part})
     sig = sig * 1000003u + reinterpret_cast<size_t>(b->p);
-  if (sig != D->ws_signature) { D->drop_graphs(); D->ws_signature = sig; }
+  if (sig != D->ws_signature || D->tune_epoch_seen != tune_epoch()) {
+    D->drop_graphs(); D->ws_signature = sig; D->tune_epoch_seen = tune_epoch();
+  }
   return 0;
 }
 
@@ -693,7 +701,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   SCV_REQUIRE(steps_max >= 1, "generate: max_len %d leaves no step to run", A->max_len);
   const int B = A->batch, M = A->n_memory, d = c.d_model;
   set_pdl_for_call(true);
-  SCV_TRY(ensure_workspace(D, B, M));
+  SCV_TRY(ensure_workspace(D, B, M, A->site_dup_threshold > 0.f));
   StepState* st = D->state.as<StepState>();
   SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s));
   // the step kernels read / write engine-owned buffers only (so a captured step can be replayed for any call);
@@ -709,11 +717,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     SCV_CUDA(cudaMemcpyAsync(D->forced_buf.p, A->forced_tokens, io * sizeof(long long), cudaMemcpyDeviceToDevice, s));
     G.forced_tokens = D->forced_buf.as<int64_t>();
   }
-  if (A->site_dup_threshold > 0.f) {
-    SCV_TRY(D->seen.ensure((size_t)B * c.vocab_size));
-    SCV_TRY(D->dlog.ensure((size_t)B * sizeof(float)));
-    SCV_CUDA(cudaMemsetAsync(D->seen.p, 0, (size_t)B * c.vocab_size, s));
-  }
+  if (A->site_dup_threshold > 0.f) SCV_CUDA(cudaMemsetAsync(D->seen.p, 0, (size_t)B * c.vocab_size, s));
   SCV_CUDA(cudaMemsetAsync(D->o_tok.p, 0, io * sizeof(long long), s));
   if (A->want_log_probs) SCV_CUDA(cudaMemsetAsync(D->o_lp.p, 0, io * sizeof(float), s));
   if (A->want_entropy) SCV_CUDA(cudaMemsetAsync(D->o_ent.p, 0, io * sizeof(float), s));
@@ -748,8 +752,8 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // unfinished-row count, H2 flag), sub-batches re-join before the second sampler kernel and before step_end.
   int n_sub = 1;
   {
-    static const int forced = [] { const char* e = getenv("SCV_SUBBATCHES"); return e ? atoi(e) : 0; }();
-    n_sub = forced > 0 ? forced : (B >= 2048 ? 2 : 1);
+    const int forced = tun().subbatches;
+    n_sub = forced > 0 ? forced : (B >= tun().sub_min_rows ? 2 : 1);
     if (prof_enabled()) n_sub = 1;       // per-kernel timing wants one kernel at a time
     n_sub = std::max(1, std::min(n_sub, kMaxSub));
     while (n_sub > 1 && round_up(ceil_div(B, n_sub), 128) * (n_sub - 1) >= B) --n_sub;
@@ -785,8 +789,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // CUDA graph of one step: the launch sequence is identical for every step (position, done flag, RNG seed all live
   // in device memory), so step 0 runs eagerly and steps >= 1 replay one instantiated graph (one launch per step
   // instead of ~150-300); cached per call configuration.
-  static const int graph_env = [] { const char* e = getenv("SCV_GRAPH"); return e ? atoi(e) : 1; }();
-  const bool use_graph = graph_env != 0 && !prof_enabled() && !sync_each && steps_max >= 3;
+  const bool use_graph = tun().graph != 0 && !prof_enabled() && !sync_each && steps_max >= 3;
   const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
                      A->forced_tokens != nullptr, A->flags, A->temperature, A->top_p, A->stop_boost,
                      A->hard_stop_threshold, A->site_dup_threshold};

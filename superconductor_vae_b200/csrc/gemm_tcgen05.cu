@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, m0 = m_tile * BM, n0 = n_tile * BN;
   const int KB = a.kblocks;
+  TraceRec* trc = tid == 0 ? trace_begin(a.trace, 100u + (uint32_t)(a.N >> 7)) : nullptr;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+  trace_end(trc);
 }
 
 // fp32 [N, K] row-major -> bf16 tiles [ceil(N/128)][ceil(K/64)][128 x 64, SW128], zero padded.
@@ -320,8 +322,8 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (tc_2cta_ok(a)) return launch_linear_tcgen05_2cta(a, s);
   if (tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
 #define SCV_SET_SMEM(A, O, R, S, N) \
   SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<A, O, R, S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, N)))
 #define SCV_SET_ALL(S, N)                                                                             \
@@ -330,7 +332,6 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
     SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256);
 #undef SCV_SET_ALL
 #undef SCV_SET_SMEM
-    attr_set = true;
   }
   TcArgs t;
   t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;
@@ -338,6 +339,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.y_split = reinterpret_cast<uint8_t*>(a.y_split); t.kb_out = ceil_div(a.N, BK);
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   t.next_w = static_cast<const uint8_t*>(a.next_w); t.next_w_bytes = (uint32_t)a.next_w_bytes;
+  t.trace = trace_ptr();
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
@@ -365,7 +367,8 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
     SCV_LAUNCH_MODE(3, 256);
   } else {
     dim3 grid(n128, mt);
-    if (n128 * mt <= 148) SCV_LAUNCH_MODE(4, 128); else SCV_LAUNCH_MODE(2, 128);
+    const int stages = tun().gemm_stages == 2 || tun().gemm_stages == 4 ? tun().gemm_stages : (n128 * mt <= 148 ? 4 : 2);
+    if (stages == 4) SCV_LAUNCH_MODE(4, 128); else SCV_LAUNCH_MODE(2, 128);
   }
 #undef SCV_LAUNCH_MODE
 #undef SCV_LAUNCH

@@ -264,13 +264,12 @@ bool tc_2cta_ok(const LinearArgs& a) {
 int launch_linear_tcgen05_2cta(const LinearArgs& a, cudaStream_t s) {
   // SCV_GEMM_2CTA_STAGES: 2 (default, two CTAs per SM) or 4 (one CTA per SM, deeper ring)
   static const int stages = [] { const char* e = getenv("SCV_GEMM_2CTA_STAGES"); return e && atoi(e) == 4 ? 4 : 2; }();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(2)));
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(2)));
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(4)));
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(4)));
-    attr_set = true;
   }
   TcArgs t = {};
   t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;

@@ -277,11 +277,10 @@ bool tc_res_ln_ok(const LinearArgs& a) {
 int launch_linear_res_ln(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_res_ln_ok(a), "fused residual + LayerNorm projection: unsupported shape (M=%d N=%d K=%d)", a.M, a.N, a.K);
   constexpr int SMEM2 = smem_bytes(2, 128) + STATS_BYTES, SMEM4 = smem_bytes(4, 128) + STATS_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(gemm_res_ln_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
     SCV_CUDA(cudaFuncSetAttribute(gemm_res_ln_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM4));
-    attr_set = true;
   }
   TcArgs t = {};
   t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt; t.kblocks = ceil_div(a.K, BK);

@@ -224,12 +224,11 @@ bool tc_persistent_ok(const LinearArgs& a) {
 }
 
 int launch_linear_tcgen05_persistent(const LinearArgs& a, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_dev[64] = {};
+  if (first_use_on_device(attr_dev)) {
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    attr_set = true;
   }
   TcArgs t;
   t.x = a.x; t.ldx = a.ldx; t.a_split = reinterpret_cast<const uint8_t*>(a.a_split); t.wt = a.wt;

@@ -181,7 +181,7 @@ class EnhancedTransformerDecoder(nn.Module):
                                       "(SURVEY.md section 8f row 3 covers the parallel teacher-forced pass only)")
         with torch.no_grad():
             L = self._sync_engine()
-            memory = self._f32(cached_memory, "cached_memory") if cached_memory is not None else \
+            memory = self._checked_memory(cached_memory) if cached_memory is not None else \
                 self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
             device = memory.device
             B, M = memory.size(0), memory.size(1)
@@ -261,6 +261,17 @@ class EnhancedTransformerDecoder(nn.Module):
         _lib.require_cuda(t, name)
         return t.detach().to(torch.float32).contiguous()
 
+    @staticmethod
+    def _check_rows(t: torch.Tensor, name: str, batch: int, features: int, weight: str) -> None:
+        """The kernels read raw pointers with the configured strides, so every shape the reference would reject in
+        F.linear / view / cat is rejected here with the same exception type (RuntimeError)."""
+        if t.dim() != 2 or t.size(1) != features:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({name} {tuple(t.shape)} against "
+                               f"{weight} [*, {features}])")
+        if t.size(0) != batch:
+            raise RuntimeError(f"{name} batch {t.size(0)} != z batch {batch}. Shapes: {name}={tuple(t.shape)}, "
+                               f"z=[{batch}, ...]")
+
     def _heads_matrix(self, heads_pred: Dict[str, torch.Tensor], batch: int, device) -> torch.Tensor:
         """[B, 24] in the order tc, sc, hp, tc_class(5), competence, count, family(14) (:845-858)."""
         fam = heads_pred.get("family_composed_14")
@@ -274,16 +285,37 @@ class EnhancedTransformerDecoder(nn.Module):
                  heads_pred["competence"].unsqueeze(-1), heads_pred["element_count_pred"].unsqueeze(-1)]
         if self.heads_input_dim > 10:
             parts.append(fam if fam is not None else torch.zeros(batch, self.heads_input_dim - 10, device=device))
-        return torch.cat([p.to(device=device, dtype=torch.float32) for p in parts], dim=-1).contiguous()
+        for p_ in parts:
+            if p_.dim() != 2:
+                raise RuntimeError(f"heads_pred entries must be [B] scalars or [B, k] rows, got a part of shape {tuple(p_.shape)}")
+        out = torch.cat([p.to(device=device, dtype=torch.float32) for p in parts], dim=-1).contiguous()
+        if out.size(1) != self.heads_input_dim:          # the reference fails in heads_to_memory[0] (F.linear)
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied (heads_input {tuple(out.shape)} against "
+                               f"heads_to_memory.0.weight [*, {self.heads_input_dim}])")
+        return out
+
+    def _checked_memory(self, cached_memory: torch.Tensor) -> torch.Tensor:
+        m = self._f32(cached_memory, "cached_memory")
+        if m.dim() != 3 or m.size(2) != self.d_model or m.size(1) < 1:
+            raise RuntimeError(f"cached_memory must be [B, n_tokens, {self.d_model}] (precompute_memory's output), "
+                               f"got {tuple(m.shape)}")
+        return m
 
     # ------------------------------------------------------------------ reference API
     def _create_memory(self, z, encoder_skip=None, stoich_pred=None, heads_pred=None) -> torch.Tensor:
         with torch.no_grad():
             L = self._sync_engine()
             z = self._f32(z, "z")
+            if z.dim() != 2 or z.size(1) != self.latent_dim:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied (z {tuple(z.shape)} against "
+                                   f"latent_to_memory.0.weight [*, {self.latent_dim}])")
             B = z.size(0)
             skip = self._f32(encoder_skip, "encoder_skip") if (self.use_skip_connection and encoder_skip is not None) else None
             stoich = self._f32(stoich_pred, "stoich_pred") if (self.use_stoich_conditioning and stoich_pred is not None) else None
+            if skip is not None:
+                self._check_rows(skip, "encoder_skip", B, self.encoder_skip_dim, "skip_to_memory.0.weight")
+            if stoich is not None:
+                self._check_rows(stoich, "stoich_pred", B, self.stoich_input_dim, "stoich_to_memory.0.weight")
             heads = self._heads_matrix(heads_pred, B, z.device) if heads_pred is not None else None
             M = self.n_memory_tokens + (self.skip_n_tokens if skip is not None else 0) + \
                 (self.stoich_n_tokens if stoich is not None else 0) + (self.heads_n_tokens if heads is not None else 0)
@@ -315,7 +347,7 @@ class EnhancedTransformerDecoder(nn.Module):
             max_len = pe_max                                                # silent clamp (:1372-1375)
         with torch.no_grad():
             L = self._sync_engine()
-            memory = self._f32(cached_memory, "cached_memory") if cached_memory is not None else \
+            memory = self._checked_memory(cached_memory) if cached_memory is not None else \
                 self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
             device = memory.device
             B, M = memory.size(0), memory.size(1)
@@ -332,6 +364,8 @@ class EnhancedTransformerDecoder(nn.Module):
             ents = torch.zeros((B, steps_max), dtype=torch.float32, device=device) if return_entropy else None
             forced = None
             if _forced_tokens is not None:
+                if _forced_tokens.dim() != 2 or _forced_tokens.size(0) != B:
+                    raise RuntimeError(f"_forced_tokens must be [{B}, L], got {tuple(_forced_tokens.shape)}")
                 forced = torch.zeros((B, steps_max), dtype=torch.int64, device=device)
                 n = min(steps_max, _forced_tokens.size(1))
                 forced[:, :n] = _forced_tokens[:, :n].to(device)
