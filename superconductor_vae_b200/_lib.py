@@ -147,13 +147,46 @@ SIGNATURES = {
 }
 
 
-def build(verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a into libscvae_b200.so (nvcc cross-compiles without a GPU)."""
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")) or f == "Makefile")
+    for f in files + [os.path.join("..", "..", "include", "scvae_b200.h")]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def build(verbose: bool = False, clean: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into libscvae_b200.so (nvcc cross-compiles without a GPU).
+
+    `clean=True` removes every object first, so a successful return proves that every source compiled (about 30 s).
+    Either way the build is recorded in csrc/build/BUILD_INFO.json together with the hash of the sources it was made
+    from; a library whose recorded hash differs from the current sources is rebuilt from scratch."""
+    import json
+    import time
+    info_path = os.path.join(CSRC, "build", "BUILD_INFO.json")
+    cur = _source_hash()
+    try:
+        with open(info_path) as fh:
+            stale = json.load(fh).get("source_sha256") != cur
+    except (OSError, ValueError):
+        stale = True
+    if clean or stale or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", CSRC, "clean"], capture_output=True, text=True)
+        clean = True
+    t0 = time.time()
     r = subprocess.run(["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))], capture_output=True, text=True)
     if r.returncode != 0:
         raise EngineError("building libscvae_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    compiled = [ln.split(" -c ")[1].split()[0] for ln in r.stdout.splitlines() if " -c " in ln]
+    if clean or compiled:
+        os.makedirs(os.path.dirname(info_path), exist_ok=True)
+        with open(info_path, "w") as fh:
+            json.dump({"source_sha256": cur, "clean_build": bool(clean), "compiled": compiled, "seconds": round(time.time() - t0, 1),
+                       "flags": "-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"}, fh, indent=1)
     if verbose:
-        print(r.stdout[-2000:])
+        print(f"libscvae_b200.so: {len(compiled)} translation units compiled ({'clean' if clean else 'incremental'} build)")
     return LIB_PATH
 
 

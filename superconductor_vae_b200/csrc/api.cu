@@ -66,8 +66,11 @@ void* trace_ptr() { return g_trace_on ? g_trace_dev : nullptr; }
 // ------------------------------------------------------------------ profiling
 struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };
 static bool g_prof = false;
+static bool g_recs_pending = false;                 // records whose events have been (re)recorded since the last harvest
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_event_pool;
+static int g_acc_n[PC_COUNT];
+static double g_acc_ms[PC_COUNT], g_acc_flops[PC_COUNT], g_acc_bytes[PC_COUNT];
 bool prof_enabled() { return g_prof; }
 static cudaEvent_t get_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
@@ -81,9 +84,26 @@ ProfScope::ProfScope(int cat, cudaStream_t s, double flops, double bytes) : idx_
   cudaEventRecord(r.a, s);
   idx_ = (int)g_recs.size();
   g_recs.push_back(r);
+  g_recs_pending = true;
 }
 ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_recs[idx_].b, s_);
+}
+void prof_step_begin() {
+  for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_recs.clear();
+  g_recs_pending = false;
+}
+void prof_mark_pending() { g_recs_pending = !g_recs.empty(); }
+int prof_harvest() {           // the caller has synchronised the stream(s) the records were taken on
+  if (!g_recs_pending) return 0;
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    SCV_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    g_acc_n[r.cat] += 1; g_acc_ms[r.cat] += t; g_acc_flops[r.cat] += r.flops; g_acc_bytes[r.cat] += r.bytes;
+  }
+  g_recs_pending = false;
+  return 0;
 }
 
 // ------------------------------------------------------------------ WeightStore
@@ -263,8 +283,8 @@ int scv_trace_read(void* records_host, int32_t max_records, int32_t* n_out) {
 }
 
 int scv_profile_begin(void) {
-  for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
-  g_recs.clear();
+  prof_step_begin();
+  for (int i = 0; i < PC_COUNT; ++i) { g_acc_n[i] = 0; g_acc_ms[i] = g_acc_flops[i] = g_acc_bytes[i] = 0.0; }
   g_prof = true;
   return 0;
 }
@@ -273,20 +293,16 @@ int scv_profile_end(int32_t n_cats, int32_t* counts, double* ms, double* flops, 
   g_prof = false;
   SCV_REQUIRE(n_cats >= PC_COUNT && counts && ms && flops && bytes, "profile_end: need room for %d categories", (int)PC_COUNT);
   SCV_CUDA(cudaDeviceSynchronize());
+  SCV_TRY(prof_harvest());
+  prof_step_begin();
   for (int i = 0; i < n_cats; ++i) { counts[i] = 0; ms[i] = flops[i] = bytes[i] = 0.0; }
-  for (auto& r : g_recs) {
-    float t = 0.f;
-    SCV_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
-    counts[r.cat] += 1; ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes;
-    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
-  }
-  g_recs.clear();
+  for (int i = 0; i < PC_COUNT; ++i) { counts[i] = g_acc_n[i]; ms[i] = g_acc_ms[i]; flops[i] = g_acc_flops[i]; bytes[i] = g_acc_bytes[i]; }
   return 0;
 }
 
 const char* scv_profile_category_name(int32_t cat) {
   static const char* names[PC_COUNT] = {"linear_simt", "layernorm", "attention_self", "attention_cross", "sampler",
-                                        "embed", "misc", "gemm_tcgen05"};
+                                        "embed", "misc", "gemm_tcgen05", "event_pair_overhead"};
   return (cat >= 0 && cat < PC_COUNT) ? names[cat] : "";
 }
 

@@ -46,8 +46,15 @@ long long launch_total();
 
 // Optional per-category kernel timing (CUDA events on the launch stream), used by bench.py's roofline pass.
 enum ProfCat : int { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_SELF, PC_ATTN_CROSS, PC_SAMPLER, PC_EMBED, PC_MISC,
-                     PC_GEMM_TC, PC_COUNT };
+                     PC_GEMM_TC, PC_NULL /* two events back to back: the overhead one ProfScope adds */, PC_COUNT };
 bool prof_enabled();
+// Profiling protocol of a replayed step (decoder.cu): prof_step_begin() forgets the previous step's records, the step is
+// enqueued or captured (every ProfScope adds a record; inside a capture its events become event-record nodes, so the
+// kernels are timed at full device speed with no host launch latency between an event and its kernel), and after every
+// execution of the step + a stream synchronise prof_harvest() adds the elapsed time of every record to the category totals.
+void prof_step_begin();
+void prof_mark_pending();
+int prof_harvest();
 struct ProfScope {
   ProfScope(int cat, cudaStream_t s, double flops, double bytes);
   ~ProfScope();

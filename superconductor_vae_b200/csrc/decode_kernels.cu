@@ -695,7 +695,10 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
       tok = 0;
       for (int i = 0; i < kSamplerThreads / 32; ++i) tok = max(tok, redi[i]);
     }
-    if (a.forced != nullptr) tok = (int)a.forced[(size_t)b * a.out_ld + step];
+    if (a.forced != nullptr) {           // teacher-forced replay; a negative entry leaves that position sampled
+      const long long f = a.forced[(size_t)b * a.out_ld + step];
+      if (f >= 0) tok = (int)f;
+    }
     const float p = sl[tok] / total;
     commit_token(a, b, step, tok, logf(fmaxf(p, 1e-8f)));                            // (:1518)
   }

@@ -43,12 +43,12 @@ constexpr int kMaxSub = 4;
 
 // Everything that is baked into the kernel arguments of one decode step.
 struct GraphKey {
-  int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced;
+  int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced, prof;
   unsigned flags;
   float temperature, top_p, stop_boost, hard_stop, site_dup;
   bool operator==(const GraphKey& o) const {
     return B == o.B && M == o.M && steps_max == o.steps_max && n_sub == o.n_sub && top_k == o.top_k &&
-           has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced &&
+           has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced && prof == o.prof &&
            flags == o.flags && temperature == o.temperature && top_p == o.top_p && stop_boost == o.stop_boost &&
            hard_stop == o.hard_stop && site_dup == o.site_dup;
   }
@@ -744,7 +744,12 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   }
   D->pinned[0] = D->pinned[1] = 0;
   bool used[2] = {false, false};
-  const bool sync_each = (A->flags & SCV_FLAG_SYNC_EVERY_STEP) != 0;
+  // Profiling pass (bench.py roofline): the host waits for every step, so no step is enqueued after the batch has
+  // finished (no-op launches would be timed and their flops counted), and the step still replays as a graph whose
+  // event-record nodes time every kernel without host launch latency in between.
+  const bool prof = prof_enabled();
+  const bool sync_each = (A->flags & SCV_FLAG_SYNC_EVERY_STEP) != 0 || prof;
+  if (prof) { SCV_CUDA(cudaStreamSynchronize(s)); SCV_TRY(prof_harvest()); }    // memory K/V projections above
   const bool two_phase = !(A->temperature < 0.01f) || A->want_entropy;
   // Sub-batches: the ~150 dependent kernels of a step are short at these sizes (a few microseconds of tensor work
   // behind fixed launch / prologue / tail costs), so the batch is decoded as independent row ranges on separate
@@ -760,6 +765,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   }
   const int sub_rows = n_sub > 1 ? round_up(ceil_div(B, n_sub), 128) : B;
   auto enqueue_step = [&](int step) -> int {
+    if (prof) { prof_step_begin(); ProfScope null_pair(PC_NULL, s, 0.0, 0.0); }
     if (n_sub == 1) {
       SCV_TRY(decode_rows(D, A, steps_max, step, 0, B, 1, s));
       if (two_phase) SCV_TRY(decode_rows(D, A, steps_max, step, 0, B, 2, s));
@@ -789,9 +795,9 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // CUDA graph of one step: the launch sequence is identical for every step (position, done flag, RNG seed all live
   // in device memory), so step 0 runs eagerly and steps >= 1 replay one instantiated graph (one launch per step
   // instead of ~150-300); cached per call configuration.
-  const bool use_graph = tun().graph != 0 && !prof_enabled() && !sync_each && steps_max >= 3;
+  const bool use_graph = tun().graph != 0 && (A->flags & SCV_FLAG_SYNC_EVERY_STEP) == 0 && steps_max >= 3;
   const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
-                     A->forced_tokens != nullptr, A->flags, A->temperature, A->top_p, A->stop_boost,
+                     A->forced_tokens != nullptr, prof ? 1 : 0, A->flags, A->temperature, A->top_p, A->stop_boost,
                      A->hard_stop_threshold, A->site_dup_threshold};
   cudaGraphExec_t exec = nullptr;
   if (use_graph)
@@ -815,6 +821,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
         if (D->graphs.size() >= 8) D->drop_graphs();
         D->graphs.push_back({key, exec});
       }
+      if (prof) prof_mark_pending();
       SCV_CUDA(cudaGraphLaunch(exec, s));
       count_launch(D->launches_per_step);
     } else {
@@ -824,6 +831,13 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     }
     if (sync_each) {
       SCV_CUDA(cudaStreamSynchronize(s));
+      if (prof) {
+        SCV_TRY(prof_harvest());
+        int done_now = 0;
+        SCV_CUDA(cudaMemcpy(&done_now, &st->done, sizeof(int), cudaMemcpyDeviceToHost));
+        if (done_now != 0) break;
+        continue;
+      }
     }
     const int poll = use_graph ? 1 : 2;
     if ((step % poll) == poll - 1 && step + 1 < steps_max) {

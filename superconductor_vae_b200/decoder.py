@@ -366,7 +366,8 @@ class EnhancedTransformerDecoder(nn.Module):
             if _forced_tokens is not None:
                 if _forced_tokens.dim() != 2 or _forced_tokens.size(0) != B:
                     raise RuntimeError(f"_forced_tokens must be [{B}, L], got {tuple(_forced_tokens.shape)}")
-                forced = torch.zeros((B, steps_max), dtype=torch.int64, device=device)
+                # positions beyond the given columns, and negative entries, stay sampled (-1)
+                forced = torch.full((B, steps_max), -1, dtype=torch.int64, device=device)
                 n = min(steps_max, _forced_tokens.size(1))
                 forced[:, :n] = _forced_tokens[:, :n].to(device)
             if _seed is None:

@@ -40,6 +40,15 @@ def _shard_meta(local: torch.Tensor, group) -> List[Tuple[int, int]]:
     return [(int(m[0]), int(m[1])) for m in metas]
 
 
+def _wire(t: torch.Tensor) -> torch.Tensor:
+    """int16 has no NCCL / gloo wire type: such rows travel as their bytes."""
+    return t.contiguous().view(torch.uint8) if t.dtype == torch.int16 else t
+
+
+def _unwire(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    return t.view(torch.int16) if dtype == torch.int16 else t
+
+
 def gather_rows(local: torch.Tensor, n_rows_total: int, pad_value=0, group=None) -> torch.Tensor:
     """All-gather [n_local, L_local] shards into [n_rows_total, L_max].
 
@@ -51,9 +60,10 @@ def gather_rows(local: torch.Tensor, n_rows_total: int, pad_value=0, group=None)
     n_max = max(m[0] for m in metas)
     buf = torch.full((n_max, l_max), pad_value, dtype=local.dtype, device=local.device)
     buf[:local.shape[0], :local.shape[1]] = local
-    parts = [torch.empty_like(buf) for _ in range(ws)]
-    dist.all_gather(parts, buf, group=group)
-    out = torch.cat([p[:m[0]] for p, m in zip(parts, metas)], dim=0)
+    wire = _wire(buf)
+    parts = [torch.empty_like(wire) for _ in range(ws)]
+    dist.all_gather(parts, wire, group=group)
+    out = torch.cat([_unwire(p, local.dtype)[:m[0]] for p, m in zip(parts, metas)], dim=0)
     assert out.shape[0] == n_rows_total, (out.shape, n_rows_total)
     return out
 
@@ -166,13 +176,14 @@ class ChunkedGather:
         buf = torch.zeros((n_max, self.pad_to), dtype=self.dtype, device=tokens.device)
         if tokens.numel() > 0:
             buf[:tokens.shape[0], :tokens.shape[1]] = tokens.to(self.dtype)
-        parts = [torch.empty_like(buf) for _ in range(self.ws)]
-        work = dist.all_gather(parts, buf, group=self.group, async_op=True)
+        wire = _wire(buf)
+        parts = [torch.empty_like(wire) for _ in range(self.ws)]
+        work = dist.all_gather(parts, wire, group=self.group, async_op=True)
         self.pending.append((work, parts, list(rows_per_rank)))
 
     def finish(self) -> torch.Tensor:
         for work, _, _ in self.pending:
             work.wait()
-        rows = [parts[r][:counts[r]] for r in range(self.ws) for _, parts, counts in self.pending]
+        rows = [_unwire(parts[r], self.dtype)[:counts[r]] for r in range(self.ws) for _, parts, counts in self.pending]
         self.pending = []
         return torch.cat(rows, dim=0)

@@ -174,6 +174,84 @@ def test_gather_rows_world_size_2():
     assert torch.equal(lp, out.float() * 0.5)
 
 
+class _FakeDecoder:
+    """Host-logic stand-in: token (r, c) = hash of the row's own conditioning, so a wrongly sliced input shows."""
+    vocab_size = 4752
+
+    def generate_with_kv_cache(self, z, stoich_pred=None, heads_pred=None, encoder_skip=None, cached_memory=None,
+                               _forced_tokens=None, return_log_probs=False, **kw):
+        ref = z if z is not None else cached_memory.reshape(cached_memory.shape[0], -1)
+        key = ref.sum(dim=1)
+        for t in (stoich_pred, encoder_skip, _forced_tokens) + tuple((heads_pred or {}).values()):
+            if t is not None:
+                assert t.shape[0] == ref.shape[0], "per-row input not cut to the shard"
+                key = key + t.reshape(t.shape[0], -1).float().sum(dim=1)
+        L = 4
+        toks = (key.unsqueeze(1) * 7 + torch.arange(L).unsqueeze(0)).to(torch.int64) % 4000 + 3
+        return toks, (toks.float() * 0.25 if return_log_probs else None), None
+
+    def sample_for_reinforce(self, z, stoich_pred=None, heads_pred=None, **kw):
+        t, lp, _ = self.generate_with_kv_cache(z, stoich_pred=stoich_pred, heads_pred=heads_pred, return_log_probs=True, **kw)
+        return t, lp, lp * 2, torch.ones_like(lp)
+
+
+def _sharded_worker(rank, ws, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=ws)
+    g = torch.Generator().manual_seed(1)
+    n = 13
+    z = torch.randint(0, 50, (n, 6), generator=g).float()
+    st = torch.randint(0, 50, (n, 3), generator=g).float()
+    hp = {"tc_pred": torch.randint(0, 50, (n,), generator=g).float()}
+    skip = torch.randint(0, 50, (n, 2), generator=g).float()
+    dec = _FakeDecoder()
+    full, full_lp, _ = dec.generate_with_kv_cache(z, stoich_pred=st, heads_pred=hp, encoder_skip=skip, return_log_probs=True)
+    t, lp, _ = parallel.generate_sharded(dec, z, stoich_pred=st, heads_pred=hp, encoder_skip=skip, return_log_probs=True)
+    mem = z.reshape(n, 2, 3)
+    fm, _, _ = dec.generate_with_kv_cache(None, cached_memory=mem)
+    tm, _, _ = parallel.generate_sharded(dec, None, cached_memory=mem)
+    B, k = 5, 3
+    tr, lpr, enr, mkr = parallel.sample_for_reinforce_sharded(dec, z[:B], k, stoich_pred=st[:B], heads_pred={"tc_pred": hp["tc_pred"][:B]})
+    fr, flr, _, _ = dec.sample_for_reinforce(z[:B].repeat(k, 1), stoich_pred=st[:B].repeat(k, 1),
+                                             heads_pred={"tc_pred": hp["tc_pred"][:B].repeat(k)})
+    bad = None
+    try:
+        parallel.generate_sharded(dec, z, stoich_pred=st[:5])
+    except RuntimeError as e:
+        bad = str(e)
+    # chunked asynchronous gather (config 4): every rank walks its slice in chunks of 3 rows
+    lo, hi = parallel.shard_bounds(n, ws, rank)
+    cg = parallel.ChunkedGather(pad_to=4, dtype=torch.int16)
+    bounds = [parallel.shard_bounds(n, ws, r) for r in range(ws)]
+    n_chunks = max((h - l + 2) // 3 for l, h in bounds)
+    for c in range(n_chunks):
+        counts = [max(0, min(3, (h - l) - 3 * c)) for l, h in bounds]
+        rows = full[lo + 3 * c: lo + 3 * c + counts[rank]]
+        cg.push(rows, counts)
+    chunked = cg.finish()
+    if rank == 0:
+        q.put((t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked))
+    dist.destroy_process_group()
+
+
+def test_generate_sharded_slices_every_per_row_input_world_size_2():
+    ws, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert t.dtype == torch.int16 and torch.equal(t.to(torch.int64), full) and torch.equal(lp, full_lp)
+    assert torch.equal(tm.to(torch.int64), fm)
+    assert tr.dtype == torch.int64 and torch.equal(tr, fr) and torch.equal(lpr, flr)     # global sample-major order
+    assert bad is not None and "stoich_pred" in bad
+    assert torch.equal(chunked.to(torch.int64), full)
+
+
 def test_legacy_vocab_of_generate_formulas_fast(golden_dir):
     from superconductor_vae_b200.decoder import _LEGACY_VOCAB
     g = torch.load(os.path.join(golden_dir, "tokenizer.pt"), weights_only=False)
@@ -194,4 +272,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    from oracle import ref_loader
+    # the unmodified reference module when oracle/_ref has been built (oracle/make_ref.py), else the golden-pinned port
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0

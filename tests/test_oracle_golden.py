@@ -201,3 +201,36 @@ def test_teacher_forced_forward_matches_reference(golden_dir, name, shape, nhead
     torch.testing.assert_close(dup, g["site_dup_logits"], rtol=2e-4, atol=2e-4)
     assert (gen.to(torch.int16) == g["generated"]).float().mean() > 0.99
 
+
+
+def test_oracle_matches_the_live_reference_module():
+    """The oracle restatement against the UNMODIFIED reference module imported from oracle/_ref (the copy
+    oracle/make_ref.py takes from /root/reference at build time; it travels to the GPU box): greedy tokens with masks +
+    stop head identical, memory / log-probs / entropy of an RNG-identical sampled rollout within fp32 noise.  This runs
+    wherever oracle/_ref exists, so the oracle is re-pinned on every box, not only by the committed fixtures."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built (run python oracle/make_ref.py in the build container)")
+    shape = W.TINY
+    sd = W.make_decoder_state_dict(shape, 0)
+    dec = ref_loader.reference_decoder(shape, sd)
+    B = 9
+    z = W.make_latents(B, shape.latent_dim, 4321)
+    stoich, heads = W.make_conditioning(B, shape.stoich_input_dim, 4321)
+    masks = OV.type_masks(**OV.TINY_LAYOUT)
+    with torch.no_grad():
+        mem = dec.precompute_memory(z, None, stoich, heads)
+    torch.testing.assert_close(DO.build_memory(sd, z, None, stoich, heads), mem, rtol=1e-5, atol=1e-6)
+    kw = dict(temperature=0.001, max_len=shape.max_len, type_masks=masks, stop_boost=10.0, hard_stop_threshold=0.8)
+    rt, _, _ = dec.generate_with_kv_cache(z, stoich_pred=stoich, heads_pred=heads, **kw)
+    ot, _, _ = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, heads_pred=heads, **kw)
+    assert torch.equal(rt, ot)
+    torch.manual_seed(5)
+    rt, rlp, ren, rmk = dec.sample_for_reinforce(z, stoich_pred=stoich, temperature=1.1, max_len=shape.max_len, stop_boost=10.0,
+                                                 heads_pred=heads)
+    torch.manual_seed(5)
+    ot, olp, oen, omk = DO.sample_for_reinforce(sd, shape.nhead, z, stoich_pred=stoich, temperature=1.1, max_len=shape.max_len,
+                                                stop_boost=10.0, heads_pred=heads)
+    assert torch.equal(rt, ot) and torch.equal(rmk, omk)
+    torch.testing.assert_close(olp, rlp, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(oen, ren, rtol=1e-4, atol=1e-5)
