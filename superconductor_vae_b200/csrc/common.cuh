@@ -48,10 +48,9 @@ long long launch_total();
 enum ProfCat : int { PC_LINEAR = 0, PC_LAYERNORM, PC_ATTN_SELF, PC_ATTN_CROSS, PC_SAMPLER, PC_EMBED, PC_MISC,
                      PC_GEMM_TC, PC_NULL /* two events back to back: the overhead one ProfScope adds */, PC_COUNT };
 bool prof_enabled();
-// Profiling protocol of a replayed step (decoder.cu): prof_step_begin() forgets the previous step's records, the step is
-// enqueued or captured (every ProfScope adds a record; inside a capture its events become event-record nodes, so the
-// kernels are timed at full device speed with no host launch latency between an event and its kernel), and after every
-// execution of the step + a stream synchronise prof_harvest() adds the elapsed time of every record to the category totals.
+// Profiling protocol of a step (decoder.cu): prof_step_begin() forgets the previous step's records, the step is enqueued
+// behind a gate kernel (every ProfScope adds a record), the gate opens, and after a stream synchronise prof_harvest() adds
+// the elapsed time of every record to the category totals.
 void prof_step_begin();
 void prof_mark_pending();
 int prof_harvest();
@@ -80,6 +79,13 @@ struct Tunables {
   int subbatches;          // SCV_SUBBATCHES: 0 = automatic
   int graph;               // SCV_GRAPH: replay one captured CUDA graph per step
   int sub_min_rows;        // SCV_SUB_MIN_ROWS: batches at least this large are decoded as sub-batches on separate streams
+  int attn_bulk;           // SCV_ATTN_BULK: cross-attention through the bulk-copy (cp.async.bulk) staged kernel
+  int attn_bulk_min_rows;  // SCV_ATTN_BULK_MIN_ROWS: ... for launches with at least this many rows
+  int attn_bulk_piece_kb;  // SCV_ATTN_BULK_PIECE_KB: a sequence's block travels as copies of this size (0 = one copy)
+  int cluster;             // SCV_CLUSTER: small batches through the cluster-parallel kernel (decode_cluster.cu); opt-in: measured
+                           // 0.76-0.92 ms per step against 0.77-0.84 ms for the grid-barrier kernel
+  int cluster_max_rows;    // SCV_CLUSTER_MAX_ROWS: ... up to this many rows (<= 64)
+  int cluster_rows;        // SCV_CLUSTER_ROWS: rows per cluster (0 = automatic: 1 up to 16 rows, 2 up to 32, else 4)
 };
 Tunables& tun();
 unsigned tune_epoch();

@@ -368,6 +368,193 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   trace_end(trc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-attention with bulk-copy staging (decode only: one query row per sequence, contiguous K / V).
+// A sequence's projected memory tokens of one layer are ONE contiguous block ([M][k(d) | v(d)] fp32 = 96 KB for
+// M = 24, d = 512), so instead of thousands of per-thread 16-byte loads a single elected thread streams whole blocks
+// into a two-stage shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier transaction counts, one persistent CTA per
+// SM, while the warps (one per head) compute scores / softmax / P*V out of shared memory.  The load side is then pure
+// DMA: no address arithmetic, no load instructions in the issue slots (the per-thread kernel above runs at 61 % issue
+// utilisation and 57 % warps active while it streams; ncu, profiles/ncu_full_r01n_summary.csv), and up to two blocks
+// (192 KB) per SM are in flight independent of how the warps are scheduled.  Same arithmetic, in the same order, as
+// attention_decode_v4_kernel, so the two kernels produce identical bits.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "XWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra XWAIT_DONE;\n\t"
+      "bra XWAIT_LOOP;\n\t"
+      "XWAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256, 1) attention_cross_bulk_kernel(AttnArgs a, int kv_floats, int q_floats, int piece_bytes) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  pdl_wait();
+  if (a.st != nullptr && a.st->done) return;
+  constexpr int PPI = 32 / LPP, UNR = 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int n = a.fixed_len, hd = a.hd;
+  float* kv_s[2] = {reinterpret_cast<float*>(bulk_smem), reinterpret_cast<float*>(bulk_smem) + kv_floats};
+  float* q_s[2] = {kv_s[1] + kv_floats, kv_s[1] + kv_floats + q_floats};
+  float* sc = q_s[1] + q_floats + (size_t)warp * a.max_n;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_s[1] + q_floats + (size_t)nwarps * a.max_n);
+  const uint32_t bar[2] = {smem_addr_u32(&bars[0]), smem_addr_u32(&bars[1])};
+  TraceRec* trc = tid == 0 ? trace_begin(a.trace, 3u) : nullptr;
+  if (tid == 0) {
+    mbar_init_(bar[0], 1);
+    mbar_init_(bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t kv_bytes = (uint32_t)kv_floats * 4u, q_bytes = (uint32_t)q_floats * 4u;
+  auto issue = [&](int row, int st) {
+    mbar_arrive_expect_tx_(bar[st], kv_bytes + q_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.kcache + (size_t)row * a.seq_stride);
+    const uint32_t dst = smem_addr_u32(kv_s[st]);
+    for (uint32_t off = 0; off < kv_bytes; off += (uint32_t)piece_bytes)      // several copies in flight per block
+      bulk_g2s_(dst + off, src + off, min((uint32_t)piece_bytes, kv_bytes - off), bar[st]);
+    bulk_g2s_(smem_addr_u32(q_s[st]), a.q + (size_t)row * a.ldq, q_bytes, bar[st]);
+  };
+  const int G = gridDim.x;
+  if (tid == 0) {
+    if ((int)blockIdx.x < a.B) issue(blockIdx.x, 0);
+    if ((int)blockIdx.x + G < a.B) issue(blockIdx.x + G, 1);
+  }
+  const int grp = lane / LPP, e0 = 4 * (lane % LPP);
+  const bool e_ok = e0 < hd;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long v_off = a.vcache - a.kcache;          // d floats: V follows K inside a token's row
+  int it = 0;
+  for (int b = blockIdx.x; b < a.B; b += G, ++it) {
+    const int st = it & 1;
+    mbar_wait_(bar[st], (uint32_t)(it >> 1) & 1u);
+    for (int h = warp; h < a.nhead; h += nwarps) {
+      const float* kb = kv_s[st] + h * hd + e0;          // K of token 0, this lane's slice of head h
+      const float4 q4 = e_ok ? *reinterpret_cast<const float4*>(q_s[st] + h * hd + e0) : zero4;
+      for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+        float4 kv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int p = p0 + u * PPI + grp;
+          kv[u] = (p < n && e_ok) ? *reinterpret_cast<const float4*>(kb + (size_t)p * a.row_stride) : zero4;
+        }
+        float d[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) d[u] = fmaf(q4.x, kv[u].x, fmaf(q4.y, kv[u].y, fmaf(q4.z, kv[u].z, q4.w * kv[u].w)));
+        if constexpr (LPP == 16 && UNR == 4) {
+          const int sub = lane & 15;
+          const bool up8 = (sub & 8) != 0, up4 = (sub & 4) != 0;
+          const float r0 = __shfl_xor_sync(0xffffffffu, up8 ? d[0] : d[2], 8);
+          const float r1 = __shfl_xor_sync(0xffffffffu, up8 ? d[1] : d[3], 8);
+          const float e0s = (up8 ? d[2] : d[0]) + r0, e1s = (up8 ? d[3] : d[1]) + r1;
+          float f = (up4 ? e1s : e0s) + __shfl_xor_sync(0xffffffffu, up4 ? e0s : e1s, 4);
+          f += __shfl_xor_sync(0xffffffffu, f, 2);
+          f += __shfl_xor_sync(0xffffffffu, f, 1);
+          const int u_mine = 2 * (sub >> 3) + ((sub >> 2) & 1);
+          const int p = p0 + u_mine * PPI + grp;
+          if ((sub & 3) == 0 && p < n) sc[p] = f * a.scale;
+        } else {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            float dd = d[u];
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            const int p = p0 + u * PPI + grp;
+            if ((lane % LPP) == 0 && p < n) sc[p] = dd * a.scale;
+          }
+        }
+      }
+      __syncwarp();
+      float m = -INFINITY;
+      for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int p = lane; p < n; p += 32) {
+        const float e = expf(sc[p] - m);
+        sc[p] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
+      __syncwarp();
+      float4 acc = zero4;
+      const float* vb = kb + v_off;
+      for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+        float4 vv[UNR];
+        float w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int p = p0 + u * PPI + grp;
+          const bool ok = p < n && e_ok;
+          vv[u] = ok ? *reinterpret_cast<const float4*>(vb + (size_t)p * a.row_stride) : zero4;
+          w[u] = ok ? sc[p] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          acc.x = fmaf(w[u], vv[u].x, acc.x); acc.y = fmaf(w[u], vv[u].y, acc.y);
+          acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
+        }
+      }
+#pragma unroll
+      for (int o = LPP; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (grp == 0 && e_ok) {
+        if (a.out_split == nullptr) {
+          *reinterpret_cast<float4*>(a.out + (size_t)b * a.ldo + h * hd + e0) = acc;
+        } else {
+          uint32_t hi0, lo0, hi1, lo1;
+          split_pair(acc.x, acc.y, hi0, lo0);
+          split_pair(acc.z, acc.w, hi1, lo1);
+          const int col = h * hd + e0;
+          const int mt = b >> 7, ri = b & 127, kb2 = col >> 6, cj = (col & 63) >> 3;
+          uint8_t* dst = a.out_split + ((size_t)mt * a.kb_out + kb2) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4) +
+                         (size_t)((col & 7) >> 2) * 8;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(hi0, hi1);
+          *reinterpret_cast<uint2*>(dst + 16384) = make_uint2(lo0, lo1);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();                         // every warp is done with stage st: refill it
+    if (tid == 0) {
+      if (b + 2 * G < a.B) issue(b + 2 * G, st);
+      else if (b + G >= a.B) pdl_launch_dependents();   // nothing left to stream for this CTA: let the next kernel ramp up
+    }
+  }
+  trace_end(trc);
+}
+
+// bytes of dynamic shared memory of the bulk kernel, or 0 when the shape does not fit two stages
+static size_t cross_bulk_smem(const AttnArgs& a, int warps) {
+  if (a.fixed_len < 0 || a.page_table != nullptr || a.rows_per_seq != 0 || a.key_skip != nullptr) return 0;
+  const size_t kv = (size_t)a.fixed_len * a.row_stride * sizeof(float), q = (size_t)a.nhead * a.hd * sizeof(float);
+  if (a.seq_stride != (long long)a.fixed_len * a.row_stride) return 0;                  // one contiguous block per sequence
+  if (a.vcache - a.kcache <= 0 || a.vcache - a.kcache >= a.row_stride) return 0;        // V inside the token's row
+  if (kv % 16 != 0 || q % 16 != 0 || (a.ldq * sizeof(float)) % 16 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(a.kcache) & 15u) != 0 || (reinterpret_cast<uintptr_t>(a.q) & 15u) != 0) return 0;
+  const size_t total = 2 * (kv + q) + (size_t)warps * a.max_n * sizeof(float) + 16;
+  return total <= 227 * 1024 ? total : 0;
+}
+
 int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a_in.hd >= 1 && a_in.hd <= 128, "attention: head_dim %d not in 1..128", a_in.hd);
   SCV_REQUIRE(a_in.max_n >= 1, "attention: max_n must be positive");
@@ -388,6 +575,26 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
                  4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
   SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
+  const size_t bulk_smem = (v4 && tun().attn_bulk != 0 && a.B >= tun().attn_bulk_min_rows) ? cross_bulk_smem(a, warps) : 0;
+  if (bulk_smem != 0) {
+    static bool attr_dev[64] = {};
+    if (first_use_on_device(attr_dev)) {
+      SCV_CUDA(cudaFuncSetAttribute(attention_cross_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCV_CUDA(cudaFuncSetAttribute(attention_cross_bulk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCV_CUDA(cudaFuncSetAttribute(attention_cross_bulk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCV_CUDA(cudaFuncSetAttribute(attention_cross_bulk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    const int kv_floats = a.fixed_len * a.row_stride, q_floats = a.nhead * a.hd;
+    const int piece = tun().attn_bulk_piece_kb > 0 ? tun().attn_bulk_piece_kb * 1024 : kv_floats * 4;
+    const dim3 grid(std::min(a.B, sm_count())), block(warps * 32);
+    const int lanes = a.hd / 4;
+    if (lanes <= 4) SCV_CUDA(launch_k(attention_cross_bulk_kernel<4>, grid, block, bulk_smem, s, a, kv_floats, q_floats, piece));
+    else if (lanes <= 8) SCV_CUDA(launch_k(attention_cross_bulk_kernel<8>, grid, block, bulk_smem, s, a, kv_floats, q_floats, piece));
+    else if (lanes <= 16) SCV_CUDA(launch_k(attention_cross_bulk_kernel<16>, grid, block, bulk_smem, s, a, kv_floats, q_floats, piece));
+    else SCV_CUDA(launch_k(attention_cross_bulk_kernel<32>, grid, block, bulk_smem, s, a, kv_floats, q_floats, piece));
+    SCV_LAUNCH_CHECK();
+    return 0;
+  }
   if (v4) {
     const int lanes = a.hd / 4;
     if (lanes <= 4) SCV_CUDA(launch_k(attention_decode_v4_kernel<4>, dim3(blocks), dim3(warps * 32), smem, s, a));
@@ -758,6 +965,18 @@ int launch_step_end(StepState* st, int max_steps, cudaStream_t s) {
   return 0;
 }
 
+__global__ void host_gate_kernel(volatile int* flag) {
+  // bounded wait (50 ms): if the host ever blocked in a launch call while the gate is closed, the gate opens by itself
+  const unsigned long long t0 = globaltimer_ns();
+  while (*flag == 0 && globaltimer_ns() - t0 < 50000000ull) __nanosleep(200);
+}
+
+int launch_host_gate(int* host_flag, cudaStream_t s) {
+  host_gate_kernel<<<1, 1, 0, s>>>(host_flag);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B, StepState* st,
                                  unsigned long long seed, unsigned long long offset) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -767,6 +986,7 @@ __global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B
   }
   if (i == 0) {
     st->step = 0; st->done = 0; st->n_unfinished = B; st->out_len = 0; st->degenerate = 0; st->next_free_page = 0;
+    st->pad[0] = 0; st->pad[1] = 0;        // pad[0]: 1 + the last step at which a row emitted its END (decode_cluster.cu)
     st->seed = seed; st->offset = offset;
   }
 }

@@ -101,6 +101,8 @@ struct SamplerArgs {
 // which = 2: second kernel (entropy / temperature sampling / log-prob), only when sampling or entropy is requested
 int launch_sampler(const SamplerArgs& a, int which, cudaStream_t s);
 int launch_step_end(StepState* st, int max_steps, cudaStream_t s);
+// one thread that spins until *host_flag (pinned host memory) becomes non-zero: holds a stream while the host enqueues
+int launch_host_gate(int* host_flag, cudaStream_t s);
 // true when launch_sampler(a, 1, ...) is the warp-per-row greedy kernel and nothing else (no second sampler kernel)
 bool sampler_plain_greedy(const SamplerArgs& a);
 
@@ -114,6 +116,51 @@ struct SmallTail {
 };
 int launch_decode_small_persist(const SmallPhase* phases_dev, int n_phases, int B, unsigned* bar, int grid, const SmallTail& tail,
                                 cudaStream_t s);
+// ---- cluster-parallel small-batch decode (decode_cluster.cu): the batch's rows are dealt to thread-block clusters of
+// kClSize CTAs; a cluster runs the whole layer stack for its rows as a tensor-parallel group (every CTA streams 1 / kClSize
+// of every weight matrix with cp.async.bulk, activations are exchanged through distributed shared memory, phases are
+// separated by mbarrier-based CLUSTER barriers, never by a grid barrier).  The step is described by a host-built program.
+constexpr int kClSize = 8;                  // CTAs per cluster (portable maximum)
+constexpr int kClMaxRows = 4;               // rows per cluster
+enum ClBuf : int { CB_X = 0, CB_XN, CB_XN2, CB_A, CB_B, CB_H, CB_C, CB_D, CB_E, CB_Q, CB_K, CB_V, CB_COUNT };
+enum ClKind : int { CL_LN = 0, CL_GEMV, CL_ATTN_SELF, CL_ATTN_CROSS, CL_SYNC };
+enum ClOut : int { CO_LOCAL = 0, CO_GATHER, CO_GLOBAL };
+struct ClInstr {                             // 64 bytes: the whole program of a step sits in shared memory
+  int kind; int act;
+  union {
+    // CL_GEMV: out[r][n] = act(in[r] . w[n] + bias[n]) (+ x[r][n]);  split = 1: CTA `rank` computes columns
+    // [rank * N / kClSize, ...), 0: rank 0 computes all N;  CO_LOCAL: out_buf[r][n - n0], CO_GATHER: out_buf[r][n] in EVERY
+    // CTA of the cluster, CO_GLOBAL: out_global[row * out_ld + n]
+    struct { const __nv_bfloat16* w; const float* bias; float* out_global; int ldw, K, N, out_ld;
+             short split, in_buf, residual, out_kind, out_buf, pad0, pad1, pad2; } g;
+    // CL_LN: dst = LayerNorm(src) * gamma + beta over n columns (every CTA normalises its own copy of the rows)
+    struct { const float* gamma; const float* beta; int src_buf, dst_buf, n; } ln;
+    // CL_ATTN_*: K / V of this layer (paged self-attention cache, or the projected memory tokens)
+    struct { float* kcache; float* vcache; long long page_stride; long long seq_stride; int row_stride, fixed_len; } at;
+  };
+};
+static_assert(sizeof(ClInstr) == 64, "ClInstr is copied into shared memory as 64-byte records");
+struct ClProgram {
+  const ClInstr* instr; int n_instr;         // device array
+  int B, d, nhead, hd, dff, V, pe_len;
+  int rows_per_cluster;                      // R: 1, 2 or 4
+  int cpl;                                   // 16-byte weight chunks per lane and K segment: 2 (segments <= 512 wide) or 3 (<= 768)
+  int buf_off[CB_COUNT]; int buf_ld[CB_COUNT]; int buf_floats;     // shared-memory layout of the activation buffers (floats)
+  const int* page_table; int pages_per_seq;
+  float scale;
+  float* x_global;                           // [B, d] residual stream: read at kernel entry (step mode / first step), written back
+  StepState* st;
+  int exp;                                   // SCV_CLUSTER_EXP (timing experiments, wrong results): 1 stream only, 2 no epilogue
+  unsigned long long* dbg;                   // SCV_CLUSTER_DEBUG: per-instruction nanoseconds of cluster 0 / rank 0 / thread 0
+};
+size_t cluster_smem_bytes(const ClProgram& p);
+int cluster_max_active(int rows_per_cluster, size_t smem);      // clusters of the kernel that can be resident at once
+// true when the decoder shape can run on the cluster kernel (head / column counts divisible by the cluster size, ...)
+bool cluster_shape_ok(int d, int nhead, int dff, int V, int pe_len, int n_memory);
+// one decode step (sampling calls: the sampler kernels follow) / the whole plain-greedy decode in one launch
+int launch_decode_cluster_step(const ClProgram& p, cudaStream_t s);
+int launch_decode_cluster_persist(const ClProgram& p, const SmallTail& tail, cudaStream_t s);
+
 int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
                      unsigned long long offset, cudaStream_t s);
 

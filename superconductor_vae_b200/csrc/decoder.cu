@@ -2,6 +2,8 @@
 // Reference: src/superconductor/models/autoregressive_decoder.py:544-899 (module + memory),
 // :1175-1557 (KV-cache decode).  See DESIGN.md for the data layout and the kernel list.
 #include <cmath>
+#include <cstring>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -94,6 +96,11 @@ struct scv_decoder {
   DevBuf sm_part;                          // per-CTA partial sums of the fused feed-forward block
   int sm_n_phases = 0, sm_grid = 0;
   bool small_active = false;               // this call decodes through the persistent small-batch kernel
+  // cluster-parallel small-batch decode (decode_cluster.cu)
+  DevBuf cl_instr, cl_dbg;
+  std::vector<int> cl_kinds;
+  ClProgram cl_prog{};
+  bool cl_active = false;
 
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
@@ -114,7 +121,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d, &fw_skip})
+                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d, &fw_skip, &cl_instr, &cl_dbg, &sm_part})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -222,7 +229,7 @@ int scv_decoder_create(const scv_decoder_config* cfg, scv_decoder** out) {
   scv_decoder* D = new scv_decoder();
   D->cfg = *cfg;
   int rc = dec_register(D);
-  if (rc == 0 && cudaMallocHost(reinterpret_cast<void**>(&D->pinned), 16 * sizeof(int)) != cudaSuccess) {
+  if (rc == 0 && cudaMallocHost(reinterpret_cast<void**>(&D->pinned), 32 * sizeof(int)) != cudaSuccess) {
     set_error("cudaMallocHost failed");
     rc = 2;
   }
@@ -513,6 +520,116 @@ static int build_small_phases(scv_decoder* D, const scv_generate_args* A, int B,
   return 0;
 }
 
+// Program of the cluster-parallel small-batch step (decode_cluster.cu): the same operations as decode_rows() below, every
+// projection split by output columns over the 8 CTAs of a cluster, activations exchanged through distributed shared memory.
+static int build_cluster_program(scv_decoder* D, const scv_generate_args* A, int B, int M) {
+  const scv_decoder_config& c = D->cfg;
+  D->cl_active = false;
+  const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward, V = c.vocab_size, pps = ceil_div(c.pe_len, kPagePos);
+  if (tun().cluster == 0 || B > tun().cluster_max_rows || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
+  if (!cluster_shape_ok(d, c.nhead, dff, V, c.pe_len, M)) return 0;
+  // Clusters that can be resident at once (8 CTAs of ~200 KB each inside one GPC: 15-16 on a B200); all of a decode's
+  // clusters should run together (a late cluster is still decoded correctly, just later), so R is the smallest rows-per-
+  // cluster count that fits the batch into them.
+  static int max_clusters = 0;
+  if (max_clusters == 0) max_clusters = std::max(1, cluster_max_active(4, 215 * 1024));
+  int R = tun().cluster_rows;
+  if (R != 1 && R != 2 && R != 4) R = B <= max_clusters ? 1 : (B <= 2 * max_clusters ? 2 : 4);
+  if (ceil_div(B, R) > max_clusters) return 0;
+  ClProgram& P = D->cl_prog;
+  P = ClProgram{};
+  P.B = B; P.d = d; P.nhead = c.nhead; P.hd = hd; P.dff = dff; P.V = V; P.pe_len = c.pe_len; P.rows_per_cluster = R;
+  {
+    auto seg = [](int K) { return K <= 768 ? K : K / 4; };               // KSEG_MAX of decode_cluster.cu
+    P.cpl = std::max(seg(d), std::max(seg(dff), seg(d / 4))) <= 512 ? 2 : 3;
+  }
+  const int hpc = c.nhead / kClSize;
+  const int widths[CB_COUNT] = {d, d, d, d, d, dff, d / 4, d / 4, d / 4, hd * hpc, hd * hpc, hd * hpc};
+  int off = 0;
+  for (int b = 0; b < CB_COUNT; ++b) { P.buf_off[b] = off; P.buf_ld[b] = round_up(widths[b], 4); off += R * P.buf_ld[b]; }
+  P.buf_floats = off;
+  P.page_table = D->ptab.as<int>(); P.pages_per_seq = pps;
+  P.scale = (float)(1.0 / std::sqrt((double)hd));
+  P.x_global = D->x.as<float>();
+  P.st = D->state.as<StepState>();
+  std::vector<ClInstr> prog;
+  auto blank = [](int kind) { ClInstr I; memset(&I, 0, sizeof(I)); I.kind = kind; return I; };
+  auto ln = [&](const LNp& p, int src, int dst) {
+    ClInstr I = blank(CL_LN); I.ln.gamma = p.g; I.ln.beta = p.b; I.ln.src_buf = src; I.ln.dst_buf = dst; I.ln.n = d; prog.push_back(I);
+  };
+  auto gemv = [&](const __nv_bfloat16* w, int ldw, int K, int N, const float* bias, int act, int in_buf, bool residual, int out_kind,
+                  int out_buf, float* out_global, int out_ld, bool split) {
+    ClInstr I = blank(CL_GEMV); I.act = act; I.g.w = w; I.g.ldw = ldw; I.g.K = K; I.g.N = N; I.g.split = split ? 1 : 0; I.g.bias = bias;
+    I.g.in_buf = (short)in_buf; I.g.residual = residual ? 1 : 0; I.g.out_kind = (short)out_kind; I.g.out_buf = (short)out_buf;
+    I.g.out_global = out_global; I.g.out_ld = out_ld;
+    prog.push_back(I);
+  };
+  auto lin = [&](const Lin& L, int act, int in_buf, bool residual, int out_kind, int out_buf) {
+    gemv(L.w, L.ldw, L.K, L.N, L.b, act, in_buf, residual, out_kind, out_buf, nullptr, 0, true);
+  };
+  auto sync = [&] { prog.push_back(blank(CL_SYNC)); };
+  const long long page_stride = (long long)c.num_layers * 2 * kPagePos * d;
+  for (int li = 0; li < c.num_layers; ++li) {
+    const DecLayer& L = D->layers[li];
+    ln(L.n1, CB_X, CB_XN);                                                                   // self attention (:1244-1296)
+    for (int part = 0; part < 3; ++part)
+      gemv(L.sa_in_w + (size_t)part * d * L.sa_in_ld, L.sa_in_ld, d, d, L.sa_in_b + part * d, ACT_NONE, CB_XN, false, CO_LOCAL,
+           CB_Q + part, nullptr, 0, true);
+    { ClInstr I = blank(CL_ATTN_SELF); I.at.kcache = D->kvpool.as<float>() + (size_t)(li * 2 + 0) * kPagePos * d;
+      I.at.vcache = D->kvpool.as<float>() + (size_t)(li * 2 + 1) * kPagePos * d; I.at.page_stride = page_stride; I.at.row_stride = d;
+      I.at.fixed_len = -1; prog.push_back(I); }
+    sync();
+    lin(L.sa_out, ACT_NONE, CB_A, true, CO_GATHER, CB_X);
+    sync();
+    ln(L.n2, CB_X, CB_XN);                                                                   // cross attention (:1299-1308)
+    gemv(L.ca_in_w, L.ca_in_ld, d, d, L.ca_in_b, ACT_NONE, CB_XN, false, CO_LOCAL, CB_Q, nullptr, 0, true);
+    { ClInstr I = blank(CL_ATTN_CROSS); float* ckv = D->ckv.as<float>() + (size_t)li * B * M * 2 * d;
+      I.at.kcache = ckv; I.at.vcache = ckv + d; I.at.seq_stride = (long long)M * 2 * d; I.at.row_stride = 2 * d; I.at.fixed_len = M;
+      prog.push_back(I); }
+    sync();
+    lin(L.ca_out, ACT_NONE, CB_A, true, CO_GATHER, CB_X);
+    sync();
+    ln(L.n3, CB_X, CB_XN);                                                                   // feed forward (:1311-1313)
+    lin(L.ff1, ACT_GELU, CB_XN, false, CO_GATHER, CB_H);
+    sync();
+    lin(L.ff2, ACT_NONE, CB_H, true, CO_GATHER, CB_X);
+    sync();
+  }
+  const bool type = A->type_masks != nullptr, stop = A->stop_boost > 0.f, dup = A->site_dup_threshold > 0.f;
+  ln(D->out_ln, CB_X, CB_XN);                                                                // heads (:1413, 1417, 1439)
+  lin(D->out_a, ACT_GELU, CB_XN, false, CO_GATHER, CB_A);
+  if (type) { ln(D->tt_ln, CB_X, CB_XN2); lin(D->tt_a, ACT_GELU, CB_XN2, false, CO_GATHER, CB_B); }
+  if (stop) lin(D->stop_a, ACT_GELU, CB_X, false, CO_GATHER, CB_C);
+  if (dup) lin(D->dup_a, ACT_GELU, CB_X, false, CO_GATHER, CB_D);
+  sync();
+  gemv(D->out_b.w, D->out_b.ldw, d, V, D->out_b.b, ACT_NONE, CB_A, false, CO_GLOBAL, 0, D->logits.as<float>(), V, true);
+  if (type) lin(D->tt_b, ACT_GELU, CB_B, false, CO_GATHER, CB_E);
+  if (stop) gemv(D->stop_b.w, D->stop_b.ldw, d / 4, 1, D->stop_b.b, ACT_NONE, CB_C, false, CO_GLOBAL, 0, D->slog.as<float>(), 1, false);
+  if (dup) gemv(D->dup_b.w, D->dup_b.ldw, d / 4, 1, D->dup_b.b, ACT_NONE, CB_D, false, CO_GLOBAL, 0, D->dlog.as<float>(), 1, false);
+  if (type) {
+    sync();
+    gemv(D->tt_c.w, D->tt_c.ldw, d / 4, 5, D->tt_c.b, ACT_NONE, CB_E, false, CO_GLOBAL, 0, D->tlog.as<float>(), 8, false);
+  }
+  P.n_instr = (int)prog.size();
+  if (prog.size() > 320 || cluster_smem_bytes(P) > 227 * 1024) return 0;      // MAX_INSTR of decode_cluster.cu
+  SCV_TRY(D->cl_instr.ensure(1024 * sizeof(ClInstr)));      // fixed size: a captured step holds this pointer
+  // (pageable host memory: the copy is staged by the driver before the call returns)
+  SCV_CUDA(cudaMemcpyAsync(D->cl_instr.p, prog.data(), prog.size() * sizeof(ClInstr), cudaMemcpyHostToDevice, D->main));
+  P.instr = D->cl_instr.as<ClInstr>(); P.n_instr = (int)prog.size();
+  static const int exp_env = [] { const char* e = getenv("SCV_CLUSTER_EXP"); return e ? atoi(e) : 0; }();
+  P.exp = exp_env;
+  static const int dbg_env = [] { const char* e = getenv("SCV_CLUSTER_DEBUG"); return e ? atoi(e) : 0; }();
+  if (dbg_env) {
+    SCV_TRY(D->cl_dbg.ensure(1024 * sizeof(unsigned long long)));
+    SCV_CUDA(cudaMemsetAsync(D->cl_dbg.p, 0, 1024 * sizeof(unsigned long long), D->main));
+    P.dbg = D->cl_dbg.as<unsigned long long>();
+    D->cl_kinds.assign(prog.size(), 0);
+    for (size_t i = 0; i < prog.size(); ++i) D->cl_kinds[i] = prog[i].kind * 10000 + (prog[i].kind == CL_GEMV ? prog[i].g.K / 8 : 0);
+  }
+  D->cl_active = true;
+  return 0;
+}
+
 // One decode step for rows [r0, r0 + B) of the call's batch (a sub-batch; every buffer is row-major by batch row and
 // the SplitTile buffers are tiled by 128 rows, so a sub-batch is a pointer offset).  phase 1 = everything up to and
 // including the first sampler kernel, phase 2 = the second sampler kernel (sampling / entropy only).
@@ -578,6 +695,17 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
   e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
   SCV_TRY(launch_embed(e, s));
+  if (D->cl_active) {                      // cluster-parallel small-batch decode (decode_cluster.cu)
+    if (phase == 3) {                      // the whole plain-greedy decode in one launch
+      SCV_REQUIRE(sampler_plain_greedy(sp), "persistent decode: the call is not plain greedy");
+      SmallTail t;
+      t.sp = sp; t.emb = D->emb; t.ld_emb = D->ld_emb; t.pe = D->pe; t.d = d; t.x = x; t.page_table = page_table; t.pages_per_seq = pps;
+      t.max_steps = steps_max;
+      return launch_decode_cluster_persist(D->cl_prog, t, s);
+    }
+    SCV_TRY(launch_decode_cluster_step(D->cl_prog, s));
+    return launch_sampler(sp, 1, s);
+  }
   if (D->small_active && phase == 3) {     // the whole decode in one launch (plain greedy): step loop inside the kernel
     SCV_REQUIRE(sampler_plain_greedy(sp), "persistent decode: the call is not plain greedy");
     SCV_CUDA(cudaMemsetAsync(D->sm_bar.p, 0, 256 * sizeof(unsigned), s));
@@ -722,7 +850,8 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   if (A->want_log_probs) SCV_CUDA(cudaMemsetAsync(D->o_lp.p, 0, io * sizeof(float), s));
   if (A->want_entropy) SCV_CUDA(cudaMemsetAsync(D->o_ent.p, 0, io * sizeof(float), s));
   A = &G;
-  SCV_TRY(build_small_phases(D, A, B, M));
+  SCV_TRY(build_cluster_program(D, A, B, M));
+  if (D->cl_active) D->small_active = false; else SCV_TRY(build_small_phases(D, A, B, M));
   if (D->small_active)
     SCV_CUDA(cudaMemcpyAsync(D->sm_phases.p, D->sm_host.data(), D->sm_host.size() * sizeof(SmallPhase), cudaMemcpyHostToDevice, s));
   // per-layer K/V projection of the memory tokens, once per call instead of once per step and layer
@@ -745,8 +874,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   D->pinned[0] = D->pinned[1] = 0;
   bool used[2] = {false, false};
   // Profiling pass (bench.py roofline): the host waits for every step, so no step is enqueued after the batch has
-  // finished (no-op launches would be timed and their flops counted), and the step still replays as a graph whose
-  // event-record nodes time every kernel without host launch latency in between.
+  // finished (no-op launches would be timed and their flops counted); see the gate kernel in the step loop.
   const bool prof = prof_enabled();
   const bool sync_each = (A->flags & SCV_FLAG_SYNC_EVERY_STEP) != 0 || prof;
   if (prof) { SCV_CUDA(cudaStreamSynchronize(s)); SCV_TRY(prof_harvest()); }    // memory K/V projections above
@@ -795,7 +923,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // CUDA graph of one step: the launch sequence is identical for every step (position, done flag, RNG seed all live
   // in device memory), so step 0 runs eagerly and steps >= 1 replay one instantiated graph (one launch per step
   // instead of ~150-300); cached per call configuration.
-  const bool use_graph = tun().graph != 0 && (A->flags & SCV_FLAG_SYNC_EVERY_STEP) == 0 && steps_max >= 3;
+  const bool use_graph = tun().graph != 0 && !sync_each && steps_max >= 3;
   const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
                      A->forced_tokens != nullptr, prof ? 1 : 0, A->flags, A->temperature, A->top_p, A->stop_boost,
                      A->hard_stop_threshold, A->site_dup_threshold};
@@ -804,7 +932,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
     for (auto& g : D->graphs) if (g.key == key) exec = g.exec;
   // Small batches, plain greedy: the step loop runs inside one persistent kernel (decode_small.cu), no host polling.
   static const int persist_env = [] { const char* e = getenv("SCV_SMALL_PERSIST"); return e ? atoi(e) : 1; }();
-  const bool persist = D->small_active && persist_env != 0 && !two_phase && !sync_each && A->temperature < 0.01f &&
+  const bool persist = (D->small_active || D->cl_active) && persist_env != 0 && !two_phase && !sync_each && A->temperature < 0.01f &&
                        c.vocab_size % 4 == 0 && (reinterpret_cast<uintptr_t>(A->type_masks) & 3u) == 0;   // sampler_plain_greedy
   if (persist) SCV_TRY(decode_rows(D, A, steps_max, 0, 0, B, 3, s));
   for (int step = 0; step < steps_max && !persist; ++step) {
@@ -821,12 +949,23 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
         if (D->graphs.size() >= 8) D->drop_graphs();
         D->graphs.push_back({key, exec});
       }
-      if (prof) prof_mark_pending();
       SCV_CUDA(cudaGraphLaunch(exec, s));
       count_launch(D->launches_per_step);
     } else {
       const long long before = launch_total();
-      SCV_TRY(enqueue_step(step));
+      if (prof) {
+        // Hold the stream behind a gate kernel while the whole step (kernels + timing events) is enqueued, then open it:
+        // the device runs the step back to back, so no interval between two events contains host launch latency.
+        // (Events recorded inside a captured graph cannot be read with cudaEventElapsedTime, hence no graph here.)
+        volatile int* gate = D->pinned + 20;
+        *gate = 0;
+        SCV_TRY(launch_host_gate(D->pinned + 20, s));
+        const int rc = enqueue_step(step);
+        __atomic_store_n(D->pinned + 20, 1, __ATOMIC_RELEASE);
+        if (rc != 0) return rc;
+      } else {
+        SCV_TRY(enqueue_step(step));
+      }
       D->launches_per_step = (int)(launch_total() - before);
     }
     if (sync_each) {
@@ -859,6 +998,18 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   SCV_CUDA(cudaStreamSynchronize(s));
   const StepState* hs = reinterpret_cast<const StepState*>(&D->pinned[2]);
   *A_user->out_steps = hs->done ? hs->out_len : hs->step;
+  if (D->cl_active && D->cl_prog.dbg != nullptr) {       // SCV_CLUSTER_DEBUG: where one CTA's step time goes
+    std::vector<unsigned long long> h(D->cl_kinds.size());
+    SCV_CUDA(cudaMemcpy(h.data(), D->cl_prog.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const char* names[] = {"layernorm", "projection", "self-attention", "cross-attention", "cluster barrier"};
+    double tot[5] = {0, 0, 0, 0, 0}; int cnt[5] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < h.size(); ++i) { tot[D->cl_kinds[i] / 10000] += (double)h[i]; cnt[D->cl_kinds[i] / 10000] += 1; }
+    const int steps = std::max(1, (int)*A_user->out_steps);
+    for (int k = 0; k < 5; ++k)
+      fprintf(stderr, "cluster decode: %-16s %3d per step, %9.1f us per step in total (cluster 0, rank 0)\n", names[k], cnt[k], tot[k] / 1e3 / steps);
+    for (size_t i = 0; i < h.size() && i < 24; ++i)
+      fprintf(stderr, "  instr %2zu kind %d K/8 %4d: %8.2f us per step\n", i, D->cl_kinds[i] / 10000, D->cl_kinds[i] % 10000, (double)h[i] / 1e3 / steps);
+  }
   D->last_B = B;
   return 0;
 }

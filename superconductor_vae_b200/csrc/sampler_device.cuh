@@ -59,7 +59,10 @@ __device__ __forceinline__ float adjust_logit(const RowCtx& c, int v, float l, u
 
 __device__ __forceinline__ int commit_token(const SamplerArgs& a, int b, int step, int token, float logprob) {
   // single thread
-  if (a.forced != nullptr) token = (int)a.forced[(size_t)b * a.out_ld + step];
+  if (a.forced != nullptr) {               // teacher-forced replay; a negative entry leaves the position to the sampler
+    const long long f = a.forced[(size_t)b * a.out_ld + step];
+    if (f >= 0) token = (int)f;
+  }
   a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
   if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
   a.cur_tokens[b] = token;

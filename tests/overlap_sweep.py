@@ -34,7 +34,7 @@ elif mode == "full":          # no masks / stop head: all 63 steps run
 else:                         # RLOO-style sampling with log-probs and entropy
     kw = dict(temperature=1.2, max_len=64, stop_boost=10.0, return_log_probs=True, return_entropy=True, _seed=7)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, sub_min_rows=2048)
+defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, sub_min_rows=2048, attn_bulk=0, attn_bulk_min_rows=256, attn_bulk_piece_kb=0)
 first = None
 for spec in specs:
     cfg = dict(defaults)

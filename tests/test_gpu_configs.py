@@ -112,7 +112,8 @@ def test_config3_rloo_8192_rows_layout_and_logprob_replay():
     sel = torch.arange(0, B, B // 64)[:64]
     rows = (torch.arange(k).unsqueeze(1) * B + sel.unsqueeze(0)).reshape(-1)     # 256 rows across the 4 sample blocks
     rt, rlp, ren = DO.generate_with_kv_cache(sd, 8, z[rows], stoich_pred=st[rows], heads_pred={n: v[rows] for n, v in hp.items()},
-                                             return_log_probs=True, return_entropy=True, forced_tokens=t[rows], **kw)
+                                             return_log_probs=True, return_entropy=True, forced_tokens=t[rows],
+                                             stop_when_all_finished=False, **kw)      # the batch ran until ITS last row ended
     assert rt.shape[1] == L
     torch.testing.assert_close(lp[rows], rlp, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(en[rows], ren, rtol=1e-3, atol=1e-3)
@@ -208,7 +209,25 @@ def test_config4_pipeline_20_tokens_matches_oracle():
     assert t.shape[1] == 63
     stoich = enc.heads_from_latent(z)["stoich_pred"].cpu()
     rt, _, _ = DO.generate_with_kv_cache(sd, 8, z.cpu(), stoich_pred=stoich, temperature=0.001, max_len=64)
-    assert torch.equal(t.cpu(), rt), f"{int((t.cpu() != rt).any(dim=1).sum())} of {n} rows differ"
+    tc = t.cpu()
+    bad = (tc != rt).any(dim=1).nonzero().flatten().tolist()
+    # 63 steps x 1024 rows = 64,512 greedy decisions with no mask narrowing the vocabulary: a decision whose two best
+    # logits are closer than the engine's logit tolerance (2e-4 abs, test_last_step_internals_match_oracle) may fall the
+    # other way, after which the row follows its own prefix.  Allowed: at most 0.5 % of the rows, and every one of them
+    # must leave the oracle at such a near-tie (the oracle's margin at the first differing step is checked).
+    assert len(bad) <= n // 200, f"{len(bad)} of {n} rows differ"
+    for r in bad:
+        pos = int((tc[r] != rt[r]).nonzero()[0])
+        trace = {}
+        DO.generate_with_kv_cache(sd, 8, z[r:r + 1].cpu(), stoich_pred=stoich[r:r + 1], temperature=0.001, max_len=pos + 2,
+                                  trace=trace)
+        lg = trace["final_logits"][pos][0]
+        top = lg.topk(2)
+        assert int(top.indices[0]) == int(rt[r, pos]) and int(tc[r, pos]) == int(top.indices[1]), (r, pos, top)
+        margin = float(top.values[0] - top.values[1])
+        print(f"row {r} leaves the oracle at step {pos}: oracle margin between its two best logits {margin:.2e}")
+        assert margin < 2e-4, (r, pos, margin)
+    print(f"config 4 (20 tokens, 63 steps): {n - len(bad)} of {n} rows identical to the oracle")
 
 
 # ------------------------------------------------------------------------------------------ product multi-GPU API on NCCL

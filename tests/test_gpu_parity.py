@@ -517,6 +517,56 @@ def test_config2_4096_latents_properties(golden_dir):
     assert int((tc == 2).any(dim=1).sum()) >= 1 and int(fl.max()) <= tc.shape[1]
 
 
+# ------------------------------------------------------------------------------------------ run-time tunables
+@pytest.mark.parametrize("rows", [6, 17, 32])
+def test_cluster_parallel_small_batch_kernel_matches_default(rows):
+    """The opt-in cluster-parallel small-batch decode (csrc/decode_cluster.cu: rows dealt to 8-CTA clusters, weights streamed
+    with cp.async.bulk, activations exchanged through distributed shared memory) decodes the same tokens as the default
+    grid-barrier kernel: plain greedy with masks + stop head (whole decode in one launch), plain greedy over all 63 steps,
+    and a sampled rollout (one launch per step; log-probs within 1e-4)."""
+    sd = W.make_decoder_state_dict(W.C512, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    z = W.make_latents(rows, 2048, 99)
+    stoich, heads = W.make_conditioning(rows, 13, 99)
+    masks = OV.type_masks()
+    cases = (dict(temperature=0.001, max_len=64, type_masks=_cuda(masks), stop_boost=10.0, hard_stop_threshold=0.8),
+             dict(temperature=0.001, max_len=64),
+             dict(temperature=1.2, max_len=64, stop_boost=10.0, return_log_probs=True, _seed=5))
+    try:
+        for kw in cases:
+            _lib.tune(cluster=0)
+            t0, lp0, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+            _lib.tune(cluster=1)
+            t1, lp1, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+            assert t0.shape == t1.shape and torch.equal(t0, t1)
+            if lp0 is not None:
+                torch.testing.assert_close(lp0, lp1, rtol=1e-4, atol=1e-4)
+    finally:
+        _lib.tune(cluster=0)
+
+
+def test_tunables_never_change_tokens():
+    """scv_tune moves work between streams / grids only: the opt-in launch configurations (grid-stride attention grid,
+    forced GEMM pipeline depth, 1 / 3 sub-batch streams, bulk-copy staged cross-attention, no graph replay) decode the
+    same tokens as the default on 2304 rows of the config-2 workload."""
+    sd = W.make_decoder_state_dict(W.C512, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    B = 2304
+    z = W.make_latents(B, 2048, 1234)
+    stoich, heads = W.make_conditioning(B, 13, 1234)
+    kw = dict(temperature=0.001, max_len=64, type_masks=_cuda(OV.type_masks()), stop_boost=10.0, hard_stop_threshold=0.8)
+    defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, attn_bulk=0, attn_bulk_piece_kb=0)
+    base, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+    try:
+        for cfg in (dict(attn_ctas_per_sm=3, gemm_stages=2), dict(subbatches=1), dict(subbatches=3), dict(attn_bulk=1),
+                    dict(attn_bulk=1, attn_bulk_piece_kb=16), dict(graph=0)):
+            _lib.tune(**{**defaults, **cfg})
+            t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+            assert torch.equal(t, base), cfg
+    finally:
+        _lib.tune(**defaults)
+
+
 # ------------------------------------------------------------------------------------------ opt-in kernels
 @pytest.mark.gpu
 def test_optin_kernels_match_default_tokens():

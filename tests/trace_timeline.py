@@ -27,7 +27,7 @@ z = W.make_latents(rows, 2048, 1234).to(dev)
 st, hp = W.make_conditioning(rows, 13, 1234)
 st, hp = st.to(dev), {k: v.to(dev) for k, v in hp.items()}
 kw = dict(temperature=0.001, max_len=64, type_masks=masks, stop_boost=10.0, hard_stop_threshold=0.8)
-defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, sub_min_rows=2048)
+defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, sub_min_rows=2048, attn_bulk=0, attn_bulk_min_rows=256, attn_bulk_piece_kb=0)
 
 
 def union_time(t0, t1):
