@@ -145,20 +145,31 @@ def main():
         tt = torch.rand((N,), generator=g) * 0.9 + 0.05
         i1, i2, tt = i1[lo:hi].to(dev), i2[lo:hi].to(dev), tt[lo:hi].to(dev)
         chunk = 65536
+        bounds = [parallel.shard_bounds(N, world, r) for r in range(world)]
+        n_chunks = max((h - l + chunk - 1) // chunk for l, h in bounds)
         out = torch.zeros((hi - lo, 63), dtype=torch.int16, device=dev)
+        # the product's multi-GPU plumbing: every chunk's int16 token ids are all-gathered asynchronously (NCCL runs on its
+        # own stream), so the gather of chunk k overlaps the decode of chunk k + 1 (parallel.ChunkedGather)
+        cg = parallel.ChunkedGather(pad_to=63, dtype=torch.int16) if world > 1 else None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         L = 0
-        for c0 in range(0, hi - lo, chunk):
-            c1 = min(hi - lo, c0 + chunk)
-            z = latent.slerp_rows(anchors, i1[c0:c1], i2[c0:c1], tt[c0:c1])
-            toks = latent.decode_z_batch(enc, dec, z, temperature=0.001, type_masks=masks, max_len=64)
-            out[c0:c1, :toks.shape[1]] = toks.to(torch.int16)
-            L = max(L, toks.shape[1])
+        for k in range(n_chunks):
+            c0, c1 = min(hi - lo, k * chunk), min(hi - lo, (k + 1) * chunk)
+            if c1 > c0:
+                z = latent.slerp_rows(anchors, i1[c0:c1], i2[c0:c1], tt[c0:c1])
+                toks = latent.decode_z_batch(enc, dec, z, temperature=0.001, type_masks=masks, max_len=64)
+                out[c0:c1, :toks.shape[1]] = toks.to(torch.int16)
+                L = max(L, toks.shape[1])
+            if cg is not None:
+                cg.push(out[c0:c1], [max(0, min(h - l, (k + 1) * chunk) - min(h - l, k * chunk)) for l, h in bounds])
         if world > 1:
-            gathered = parallel.gather_rows(out[:, :L].contiguous(), N, 0)
+            gathered = cg.finish()
+            lmax = torch.tensor([L], device=dev)
+            dist.all_reduce(lmax, op=dist.ReduceOp.MAX)
+            gathered = gathered[:, :int(lmax)]
         else:
             gathered = out[:, :L]
         torch.cuda.synchronize()
@@ -180,7 +191,7 @@ def main():
             tok.decode_batch(gathered[:20000])
             dt_rows = (time.perf_counter() - t1) * (N / 20000.0)
             emit(({"config": 4, "what": "SLERP latents -> heads_from_latent -> greedy decode (masks + stop head), "
-                              "sharded over ranks, gather of int16 token ids", "latents": N, "n_gpus": world,
+                              "sharded over ranks, chunked asynchronous all-gather of int16 token ids (parallel.ChunkedGather)", "latents": N, "n_gpus": world,
                               "seconds": dt, "formulas_per_s": N / dt, "max_len_gathered": int(gathered.shape[1]),
                               "mean_formula_len": float(lens.float().mean()), "distinct_candidates": len(formulas),
                               "decode_unique_seconds": dt_unique, "decode_every_row_seconds_extrapolated": dt_rows,

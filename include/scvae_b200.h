@@ -191,6 +191,13 @@ int scv_slerp_rows(const float* anchors, int32_t dim, const int32_t* i1, const i
 int scv_tokens_canonical_hash(const int64_t* tokens, int64_t n_rows, int32_t row_len, int16_t* canonical,
                               uint64_t* hash, int32_t* length, void* stream);
 
+/* element_similarity (scripts/holdout/holdout_search.py:149-182) of every candidate x target pair: 0.5 * Jaccard of the
+ * element sets + 0.5 * sum over shared elements of min(normalised amounts).  comp_a [n_a, n_elements], comp_b
+ * [n_b, n_elements]: amounts per element column as parse_formula_elements (:109-125) returns them, a NEGATIVE value marks
+ * an element the formula does not contain; doubles like the reference's Python floats.  out [n_a, n_b]. */
+int scv_element_similarity(const double* comp_a, const double* comp_b, int32_t n_a, int32_t n_b, int32_t n_elements,
+                           double* out, void* stream);
+
 /* Token-level rollout reward (replaces compute_reward_gpu_native,
  * src/superconductor/losses/reward_gpu_native.py:448-722, called after every rollout at
  * scripts/train_v12_clean.py:2745-2752, 2829-2836, 2942-2950).  The struct carries the fields of GPURewardConfig

@@ -372,3 +372,25 @@ def first_end_lengths(tokens: torch.Tensor) -> torch.Tensor:
     is_end = tokens == END_IDX
     pos = torch.argmax(is_end.int(), dim=1) + 1
     return torch.where(is_end.any(dim=1), pos, torch.tensor(L))
+
+
+def scheduled_sampling_mask(batch: int, seq_len: int, ratio: float, positional: bool = False, decay: float = 0.5) -> torch.Tensor:
+    """The keep-ground-truth mask of the reference's scheduled sampling (:1037-1045), drawn from the CURRENT global CPU
+    generator exactly like the reference draws it (one torch.rand(B, L) call after the positions tensor is built)."""
+    if positional and ratio < 1.0:
+        pos = torch.arange(seq_len).float() / max(seq_len - 1, 1)
+        tf_pos = (ratio * (1.0 + decay * (1.0 - pos))).clamp(0.0, 1.0)
+        return torch.rand(batch, seq_len) < tf_pos.unsqueeze(0)
+    return torch.rand(batch, seq_len) < ratio
+
+
+def forward_scheduled_sampling(sd, nhead, z, target_tokens, use_gt_mask, encoder_skip=None, stoich_pred=None,
+                               cached_memory=None, heads_pred=None):
+    """EnhancedTransformerDecoder.forward with teacher_forcing_ratio < 1 (:987-1082): pass 1 on the ground truth, argmax,
+    mix with the ground truth where `use_gt_mask` [B, L] is False, pass 2 on START + the mixed tokens."""
+    memory = cached_memory if cached_memory is not None else build_memory(sd, z, encoder_skip, stoich_pred, heads_pred, nhead)
+    first = forward_teacher_forced(sd, nhead, z, target_tokens, cached_memory=memory)
+    mixed = torch.where(use_gt_mask, target_tokens[:, 1:], first[1])
+    mixed_inputs = torch.cat([target_tokens[:, :1], mixed[:, :-1]], dim=1)
+    # forward_teacher_forced drops the last column of what it is given: append a dummy one
+    return forward_teacher_forced(sd, nhead, z, torch.cat([mixed_inputs, mixed_inputs[:, -1:]], dim=1), cached_memory=memory)

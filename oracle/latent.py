@@ -31,3 +31,52 @@ def unique_formulas(tokens, decode):
         counts[seen[f]] += 1
     return order, inverse, counts
 
+
+
+# ---- candidate scoring (second half) ------------------------------------------------------------------
+_ELEMENT_PATTERN = r'([A-Z][a-z]?)(?:\((\d+)/(\d+)\)|\((\d+)\)|(\d+(?:\.\d+)?))?'
+
+
+def parse_formula_elements(formula: str) -> dict:
+    """{element: summed amount} of a formula string, restated from scripts/holdout/holdout_search.py:109-125 over
+    data/canonical_ordering.py:110-152 (CanonicalOrderer.parse_formula) and :87-96 (fraction_value): `El(p/q)` -> p / q,
+    `El(n)` and `Eln` / `El0.n` -> the number, a bare element -> 1; repeated elements add up; any exception (a zero
+    denominator) -> {}.  TEST INFRASTRUCTURE."""
+    import re
+    try:
+        out = {}
+        for m in re.finditer(_ELEMENT_PATTERN, formula):
+            el = m.group(1)
+            if not el:
+                continue
+            if m.group(2) and m.group(3):
+                val = int(m.group(2)) / int(m.group(3))
+            elif m.group(4):
+                val = int(m.group(4)) / 1
+            elif m.group(5):
+                try:
+                    val = float(m.group(5))
+                except ValueError:
+                    val = 1.0
+            else:
+                val = 1.0
+            out[el] = out.get(el, 0) + val
+        return out
+    except Exception:
+        return {}
+
+
+def element_similarity(formula_a: str, formula_b: str) -> float:
+    """0.5 * Jaccard(element sets) + 0.5 * sum over shared elements of min(normalised amounts)
+    (scripts/holdout/holdout_search.py:149-182)."""
+    pa, pb = parse_formula_elements(formula_a), parse_formula_elements(formula_b)
+    if not pa or not pb:
+        return 0.0
+    union, shared = set(pa) | set(pb), set(pa) & set(pb)
+    jaccard = len(shared) / len(union)
+    frac = 0.0
+    if shared:
+        ta, tb = sum(pa.values()), sum(pb.values())
+        for el in shared:
+            frac += min(pa[el] / max(ta, 1e-8), pb[el] / max(tb, 1e-8))
+    return 0.5 * jaccard + 0.5 * frac

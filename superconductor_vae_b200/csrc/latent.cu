@@ -129,3 +129,56 @@ extern "C" int scv_tokens_canonical_hash(const int64_t* tokens, int64_t n_rows, 
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Compositional similarity of candidate x target formulas (scripts/holdout/holdout_search.py:149-182):
+//   0.5 * |shared elements| / |all elements| + 0.5 * sum over shared elements of min(a_e / sum a, b_e / sum b).
+// Compositions arrive as dense rows over the batch's element columns, absent elements marked by a negative amount
+// (amounts parsed from a formula are never negative).  Doubles, like the reference's Python floats.  One CTA per
+// candidate row: the row and its total are staged in shared memory once, threads walk the targets.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128)
+element_similarity_kernel(const double* __restrict__ a, const double* __restrict__ b, int n_a, int n_b, int n_el,
+                          double* __restrict__ out) {
+  extern __shared__ double row_a[];
+  __shared__ double total_a;
+  __shared__ int present_a;
+  const int i = blockIdx.x;
+  if (threadIdx.x == 0) { total_a = 0.0; present_a = 0; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_el; e += blockDim.x) row_a[e] = a[(size_t)i * n_el + e];
+  __syncthreads();
+  if (threadIdx.x == 0) {                      // sequential, in column order: the same sum for every thread
+    double t = 0.0; int c = 0;
+    for (int e = 0; e < n_el; ++e) if (row_a[e] >= 0.0) { t += row_a[e]; ++c; }
+    total_a = t; present_a = c;
+  }
+  __syncthreads();
+  const double ta = fmax(total_a, 1e-8);
+  for (int j = threadIdx.x; j < n_b; j += blockDim.x) {
+    const double* rb = b + (size_t)j * n_el;
+    double tb = 0.0; int cb = 0;
+    for (int e = 0; e < n_el; ++e) if (rb[e] >= 0.0) { tb += rb[e]; ++cb; }
+    double sim = 0.0;
+    if (present_a > 0 && cb > 0) {
+      tb = fmax(tb, 1e-8);
+      int shared = 0; double frac = 0.0;
+      for (int e = 0; e < n_el; ++e)
+        if (row_a[e] >= 0.0 && rb[e] >= 0.0) { ++shared; frac += fmin(row_a[e] / ta, rb[e] / tb); }
+      sim = 0.5 * (double)shared / (double)(present_a + cb - shared) + 0.5 * frac;
+    }
+    out[(size_t)i * n_b + j] = sim;
+  }
+}
+}  // namespace
+
+extern "C" int scv_element_similarity(const double* comp_a, const double* comp_b, int32_t n_a, int32_t n_b, int32_t n_elements,
+                                      double* out, void* stream) {
+  SCV_REQUIRE(comp_a && comp_b && out && n_a > 0 && n_b > 0 && n_elements > 0, "element_similarity: bad arguments");
+  SCV_REQUIRE(n_elements <= 4096, "element_similarity: %d element columns (at most 4096)", n_elements);
+  element_similarity_kernel<<<n_a, 128, (size_t)n_elements * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+      comp_a, comp_b, n_a, n_b, n_elements, out);
+  SCV_LAUNCH_CHECK();
+  return 0;
+}

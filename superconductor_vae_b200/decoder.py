@@ -11,7 +11,8 @@ Mirrors the reference's public surface for the decode path
 The module holds ordinary fp32 ``nn.Parameter``s under the reference's names (so
 ``load_state_dict`` of a reference checkpoint works and an optimiser can keep updating them); before
 each engine call, parameters whose version changed are re-uploaded and rounded to bf16 once.
-The teacher-forced training ``forward`` is outside this engine's scope.
+``forward`` (teacher forcing and the two-pass scheduled sampling) runs on the engine as an
+inference pass; it builds no autograd graph.
 """
 from __future__ import annotations
 
@@ -74,6 +75,8 @@ class EnhancedTransformerDecoder(nn.Module):
         self.max_elements = max_elements
         self.memory_bottleneck_dim = memory_bottleneck_dim
         self.encoder_skip_dim = encoder_skip_dim
+        self.use_position_dependent_tf = use_position_dependent_tf      # scheduled sampling (:1037-1043)
+        self.tf_position_decay = tf_position_decay
 
         self.token_embedding = nn.Embedding(self.vocab_size, d_model, padding_idx=PAD_IDX)
         self.pos_encoding = _PositionalEncoding(d_model, max_len, dropout)
@@ -169,22 +172,25 @@ class EnhancedTransformerDecoder(nn.Module):
         return cls.from_state_dict(module.state_dict(), nhead=module.nhead, device=device)
 
     def forward(self, z, target_tokens, encoder_skip=None, teacher_forcing_ratio: float = 1.0, stoich_pred=None,
-                cached_memory=None, heads_pred=None):
-        """Teacher-forced forward with ``teacher_forcing_ratio = 1.0`` (reference :901-985), inference
-        only (no autograd graph): every position of every row in one engine pass.
+                cached_memory=None, heads_pred=None, *, _use_gt_mask: Optional[torch.Tensor] = None):
+        """Teacher-forced forward (reference :901-1082), inference only (no autograd graph): every position
+        of every row in one engine pass.
+
+        ``teacher_forcing_ratio >= 1``: the parallel pass on the ground-truth inputs (:947-985).
+        ``teacher_forcing_ratio < 1``: the reference's two-pass scheduled sampling (:987-1082): pass 1 on the ground truth,
+        its argmax tokens are mixed with the ground truth position by position (``rand < ratio`` keeps the ground truth;
+        with ``use_position_dependent_tf`` the ratio is scaled by ``1 + tf_position_decay * (1 - pos / (L - 1))``), pass 2
+        runs on START + the mixed tokens.  The mask is drawn with ``torch.rand`` on the module's device like the
+        reference does; tests inject it through ``_use_gt_mask`` ([B, L-1] bool) to compare with a CPU run.
 
         Returns ``(logits [B, L-1, V], generated [B, L-1], stop_logits [B, L-1], type_logits [B, L-1, 5],
-        site_dup_logits [B, L-1] or None when the checkpoint has no site_dup_head)``, like the reference.
-        Scheduled sampling (ratio < 1, the reference's two-pass scheme :987-1100) is not built."""
-        if teacher_forcing_ratio < 1.0:
-            raise NotImplementedError("scheduled sampling (teacher_forcing_ratio < 1) is outside the B200 engine "
-                                      "(SURVEY.md section 8f row 3 covers the parallel teacher-forced pass only)")
+        site_dup_logits [B, L-1] or None when the checkpoint has no site_dup_head)``, like the reference."""
         with torch.no_grad():
-            L = self._sync_engine()
+            self._sync_engine()
             memory = self._checked_memory(cached_memory) if cached_memory is not None else \
                 self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
             device = memory.device
-            B, M = memory.size(0), memory.size(1)
+            B = memory.size(0)
             tokens = target_tokens.to(device=device, dtype=torch.int64)
             if tokens.dim() != 2 or tokens.size(0) != B or tokens.size(1) < 2:
                 raise RuntimeError(f"target_tokens must be [{B}, seq_len >= 2], got {tuple(tokens.shape)}")
@@ -194,18 +200,43 @@ class EnhancedTransformerDecoder(nn.Module):
             if seq > self.pos_encoding.pe.shape[1]:
                 raise RuntimeError(f"The size of tensor a ({seq}) must match the size of tensor b "
                                    f"({self.pos_encoding.pe.shape[1]}) at non-singleton dimension 1")
-            tokens = tokens.contiguous()
-            logits = torch.empty((B, seq, self.vocab_size), dtype=torch.float32, device=device)
-            stop = torch.empty((B, seq), dtype=torch.float32, device=device)
-            typ = torch.empty((B, seq, N_TOKEN_TYPES), dtype=torch.float32, device=device)
-            has_dup = hasattr(self, "site_dup_head")
-            dup = torch.empty((B, seq), dtype=torch.float32, device=device) if has_dup else None
-            args = _lib.ForwardArgs(batch=B, seq_len=seq, n_memory=M, memory=_lib.ptr(memory), tokens=_lib.ptr(tokens),
-                                    ld_tokens=tokens.size(1), out_logits=_lib.ptr(logits), out_stop=_lib.ptr(stop),
-                                    out_type=_lib.ptr(typ), out_dup=_lib.ptr(dup) if has_dup else None)
-            with torch.cuda.device(device):
-                _lib.check(L.scv_decoder_forward(self._engine, C.byref(args), _lib.current_stream()), "forward")
+            inputs = tokens[:, :-1].contiguous()
+            if teacher_forcing_ratio >= 1.0:
+                logits, stop, typ, dup = self._forward_pass(memory, inputs)
+                return logits, logits.argmax(dim=-1), stop, typ, dup
+            first_logits, _, _, _ = self._forward_pass(memory, inputs, heads=False)             # pass 1 (:1012-1031)
+            predicted = first_logits.argmax(dim=-1)
+            if _use_gt_mask is not None:
+                use_gt = _use_gt_mask.to(device=device, dtype=torch.bool)
+                if tuple(use_gt.shape) != (B, seq):
+                    raise RuntimeError(f"_use_gt_mask must be [{B}, {seq}], got {tuple(use_gt.shape)}")
+            elif self.use_position_dependent_tf:                                               # (:1037-1043)
+                pos = torch.arange(seq, device=device).float() / max(seq - 1, 1)
+                tf_pos = (teacher_forcing_ratio * (1.0 + self.tf_position_decay * (1.0 - pos))).clamp(0.0, 1.0)
+                use_gt = torch.rand(B, seq, device=device) < tf_pos.unsqueeze(0)
+            else:
+                use_gt = torch.rand(B, seq, device=device) < teacher_forcing_ratio              # (:1045)
+            mixed = torch.where(use_gt, tokens[:, 1:], predicted)                               # (:1051)
+            mixed_inputs = torch.cat([tokens[:, :1], mixed[:, :-1]], dim=1).contiguous()        # (:1056)
+            logits, stop, typ, dup = self._forward_pass(memory, mixed_inputs)                   # pass 2 (:1058-1082)
             return logits, logits.argmax(dim=-1), stop, typ, dup
+
+    def _forward_pass(self, memory: torch.Tensor, inputs: torch.Tensor, heads: bool = True):
+        """One parallel pass of the layer stack over ``inputs`` [B, L] (PAD inputs are masked as keys, :952)."""
+        L = _lib.lib()
+        device = memory.device
+        B, M, seq = memory.size(0), memory.size(1), inputs.size(1)
+        logits = torch.empty((B, seq, self.vocab_size), dtype=torch.float32, device=device)
+        stop = torch.empty((B, seq), dtype=torch.float32, device=device) if heads else None
+        typ = torch.empty((B, seq, N_TOKEN_TYPES), dtype=torch.float32, device=device) if heads else None
+        has_dup = heads and hasattr(self, "site_dup_head")
+        dup = torch.empty((B, seq), dtype=torch.float32, device=device) if has_dup else None
+        args = _lib.ForwardArgs(batch=B, seq_len=seq, n_memory=M, memory=_lib.ptr(memory), tokens=_lib.ptr(inputs),
+                                ld_tokens=inputs.size(1), out_logits=_lib.ptr(logits), out_stop=_lib.ptr(stop),
+                                out_type=_lib.ptr(typ), out_dup=_lib.ptr(dup))
+        with torch.cuda.device(device):
+            _lib.check(L.scv_decoder_forward(self._engine, C.byref(args), _lib.current_stream()), "forward")
+        return logits, stop, typ, dup
 
     # ------------------------------------------------------------------ engine plumbing
     def _config(self) -> _lib.DecoderConfig:

@@ -6,6 +6,7 @@ and the V14.3-complete variant in notebooks/generative_evaluation.ipynb cells 12
 """
 from __future__ import annotations
 
+import re
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -98,3 +99,69 @@ def decode_unique(tokenizer, tokens: torch.Tensor):
     uniq, inverse, counts, _ = unique_sequences(tokens)
     return tokenizer.decode_batch(uniq.to(torch.int64)), inverse, counts
 
+
+
+# ------------------------------------------------------------------ candidate scoring (second half)
+_ELEMENT_PATTERN = re.compile(r'([A-Z][a-z]?)(?:\((\d+)/(\d+)\)|\((\d+)\)|(\d+(?:\.\d+)?))?')
+
+
+def parse_formula_elements(formula: str) -> Dict[str, float]:
+    """{element: summed amount} of a formula string, same result as the reference's parse_formula_elements
+    (scripts/holdout/holdout_search.py:109-125): `El(p/q)` -> p / q, `El(n)`, `Eln`, `El0.n` -> the number, a bare element
+    -> 1, repeated elements add up, anything that makes the reference's parser raise (a zero denominator) -> {}."""
+    out: Dict[str, float] = {}
+    for m in _ELEMENT_PATTERN.finditer(formula):
+        el, num, den, par, plain = m.groups()
+        if num and den:
+            if int(den) == 0:
+                return {}
+            val = int(num) / int(den)
+        elif par:
+            val = float(int(par))
+        elif plain:
+            val = float(plain)
+        else:
+            val = 1.0
+        out[el] = out.get(el, 0) + val
+    return out
+
+
+def composition_matrix(formulas: List[str], elements: Optional[List[str]] = None):
+    """(float64 [N, E] host tensor, element column names): parsed amounts per formula, -1 where the formula does not
+    contain the element (the layout scv_element_similarity takes)."""
+    parsed = [parse_formula_elements(f) for f in formulas]
+    if elements is None:
+        elements = sorted({e for p in parsed for e in p})
+    col = {e: i for i, e in enumerate(elements)}
+    m = torch.full((len(formulas), max(len(elements), 1)), -1.0, dtype=torch.float64)
+    for r, p in enumerate(parsed):
+        for e, v in p.items():
+            m[r, col[e]] = v
+    return m, elements
+
+
+@torch.no_grad()
+def element_similarity_matrix(candidates: List[str], targets: List[str], device="cuda") -> torch.Tensor:
+    """similarity[i, j] = element_similarity(candidates[i], targets[j]) for every pair, on the device (one kernel): the
+    holdout search scores each of its ~31,000 candidates per target against the target formula
+    (scripts/holdout/holdout_search.py:149-182 inside the candidate loops); float64 [len(candidates), len(targets)]."""
+    L = _lib.lib()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.EngineError("element_similarity_matrix runs on a CUDA device (sm_100a); this package has no CPU fallback")
+    if not candidates or not targets:
+        return torch.zeros((len(candidates), len(targets)), dtype=torch.float64, device=dev)
+    parsed_elements = sorted({e for f in list(candidates) + list(targets) for e in parse_formula_elements(f)})
+    a, _ = composition_matrix(candidates, parsed_elements)
+    b, _ = composition_matrix(targets, parsed_elements)
+    a, b = a.to(dev).contiguous(), b.to(dev).contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.scv_element_similarity(_lib.ptr(a), _lib.ptr(b), a.shape[0], b.shape[0], a.shape[1], _lib.ptr(out),
+                                            _lib.current_stream()), "element_similarity")
+    return out
+
+
+def element_similarity(formula_a: str, formula_b: str, device="cuda") -> float:
+    """The reference's scalar function (same name and arguments) through the device kernel."""
+    return float(element_similarity_matrix([formula_a], [formula_b], device)[0, 0])

@@ -64,7 +64,7 @@ def test_no_cpu_fallback():
         m.generate_with_kv_cache(W.make_latents(2, W.TINY.latent_dim), temperature=0.001)
     with pytest.raises(S.EngineError):                       # teacher-forced forward: engine only, no CPU path either
         m(torch.zeros(1, W.TINY.latent_dim), torch.zeros(1, 4, dtype=torch.long))
-    with pytest.raises(NotImplementedError):                 # scheduled sampling is not built
+    with pytest.raises(S.EngineError):                       # ... nor has the scheduled-sampling (two-pass) forward
         m(torch.zeros(1, W.TINY.latent_dim), torch.zeros(1, 4, dtype=torch.long), teacher_forcing_ratio=0.5)
     names = list(inspect.signature(S.EnhancedTransformerDecoder.forward).parameters)[1:8]
     assert names == ["z", "target_tokens", "encoder_skip", "teacher_forcing_ratio", "stoich_pred", "cached_memory", "heads_pred"]

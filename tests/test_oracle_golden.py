@@ -234,3 +234,44 @@ def test_oracle_matches_the_live_reference_module():
     assert torch.equal(rt, ot) and torch.equal(rmk, omk)
     torch.testing.assert_close(olp, rlp, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(oen, ren, rtol=1e-4, atol=1e-5)
+
+
+def test_formula_parsing_and_similarity_match_reference(golden_dir):
+    """parse_formula_elements / element_similarity of the oracle and of the product's host parser against
+    the outputs of the reference functions (tests/golden/make_golden_similarity.py: 37 formulas incl. fractions,
+    decimals, repeated elements, isotope-like garbage, a zero denominator, empty strings)."""
+    from superconductor_vae_b200 import latent as PL
+    g = torch.load(os.path.join(golden_dir, "similarity.pt"), weights_only=False)
+    F = g["formulas"]
+    for f, p in zip(F, g["parsed"]):
+        assert OL.parse_formula_elements(f) == p, f
+        assert PL.parse_formula_elements(f) == p, f
+    for i, a in enumerate(F):
+        for j, b in enumerate(F):
+            assert abs(OL.element_similarity(a, b) - float(g["similarity"][i, j])) < 1e-15, (a, b)
+    m, cols = PL.composition_matrix(F)
+    assert m.shape == (len(F), len(cols)) and float(m[F.index("MgB2"), cols.index("B")]) == 2.0
+    assert float(m[F.index("MgB2"), cols.index("Cu")]) == -1.0
+
+
+@pytest.mark.parametrize("name,shape", [("tiny", W.TINY), ("c512", W.C512)])
+def test_scheduled_sampling_oracle_matches_reference(golden_dir, name, shape):
+    """forward with teacher_forcing_ratio < 1 (reference :987-1082, two passes): the oracle against the reference's own
+    outputs, the keep-ground-truth mask reproduced from the reference's seed."""
+    g = torch.load(os.path.join(golden_dir, "forward_ss.pt"), weights_only=False)[name]
+    base = torch.load(os.path.join(golden_dir, "forward_tf.pt"), weights_only=False)[name]
+    sd = W.make_decoder_state_dict(shape, 0)
+    for c in g:
+        B = c["B"]
+        tgt = base["target_tokens"][:B]
+        z = W.make_latents(base["B"], shape.latent_dim, base["seed_in"])[:B]
+        stoich, heads = W.make_conditioning(base["B"], shape.stoich_input_dim, base["seed_in"])
+        stoich, heads = stoich[:B], {k: v[:B] for k, v in heads.items()}
+        torch.manual_seed(c["seed"])
+        mask = DO.scheduled_sampling_mask(B, tgt.shape[1] - 1, c["ratio"], c["positional"], c["decay"])
+        logits, gen, stop, typ, dup = DO.forward_scheduled_sampling(sd, shape.nhead, z, tgt, mask, stoich_pred=stoich, heads_pred=heads)
+        torch.testing.assert_close(logits, c["logits"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(stop, c["stop_logits"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(typ, c["type_logits"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(dup, c["site_dup_logits"], rtol=1e-4, atol=2e-5)
+        assert torch.equal(gen.to(torch.int16), c["generated"])
