@@ -86,6 +86,9 @@ int scv_decoder_build_memory(scv_decoder* dec, int32_t batch, const float* z, co
 
 #define SCV_FLAG_H2_UNIFORM_FALLBACK 1u /* reproduce :1464-1466/:1512-1513 (batch-global degenerate guard) */
 #define SCV_FLAG_SYNC_EVERY_STEP 2u     /* debugging: synchronise after every step */
+#define SCV_FLAG_COMPACT_FINISHED 4u    /* opt-in: rows that have emitted END are retired (the reference keeps decoding them until
+                                           every row has finished, :1541-1548): outputs are identical up to and including
+                                           each row's first END - what every caller consumes - and PAD / 0 after it */
 
 /* generate_with_kv_cache (models/autoregressive_decoder.py:1321-1557). */
 typedef struct scv_generate_args {

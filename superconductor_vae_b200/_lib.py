@@ -94,6 +94,7 @@ class EncoderHeadsOut(C.Structure):
 
 FLAG_H2_UNIFORM_FALLBACK = 1
 FLAG_SYNC_EVERY_STEP = 2
+FLAG_COMPACT_FINISHED = 4
 
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test walks
 SIGNATURES = {

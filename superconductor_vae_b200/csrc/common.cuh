@@ -243,7 +243,10 @@ struct LinearArgs {
   void* y_split = nullptr;                         // write the output in SplitTile form instead of fp32 rows
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
-  const int* done_flag = nullptr;                  // device flag: skip the work when *done_flag != 0
+  const int* done_flag = nullptr;                  // &StepState::done: skip the work when it is set; with compaction of
+                                                   // finished rows (done_flag[6] = StepState::pad[1] > 0) row tiles at or
+                                                   // beyond that many rows are skipped as well
+  int row_base = 0;                                // first row of this launch inside the call's batch (sub-batches)
   const void* next_w = nullptr; size_t next_w_bytes = 0;   // tiled weights of the NEXT projection: prefetched into L2
   // LayerNorm(y) written as a SplitTile by the same kernel (gemm_tcgen05_ln.cu; callers check tc_res_ln_ok first)
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr; void* ln_out_split = nullptr;

@@ -21,8 +21,13 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
   pdl_launch_dependents();
   const int b = blockIdx.x;
   const int step = a.st->step;
+  int ob = b;
+  if (a.row_map != nullptr) {                 // finished rows are compacted away: slot -> row
+    if (a.slot_base + b >= a.st->pad[1]) return;
+    ob = a.row_map[a.slot_base + b];
+  }
   if (threadIdx.x == 0 && (step & (kPagePos - 1)) == 0) {
-    a.page_table[b * a.pages_per_seq + (step >> kPageShift)] = atomicAdd(&a.st->next_free_page, 1);
+    a.page_table[ob * a.pages_per_seq + (step >> kPageShift)] = atomicAdd(&a.st->next_free_page, 1);
   }
   const int tok = a.cur_tokens[b];
   const __nv_bfloat16* row = a.table + (size_t)tok * a.ld_table;
@@ -225,14 +230,16 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   for (int gw = blockIdx.x * wpb + warp_in_block; gw < n_items; gw += gridDim.x * wpb) {
   const int b = gw / a.nhead, h = gw % a.nhead;
   const int hd = a.hd;
-  const int sb = a.rows_per_seq > 0 ? b / a.rows_per_seq : b;          // sequence whose K / V this query row attends to
+  if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) continue;       // slot of a finished row (compaction)
+  // sequence whose K / V this query row attends to
+  const int sb = a.row_map != nullptr ? a.row_map[a.slot_base + b] : (a.rows_per_seq > 0 ? b / a.rows_per_seq : b);
   const int n = a.fixed_len >= 0 ? a.fixed_len : (a.rows_per_seq > 0 ? b - sb * a.rows_per_seq + 1 : a.st->step + 1);
   float* sc = sc_all + (size_t)warp_in_block * a.max_n;
   const int grp = lane / LPP, e0 = 4 * (lane % LPP);
   const bool e_ok = e0 < hd;
 
   const bool paged = a.page_table != nullptr;
-  const int* pt = paged ? a.page_table + (size_t)b * a.pages_per_seq : nullptr;
+  const int* pt = paged ? a.page_table + (size_t)(a.row_map != nullptr ? sb : b) * a.pages_per_seq : nullptr;
   auto row_off = [&](int p) -> size_t {
     if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
     return (size_t)sb * a.seq_stride + (size_t)p * a.row_stride + h * hd;
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(256, 1) attention_cross_bulk_kernel(AttnArgs a
 
 // bytes of dynamic shared memory of the bulk kernel, or 0 when the shape does not fit two stages
 static size_t cross_bulk_smem(const AttnArgs& a, int warps) {
-  if (a.fixed_len < 0 || a.page_table != nullptr || a.rows_per_seq != 0 || a.key_skip != nullptr) return 0;
+  if (a.fixed_len < 0 || a.page_table != nullptr || a.rows_per_seq != 0 || a.key_skip != nullptr || a.row_map != nullptr) return 0;
   const size_t kv = (size_t)a.fixed_len * a.row_stride * sizeof(float), q = (size_t)a.nhead * a.hd * sizeof(float);
   if (a.seq_stride != (long long)a.fixed_len * a.row_stride) return 0;                  // one contiguous block per sequence
   if (a.vcache - a.kcache <= 0 || a.vcache - a.kcache >= a.row_stride) return 0;        // V inside the token's row
@@ -575,6 +582,7 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
                  4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
   SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
+  SCV_REQUIRE(a.row_map == nullptr || v4, "attention: compaction of finished rows needs head_dim %% 4 == 0 and 16-byte aligned rows");
   const size_t bulk_smem = (v4 && tun().attn_bulk != 0 && a.B >= tun().attn_bulk_min_rows) ? cross_bulk_smem(a, warps) : 0;
   if (bulk_smem != 0) {
     static bool attr_dev[64] = {};
@@ -693,6 +701,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
   if (a.st->done) return;
   pdl_launch_dependents();
   const int b = blockIdx.x, step = a.st->step;
+  if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) return;
   const int bad = stage_logits(a, b, step, sl);
   const int row_bad = __syncthreads_or(bad & 1);
   // test before the atomic: with a type mask every row is "bad" and they would all serialise on this one word
@@ -714,6 +723,7 @@ __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
   if (a.st->done) return;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= a.B) return;
+  if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) return;
   const int step = a.st->step;
   const int tok = greedy_row_token(a, b, step, lane);
   if (threadIdx.x == 0) pdl_launch_dependents();
@@ -733,6 +743,8 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
   if (a.st->done) return;
   pdl_launch_dependents();
   const int b = blockIdx.x, step = a.st->step, V = a.V, tid = threadIdx.x;
+  if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) return;
+  const int ob = orig_row(a, b);
   const int bad = stage_logits(a, b, step, sl);
   const int row_real_bad = __syncthreads_or(bad & 2);
   const bool degenerate = (a.flags & 1u) ? (a.st->degenerate != 0) : (row_real_bad != 0);
@@ -755,7 +767,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
       }
       H = -block_sum(h, redv);
     }
-    if (tid == 0) a.out_entropy[(size_t)b * a.out_ld + step] = H;
+    if (tid == 0) a.out_entropy[(size_t)ob * a.out_ld + step] = H;
   }
   if (a.temperature != 1.0f) {
     __syncthreads();
@@ -829,7 +841,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
     }
   }
   // probs = softmax(logits) (:1511); uniform when degenerate (:1512-1513)
-  const float u = Philox::uniform(a.st->seed, a.st->offset, (uint32_t)(b + a.row_base), (uint32_t)step);
+  const float u = Philox::uniform(a.st->seed, a.st->offset, (uint32_t)(a.row_map != nullptr ? ob : b + a.row_base), (uint32_t)step);
   if (degenerate) {
     if (tid == 0) {
       int tok = min((int)(u * (float)V), V - 1);
@@ -903,7 +915,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase2_kernel(Sampler
       for (int i = 0; i < kSamplerThreads / 32; ++i) tok = max(tok, redi[i]);
     }
     if (a.forced != nullptr) {           // teacher-forced replay; a negative entry leaves that position sampled
-      const long long f = a.forced[(size_t)b * a.out_ld + step];
+      const long long f = a.forced[(size_t)ob * a.out_ld + step];
       if (f >= 0) tok = (int)f;
     }
     const float p = sl[tok] / total;
@@ -978,22 +990,72 @@ int launch_host_gate(int* host_flag, cudaStream_t s) {
 }
 
 __global__ void init_rows_kernel(int* cur_tokens, unsigned char* finished, int B, StepState* st,
-                                 unsigned long long seed, unsigned long long offset) {
+                                 unsigned long long seed, unsigned long long offset, int* row_map) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     cur_tokens[i] = kStartIdx;     // (:1392)
     finished[i] = 0;
+    if (row_map != nullptr) row_map[i] = i;
   }
   if (i == 0) {
     st->step = 0; st->done = 0; st->n_unfinished = B; st->out_len = 0; st->degenerate = 0; st->next_free_page = 0;
-    st->pad[0] = 0; st->pad[1] = 0;        // pad[0]: 1 + the last step at which a row emitted its END (decode_cluster.cu)
+    st->pad[0] = 0;                        // 1 + the last step at which a row emitted its END (decode_cluster.cu)
+    st->pad[1] = row_map != nullptr ? B : 0;   // rows still being decoded (compaction of finished rows), 0 = off
     st->seed = seed; st->offset = offset;
   }
 }
 
+// Opt-in retirement of finished rows: after the sampler, the slots whose row has not emitted END move to the front (stable),
+// so the next step's projections / attention / sampler run on st->pad[1] rows only.  One CTA, <= 16 slots per thread.
+__global__ void __launch_bounds__(1024) compact_rows_kernel(int* row_map, int* cur_tokens, const unsigned char* finished,
+                                                            StepState* st, int B) {
+  __shared__ int warp_tot[32];
+  __shared__ int total;
+  pdl_wait();
+  if (st->done) return;
+  const int n = st->pad[1], tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int PER = 16;                       // B <= 16384
+  int rows[PER], toks[PER];
+  int keep = 0;
+  const int s0 = tid * PER;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int sl = s0 + j;
+    rows[j] = -1;
+    if (sl < n) {
+      const int r = row_map[sl];
+      if (finished[r] == 0) { rows[keep] = r; toks[keep] = cur_tokens[sl]; ++keep; }
+    }
+  }
+  int incl = keep;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();                              // every slot has been read before any is overwritten
+  if (w == 0) {
+    int v = warp_tot[lane], in2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, in2, o); if (lane >= o) in2 += t; }
+    warp_tot[lane] = in2 - v;
+    if (lane == 31) total = in2;
+  }
+  __syncthreads();
+  const int base = warp_tot[w] + incl - keep;
+  for (int j = 0; j < keep; ++j) { row_map[base + j] = rows[j]; cur_tokens[base + j] = toks[j]; }
+  if (tid == 0) st->pad[1] = total;
+  (void)B;
+}
+
+int launch_compact_rows(int* row_map, int* cur_tokens, const unsigned char* finished, StepState* st, int B, cudaStream_t s) {
+  SCV_REQUIRE(B <= 16384, "compaction of finished rows: %d rows (at most 16384 per call)", B);
+  SCV_CUDA(launch_k(compact_rows_kernel, dim3(1), dim3(1024), 0, s, row_map, cur_tokens, finished, st, B));
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
-                     unsigned long long offset, cudaStream_t s) {
-  init_rows_kernel<<<ceil_div(B, 256), 256, 0, s>>>(cur_tokens, finished, B, st, seed, offset);
+                     unsigned long long offset, cudaStream_t s, int* row_map) {
+  init_rows_kernel<<<ceil_div(B, 256), 256, 0, s>>>(cur_tokens, finished, B, st, seed, offset, row_map);
   SCV_LAUNCH_CHECK();
   return 0;
 }

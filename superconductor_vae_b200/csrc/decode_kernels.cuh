@@ -17,7 +17,8 @@ struct StepState {
   int out_len;         // number of executed steps L
   int degenerate;      // batch-global "logits contain nan/inf" flag of the current step (:1464-1466)
   int next_free_page;  // bump allocator over the KV page pool
-  int pad[2];
+  int pad[2];          // pad[0]: 1 + last step at which a row emitted END (decode_cluster.cu); pad[1]: rows still being decoded
+                       // when finished rows are compacted away (0 = no compaction): kernels skip slots >= pad[1]
   unsigned long long seed, offset;   // Philox key / counter offset of this call (kept out of the kernel arguments)
 };
 
@@ -28,6 +29,7 @@ struct EmbedArgs {
   float* x; int B;
   int* page_table; int pages_per_seq;
   StepState* st;
+  const int* row_map = nullptr; int slot_base = 0;   // compaction: slot -> row of the call's batch (page_table is indexed by row)
 };
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
 // x[b * L + t] = token_embedding[tokens[b, t]] + pe[t] for every position (teacher-forced forward, :947-949)
@@ -53,6 +55,9 @@ struct AttnArgs {
   const unsigned char* key_skip = nullptr;
   const StepState* st = nullptr;                         // null: no done flag / step counter (forward)
   void* trace = nullptr;                                 // CTA residency trace (common.cuh), normally null
+  // compaction of finished rows: query row b is slot slot_base + b; its sequence (page table row, projected memory) is
+  // row_map[slot]; page_table / kcache / vcache are then NOT offset to the sub-batch
+  const int* row_map = nullptr; int slot_base = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 
@@ -96,11 +101,15 @@ struct SamplerArgs {
   int* cur_tokens = nullptr; unsigned char* finished = nullptr;
   const long long* forced = nullptr;
   StepState* st = nullptr;
+  // compaction of finished rows: logits / head outputs / cur_tokens are indexed by slot, everything else by row_map[slot]
+  const int* row_map = nullptr; int slot_base = 0;
 };
 // which = 1: first kernel (stages logits, publishes the H2 flag, picks the token when the call is plain greedy);
 // which = 2: second kernel (entropy / temperature sampling / log-prob), only when sampling or entropy is requested
 int launch_sampler(const SamplerArgs& a, int which, cudaStream_t s);
 int launch_step_end(StepState* st, int max_steps, cudaStream_t s);
+// stable compaction of the slots whose row has not emitted END (row_map, cur_tokens in place); st->pad[1] = rows left
+int launch_compact_rows(int* row_map, int* cur_tokens, const unsigned char* finished, StepState* st, int B, cudaStream_t s);
 // one thread that spins until *host_flag (pinned host memory) becomes non-zero: holds a stream while the host enqueues
 int launch_host_gate(int* host_flag, cudaStream_t s);
 // true when launch_sampler(a, 1, ...) is the warp-per-row greedy kernel and nothing else (no second sampler kernel)
@@ -162,6 +171,6 @@ int launch_decode_cluster_step(const ClProgram& p, cudaStream_t s);
 int launch_decode_cluster_persist(const ClProgram& p, const SmallTail& tail, cudaStream_t s);
 
 int launch_init_rows(int* cur_tokens, unsigned char* finished, int B, StepState* st, unsigned long long seed,
-                     unsigned long long offset, cudaStream_t s);
+                     unsigned long long offset, cudaStream_t s, int* row_map = nullptr);
 
 }  // namespace scv

@@ -77,6 +77,7 @@ struct scv_decoder {
   DevBuf xn_s, attn_s, ff_s, h2_s;   // SplitTile (bf16 hi/lo) activations feeding the tcgen05 projections
   DevBuf msplit;                     // SplitTile scratch of the memory builder / memory-token projection
   DevBuf seen, dlog;                 // site-dup gating: [B, V] seen-element bitmap, [B] site_dup_head logit
+  DevBuf row_map;                    // compaction of finished rows: slot -> row of the call's batch
   DevBuf o_tok, o_lp, o_ent, masks_buf, forced_buf;   // engine-owned I/O so that a captured step never bakes caller pointers
   std::vector<GraphEntry> graphs;    // one instantiated CUDA graph of a decode step per call configuration
   size_t ws_signature = 0;
@@ -121,7 +122,7 @@ struct scv_decoder {
   ~scv_decoder() {
     for (DevBuf* b : {&x, &xn, &qkv, &attn, &q2, &ff, &h1, &h2, &t3, &logits, &tlog, &slog, &ckv, &kvpool, &cur,
                       &fin, &ptab, &state, &mtmp, &xn_s, &attn_s, &ff_s, &h2_s, &o_tok, &o_lp, &o_ent, &masks_buf,
-                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d, &fw_skip, &cl_instr, &cl_dbg, &sm_part})
+                      &forced_buf, &seen, &dlog, &msplit, &sm_phases, &sm_bar, &sm_h2b, &sm_t3s, &sm_t3d, &fw_skip, &cl_instr, &cl_dbg, &sm_part, &row_map})
       b->release();
     drop_graphs();
     if (pinned) cudaFreeHost(pinned);
@@ -377,6 +378,7 @@ static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = f
   SCV_TRY(D->o_ent.ensure(io * f));
   SCV_TRY(D->forced_buf.ensure(io * sizeof(long long)));
   SCV_TRY(D->masks_buf.ensure((size_t)5 * c.vocab_size));
+  SCV_TRY(D->row_map.ensure((size_t)B * sizeof(int)));
   if (need_site_dup) {      // captured steps bake these pointers in as well, so they belong to the signature below
     SCV_TRY(D->seen.ensure((size_t)B * c.vocab_size));
     SCV_TRY(D->dlog.ensure((size_t)B * sizeof(float)));
@@ -386,7 +388,7 @@ static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = f
   for (const DevBuf* b : {&D->x, &D->xn, &D->qkv, &D->attn, &D->q2, &D->ff, &D->h1, &D->h2, &D->t3, &D->logits, &D->tlog,
                           &D->slog, &D->ckv, &D->kvpool, &D->cur, &D->fin, &D->ptab, &D->state, &D->xn_s, &D->attn_s,
                           &D->ff_s, &D->h2_s, &D->o_tok, &D->o_lp, &D->o_ent, &D->masks_buf, &D->forced_buf, &D->seen,
-                          &D->dlog, &D->sm_part})
+                          &D->dlog, &D->sm_part, &D->row_map})
     sig = sig * 1000003u + reinterpret_cast<size_t>(b->p);
   if (sig != D->ws_signature || D->tune_epoch_seen != tune_epoch()) {
     D->drop_graphs(); D->ws_signature = sig; D->tune_epoch_seen = tune_epoch();
@@ -644,15 +646,21 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   float* x = D->x.as<float>() + (size_t)r0 * d; float* xn = D->xn.as<float>() + (size_t)r0 * d;
   float* qkv = D->qkv.as<float>() + (size_t)r0 * 3 * d; float* attn = D->attn.as<float>() + (size_t)r0 * d;
   float* q2 = D->q2.as<float>() + (size_t)r0 * d; float* ff = D->ff.as<float>() + (size_t)r0 * dff;
-  int* page_table = D->ptab.as<int>() + (size_t)r0 * pps;
+  int* page_table = D->ptab.as<int>() + (size_t)(((A->flags & SCV_FLAG_COMPACT_FINISHED) != 0 && !D->small_active && !D->cl_active) ? 0 : r0) * pps;
   // Tensor-core step: every projection input is handed over as a bf16 hi/lo SplitTile written by its producer
   // (LayerNorm, attention, previous GEMM epilogue); nullptr selects the fp32 CUDA-core path.
   const bool tc = use_tensor_cores(c, Bfull);
+  // Opt-in retirement of finished rows (SCV_FLAG_COMPACT_FINISHED, per-projection path only): per-step buffers are indexed
+  // by SLOT, everything that lives for the whole call (KV pages, projected memory, outputs, flags) by row_map[slot].
+  const bool compact = (A->flags & SCV_FLAG_COMPACT_FINISHED) != 0 && !D->small_active && !D->cl_active;
+  const int* row_map = compact ? D->row_map.as<int>() : nullptr;
+  const int ob = compact ? 0 : r0;            // offset of row-indexed arrays: none when rows are looked up through row_map
   auto tile_off = [&](const DevBuf& b, int K) -> void* {
     return static_cast<unsigned char*>(b.p) + (size_t)(r0 / 128) * ceil_div(K, 64) * 32768;
   };
   // each tensor-core projection prefetches the tiled weights of the projection that follows it (common.cuh next_w)
   auto next = [&](LinearArgs& l, const __nv_bfloat16* wt, int N, int K) {
+    l.row_base = r0;
     if (tc && wt != nullptr) { l.next_w = wt; l.next_w_bytes = tc_packed_elems(N, K) * sizeof(__nv_bfloat16); }
   };
   void* xn_s = tc ? tile_off(D->xn_s, d) : nullptr; void* attn_s = tc ? tile_off(D->attn_s, d) : nullptr;
@@ -665,15 +673,15 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   sp.stop_boost = A->stop_boost; sp.hard_stop = A->hard_stop_threshold;
   if (A->site_dup_threshold > 0.f) {
     sp.dup_logits = D->dlog.as<float>() + r0; sp.dup_threshold = A->site_dup_threshold;
-    sp.seen = D->seen.as<unsigned char>() + (size_t)r0 * c.vocab_size;
+    sp.seen = D->seen.as<unsigned char>() + (size_t)ob * c.vocab_size;
   }
   sp.want_logprobs = A->want_log_probs; sp.want_entropy = A->want_entropy; sp.flags = A->flags;
-  sp.row_base = r0;
-  sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens) + (size_t)r0 * steps_max;
-  sp.out_logprobs = A->want_log_probs ? A->out_log_probs + (size_t)r0 * steps_max : nullptr;
-  sp.out_entropy = A->want_entropy ? A->out_entropy + (size_t)r0 * steps_max : nullptr;
-  sp.out_ld = steps_max; sp.cur_tokens = D->cur.as<int>() + r0; sp.finished = D->fin.as<unsigned char>() + r0;
-  sp.forced = A->forced_tokens ? reinterpret_cast<const long long*>(A->forced_tokens) + (size_t)r0 * steps_max : nullptr;
+  sp.row_base = r0; sp.row_map = row_map; sp.slot_base = r0;
+  sp.out_tokens = reinterpret_cast<long long*>(A->out_tokens) + (size_t)ob * steps_max;
+  sp.out_logprobs = A->want_log_probs ? A->out_log_probs + (size_t)ob * steps_max : nullptr;
+  sp.out_entropy = A->want_entropy ? A->out_entropy + (size_t)ob * steps_max : nullptr;
+  sp.out_ld = steps_max; sp.cur_tokens = D->cur.as<int>() + r0; sp.finished = D->fin.as<unsigned char>() + ob;
+  sp.forced = A->forced_tokens ? reinterpret_cast<const long long*>(A->forced_tokens) + (size_t)ob * steps_max : nullptr;
   sp.st = st;
   if (phase == 2) return launch_sampler(sp, 2, s);
   auto norm = [&](const LNp& P, float* fp32_out) -> int {
@@ -693,7 +701,7 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
 
   EmbedArgs e;
   e.table = D->emb; e.ld_table = D->ld_emb; e.pe = D->pe; e.d = d; e.cur_tokens = D->cur.as<int>() + r0; e.x = x; e.B = B;
-  e.page_table = page_table; e.pages_per_seq = pps; e.st = st;
+  e.page_table = page_table; e.pages_per_seq = pps; e.st = st; e.row_map = row_map; e.slot_base = r0;
   SCV_TRY(launch_embed(e, s));
   if (D->cl_active) {                      // cluster-parallel small-batch decode (decode_cluster.cu)
     if (phase == 3) {                      // the whole plain-greedy decode in one launch
@@ -740,6 +748,7 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     sa.out = attn; sa.ldo = d; sa.B = B; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale; sa.fixed_len = -1;
     sa.max_n = std::max(c.pe_len, M); sa.st = st; sa.host_len_hint = host_step + 1;
     sa.out_split = static_cast<unsigned char*>(attn_s); sa.kb_out = d / 64;
+    sa.row_map = row_map; sa.slot_base = r0;
     SCV_TRY(launch_attention(sa, s));
     LinearArgs o = lin_args(attn, d, L.sa_out, x, d, B, ACT_NONE, done);
     o.residual = x; o.ldr = d; o.a_split = attn_s;
@@ -753,11 +762,12 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
     ca.q = q2; ca.ldq = d;
-    float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + r0) * M * 2 * d;
+    float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + ob) * M * 2 * d;
     ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d; ca.row_stride = 2 * d;
     ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
     ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
     ca.out_split = static_cast<unsigned char*>(attn_s); ca.kb_out = d / 64;
+    ca.row_map = row_map; ca.slot_base = r0;
     SCV_TRY(launch_attention(ca, s));
     LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
     co.residual = x; co.ldr = d; co.a_split = attn_s;
@@ -779,19 +789,19 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   float* logits = D->logits.as<float>() + (size_t)r0 * c.vocab_size;
   float* tlog = D->tlog.as<float>() + (size_t)r0 * 8; float* slog = D->slog.as<float>() + r0;
   LinearArgs oa = lin_args(h1, d, D->out_a, h2, d, B, ACT_GELU, done);
-  oa.a_split = xn_s; oa.y_split = h2_s;
+  oa.a_split = xn_s; oa.y_split = h2_s; oa.row_base = r0;
   next(oa, D->out_b.wt, c.vocab_size, d);
   SCV_TRY(launch_linear(oa, 0, s));
-  LinearArgs ob = lin_args(h2, d, D->out_b, logits, c.vocab_size, B, ACT_NONE, done);
-  ob.a_split = h2_s;
-  SCV_TRY(launch_linear(ob, 0, s));
+  LinearArgs ob_ = lin_args(h2, d, D->out_b, logits, c.vocab_size, B, ACT_NONE, done);
+  ob_.a_split = h2_s; ob_.row_base = r0;
+  SCV_TRY(launch_linear(ob_, 0, s));
   if (A->type_masks != nullptr) {
     SCV_TRY(norm(D->tt_ln, h1));
     LinearArgs ta = lin_args(h1, d, D->tt_a, h2, d, B, ACT_GELU, done);
-    ta.a_split = xn_s; ta.y_split = h2_s;
+    ta.a_split = xn_s; ta.y_split = h2_s; ta.row_base = r0;
     SCV_TRY(launch_linear(ta, 0, s));
     LinearArgs tb = lin_args(h2, d, D->tt_b, t3, d / 4, B, ACT_GELU, done);
-    tb.a_split = h2_s;
+    tb.a_split = h2_s; tb.row_base = r0;
     SCV_TRY(launch_linear(tb, 0, s));
     SCV_TRY(launch_linear(lin_args(t3, d / 4, D->tt_c, tlog, 8, B, ACT_NONE, done), 0, s));
   }
@@ -831,7 +841,9 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   set_pdl_for_call(true);
   SCV_TRY(ensure_workspace(D, B, M, A->site_dup_threshold > 0.f));
   StepState* st = D->state.as<StepState>();
-  SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s));
+  const bool want_compact = (A->flags & SCV_FLAG_COMPACT_FINISHED) != 0;
+  SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s,
+                           want_compact ? D->row_map.as<int>() : nullptr));
   // the step kernels read / write engine-owned buffers only (so a captured step can be replayed for any call);
   // caller tensors are copied in here and out after the loop
   const size_t io = (size_t)B * steps_max;
@@ -917,6 +929,8 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
         for (int i = 0; i < n_sub; ++i) SCV_CUDA(cudaStreamWaitEvent(s, D->ev_sub[i], 0));
       }
     }
+    if ((A->flags & SCV_FLAG_COMPACT_FINISHED) != 0 && !D->small_active && !D->cl_active)
+      SCV_TRY(launch_compact_rows(D->row_map.as<int>(), D->cur.as<int>(), D->fin.as<unsigned char>(), st, B, s));
     SCV_TRY(launch_step_end(st, steps_max, s));
     return 0;
   };

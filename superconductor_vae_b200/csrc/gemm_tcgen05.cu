@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, m0 = m_tile * BM, n0 = n_tile * BN;
   const int KB = a.kblocks;
+  // Compaction of finished rows: this row tile holds no live row.  (StepState::pad[1] was written several kernels ago -
+  // by the compaction kernel of the previous step - so it may be read before griddepcontrol.wait.)
+  if (a.done_flag != nullptr && a.done_flag[6] > 0 && a.row_base + m0 >= a.done_flag[6]) return;
   TraceRec* trc = tid == 0 ? trace_begin(a.trace, 100u + (uint32_t)(a.N >> 7)) : nullptr;
 
   if (tid == 0) {
@@ -340,6 +343,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.M = a.M; t.N = a.N; t.K = a.K; t.act = a.act; t.done_flag = a.done_flag;
   t.next_w = static_cast<const uint8_t*>(a.next_w); t.next_w_bytes = (uint32_t)a.next_w_bytes;
   t.trace = trace_ptr();
+  t.row_base = a.row_base;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));

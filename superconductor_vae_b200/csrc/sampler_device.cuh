@@ -23,7 +23,11 @@ struct RowCtx {
   bool stop_on, force, dup_suppress, late;
   float boost, length_boost;
 };
+// b = row of the per-step buffers (logits, head outputs: the SLOT when finished rows are compacted away), ob = the row of
+// the call's batch it stands for (outputs, finished flags, site-dup bitmap); ob == b without compaction.
+__device__ __forceinline__ int orig_row(const SamplerArgs& a, int b) { return a.row_map != nullptr ? a.row_map[a.slot_base + b] : b; }
 __device__ __forceinline__ RowCtx make_row_ctx(const SamplerArgs& a, int b, int step) {
+  const int ob = orig_row(a, b);
   RowCtx c;
   int pred_type = 0;
   if (a.type_masks != nullptr) {
@@ -37,13 +41,13 @@ __device__ __forceinline__ RowCtx make_row_ctx(const SamplerArgs& a, int b, int 
   c.force = false;
   if (c.stop_on) {
     sp = sigmoidf_(__ldcg(a.stop_logits + b));
-    c.force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[b] == 0;
+    c.force = a.hard_stop > 0.f && sp > a.hard_stop && a.finished[ob] == 0;
   }
   c.boost = a.stop_boost * sp;
   c.late = c.stop_on && step > 10;
   c.length_boost = c.late ? 10.0f * (float)(step - 10) / (float)max(a.max_len - 10, 1) : 0.f;
   c.dup_suppress = a.seen != nullptr && step > 0 && sigmoidf_(__ldcg(a.dup_logits + b)) < a.dup_threshold;
-  c.seen_row = c.dup_suppress ? a.seen + (size_t)b * a.V : nullptr;
+  c.seen_row = c.dup_suppress ? a.seen + (size_t)ob * a.V : nullptr;
   c.mk = a.type_masks != nullptr ? a.type_masks + (size_t)pred_type * a.V : nullptr;
   return c;
 }
@@ -59,17 +63,18 @@ __device__ __forceinline__ float adjust_logit(const RowCtx& c, int v, float l, u
 
 __device__ __forceinline__ int commit_token(const SamplerArgs& a, int b, int step, int token, float logprob) {
   // single thread
+  const int ob = orig_row(a, b);
   if (a.forced != nullptr) {               // teacher-forced replay; a negative entry leaves the position to the sampler
-    const long long f = a.forced[(size_t)b * a.out_ld + step];
+    const long long f = a.forced[(size_t)ob * a.out_ld + step];
     if (f >= 0) token = (int)f;
   }
-  a.out_tokens[(size_t)b * a.out_ld + step] = (long long)token;
-  if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)b * a.out_ld + step] = logprob;
+  a.out_tokens[(size_t)ob * a.out_ld + step] = (long long)token;
+  if (a.out_logprobs != nullptr) a.out_logprobs[(size_t)ob * a.out_ld + step] = logprob;
   a.cur_tokens[b] = token;
   // ids 20..137 are the element range of the pre-V13 vocabulary; the reference still uses it
-  if (a.seen != nullptr && token >= 20 && token <= 137 && a.finished[b] == 0) a.seen[(size_t)b * a.V + token] = 1;
-  if (token == kEndIdx && a.finished[b] == 0) {
-    a.finished[b] = 1;
+  if (a.seen != nullptr && token >= 20 && token <= 137 && a.finished[ob] == 0) a.seen[(size_t)ob * a.V + token] = 1;
+  if (token == kEndIdx && a.finished[ob] == 0) {
+    a.finished[ob] = 1;
     atomicSub(&a.st->n_unfinished, 1);
   }
   return token;

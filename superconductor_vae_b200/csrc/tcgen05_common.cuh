@@ -97,6 +97,7 @@ struct TcArgs {
   const uint8_t* next_w; uint32_t next_w_bytes;   // L2 prefetch of the next projection's weights (0 = none)
   const float* ln_gamma; const float* ln_beta; uint8_t* ln_out;   // gemm_tcgen05_ln.cu: LayerNorm of the output row
   void* trace;                                                    // CTA residency trace (common.cuh), normally null
+  int row_base;                                                   // first row of the launch inside the call's batch
 };
 
 

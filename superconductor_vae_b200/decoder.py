@@ -127,6 +127,10 @@ class EnhancedTransformerDecoder(nn.Module):
         self._engine_versions: Dict[str, Tuple[int, int]] = {}
         self.max_rows_per_call = 8192        # rows decoded per engine call; larger batches are chunked
         self.h2_uniform_fallback = True      # reproduce the reference's batch-global degenerate guard
+        # Opt-in: retire a row once it has emitted END instead of decoding it until EVERY row has finished
+        # like the reference does (:1541-1548).  Tokens / log-probs / entropy are identical up to and including each
+        # row's first END - what every caller consumes - and PAD / 0.0 after it; the executed length L is the same.
+        self.compact_finished = False
         self.last_steps: Optional[int] = None
 
     # ------------------------------------------------------------------ construction helpers
@@ -404,6 +408,8 @@ class EnhancedTransformerDecoder(nn.Module):
             if _seed is None:
                 _seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if not (temperature < 0.01) else 0
             flags = _lib.FLAG_H2_UNIFORM_FALLBACK if self.h2_uniform_fallback else 0
+            if self.compact_finished:
+                flags |= _lib.FLAG_COMPACT_FINISHED
             steps_done = 0
             chunk = max(1, int(self.max_rows_per_call))
             with torch.cuda.device(device):
@@ -428,6 +434,15 @@ class EnhancedTransformerDecoder(nn.Module):
                     steps_done = max(steps_done, out_steps.value)
                     self._last_B = hi - lo
             self.last_steps = steps_done
+            if self.compact_finished:
+                # same outputs whichever kernel path decoded the rows: nothing after a row's first END
+                t_ = tokens[:, :steps_done]
+                after = (torch.cumsum((t_ == END_IDX).to(torch.int32), dim=1) - (t_ == END_IDX).to(torch.int32)) > 0
+                tokens[:, :steps_done].masked_fill_(after, PAD_IDX)
+                if lps is not None:
+                    lps[:, :steps_done].masked_fill_(after, 0.0)
+                if ents is not None:
+                    ents[:, :steps_done].masked_fill_(after, 0.0)
             gen = tokens[:, :steps_done].contiguous()
             return (gen, lps[:, :steps_done].contiguous() if lps is not None else None,
                     ents[:, :steps_done].contiguous() if ents is not None else None)

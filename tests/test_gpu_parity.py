@@ -607,6 +607,36 @@ def test_cluster_parallel_small_batch_kernel_matches_default(rows):
         _lib.tune(cluster=0)
 
 
+@pytest.mark.parametrize("rows", [24, 300, 2304])
+def test_compact_finished_matches_reference_semantics_up_to_end(rows):
+    """Opt-in retirement of finished rows (decoder.compact_finished): rows that have emitted END leave the batch
+    (slots are compacted after every step, projections / attention / sampler skip the empty slots).  Against the default
+    (reference semantics: finished rows keep decoding): identical tokens, log-probs and entropy up to and including every
+    row's first END, PAD / 0 after it, same executed length; on a sampled rollout whose rows end at very different steps
+    (24 rows: persistent small-batch kernel; 300: one stream; 2304: two sub-batch streams)."""
+    sd = W.make_decoder_state_dict(W.C512, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    z = W.make_latents(rows, 2048, 4242)
+    stoich, heads = W.make_conditioning(rows, 13, 4242)
+    for kw in (dict(temperature=1.2, max_len=64, stop_boost=10.0, return_log_probs=True, return_entropy=True, _seed=17),
+               dict(temperature=0.001, max_len=64, type_masks=_cuda(OV.type_masks()), stop_boost=10.0, hard_stop_threshold=0.8)):
+        t0, lp0, en0 = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+        dec.compact_finished = True
+        try:
+            t1, lp1, en1 = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
+        finally:
+            dec.compact_finished = False
+        assert t0.shape == t1.shape
+        is_end = t0 == 2
+        after = (torch.cumsum(is_end.int(), dim=1) - is_end.int()) > 0          # strictly after the first END
+        assert torch.equal(t1[~after], t0[~after]) and int(t1[after].abs().sum()) == 0
+        if lp0 is not None:
+            assert torch.equal(lp1[~after], lp0[~after]) and float(lp1[after].abs().sum()) == 0.0
+            assert torch.equal(en1[~after], en0[~after]) and float(en1[after].abs().sum()) == 0.0
+            ends = torch.where(is_end.any(dim=1), is_end.int().argmax(dim=1), torch.full((rows,), t0.shape[1], device=t0.device))
+            assert int(ends.max()) - int(ends.min()) >= 5                          # the rollout really is ragged
+
+
 def test_tunables_never_change_tokens():
     """scv_tune moves work between streams / grids only: the opt-in launch configurations (grid-stride attention grid,
     forced GEMM pipeline depth, 1 / 3 sub-batch streams, bulk-copy staged cross-attention, no graph replay) decode the
