@@ -82,6 +82,8 @@ struct Tunables {
   int attn_bulk;           // SCV_ATTN_BULK: cross-attention through the bulk-copy (cp.async.bulk) staged kernel
   int attn_bulk_min_rows;  // SCV_ATTN_BULK_MIN_ROWS: ... for launches with at least this many rows
   int attn_bulk_piece_kb;  // SCV_ATTN_BULK_PIECE_KB: a sequence's block travels as copies of this size (0 = one copy)
+  int cond_tc_min_rows;    // SCV_COND_TC_MIN_ROWS: calls with at least this many rows run the small conditioning projections
+                           // (stoich / heads / skip memory branches, sc_head.0, family heads) on the tensor cores
   int cluster;             // SCV_CLUSTER: small batches through the cluster-parallel kernel (decode_cluster.cu); opt-in: measured
                            // 0.76-0.92 ms per step against 0.77-0.84 ms for the grid-barrier kernel
   int cluster_max_rows;    // SCV_CLUSTER_MAX_ROWS: ... up to this many rows (<= 64)

@@ -153,18 +153,18 @@ static int dec_register(scv_decoder* D) {
   if (c.skip_n_tokens > 0) {
     const int n_skip = d * c.skip_n_tokens;
     SCV_TRY(W.add_linear("skip_to_memory.0", n_skip / 2, c.encoder_skip_dim, &D->skip_a));
-    SCV_TRY(W.add_linear("skip_to_memory.2", n_skip, n_skip / 2, &D->skip_b));
+    SCV_TRY(W.add_linear("skip_to_memory.2", n_skip, n_skip / 2, &D->skip_b, true, true));
   }
   if (c.n_stoich_tokens > 0) {
     SCV_TRY(W.add_linear("stoich_to_memory.0", d, c.stoich_input_dim, &D->s2m_a));
     SCV_TRY(W.add_layernorm("stoich_to_memory.1", d, &D->s2m_ln));
-    SCV_TRY(W.add_linear("stoich_to_memory.3", d * c.n_stoich_tokens, d, &D->s2m_b));
+    SCV_TRY(W.add_linear("stoich_to_memory.3", d * c.n_stoich_tokens, d, &D->s2m_b, true, true));
   }
   if (c.heads_n_tokens > 0) {
     SCV_TRY(W.add_linear("heads_to_memory.0", d / 2, c.heads_input_dim, &D->h2m_a));
     SCV_TRY(W.add_layernorm("heads_to_memory.1", d / 2, &D->h2m_ln));
-    SCV_TRY(W.add_linear("heads_to_memory.3", d, d / 2, &D->h2m_b));
-    SCV_TRY(W.add_linear("heads_to_memory.5", d * c.heads_n_tokens, d, &D->h2m_c));
+    SCV_TRY(W.add_linear("heads_to_memory.3", d, d / 2, &D->h2m_b, true, true));
+    SCV_TRY(W.add_linear("heads_to_memory.5", d * c.heads_n_tokens, d, &D->h2m_c, true, true));
   }
   D->layers.resize(c.num_layers);
   for (int i = 0; i < c.num_layers; ++i) {
@@ -311,22 +311,27 @@ int scv_decoder_build_memory(scv_decoder* D, int32_t B, const float* z, const fl
     SCV_TRY(launch_linear(lin_args(t0, Hd, D->l2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
   }
   col += c.n_memory_tokens * d;
+  // The second layers of the small conditioning branches ([B, d] x [d, 4 d] each) are 110 GFLOP apiece at 52.8 K rows
+  // (3 ms each on the fp32 CUDA-core kernel): tensor cores for calls of >= cond_tc_min_rows rows (default 16384: the
+  // encoder -> memory-token pipeline of BASELINE config 5).  Decode-sized calls keep the fp32 kernel (every product exact):
+  // with the two-term activation split of the tensor path 1 of the 4096 greedy rows of config 2 left the oracle at a near-tie.
+  auto lin_impl = [&](LinearArgs a) { a.wt = B >= tun().cond_tc_min_rows ? a.wt : nullptr; return launch_linear(a, 0, s); };
   if (use_skip) {                                                          // (:806-809)
     SCV_TRY(launch_linear(lin_args(skip, c.encoder_skip_dim, D->skip_a, t0, D->skip_a.N, B, ACT_GELU), 0, s));
-    SCV_TRY(launch_linear(lin_args(t0, D->skip_a.N, D->skip_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    SCV_TRY(lin_impl(lin_args(t0, D->skip_a.N, D->skip_b, memory_out + col, ldm, B, ACT_NONE)));
     col += c.skip_n_tokens * d;
   }
   if (use_stoich) {                                                        // (:813-816)
     SCV_TRY(launch_linear(lin_args(stoich, c.stoich_input_dim, D->s2m_a, t0, d, B, ACT_NONE), 0, s));
     SCV_TRY(launch_layernorm(t0, d, D->s2m_ln.g, D->s2m_ln.b, t0, d, B, d, ACT_GELU, nullptr, s));
-    SCV_TRY(launch_linear(lin_args(t0, d, D->s2m_b, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    SCV_TRY(lin_impl(lin_args(t0, d, D->s2m_b, memory_out + col, ldm, B, ACT_NONE)));
     col += c.n_stoich_tokens * d;
   }
   if (use_heads) {                                                         // (:858-868)
     SCV_TRY(launch_linear(lin_args(heads_in, c.heads_input_dim, D->h2m_a, t0, d / 2, B, ACT_NONE), 0, s));
     SCV_TRY(launch_layernorm(t0, d / 2, D->h2m_ln.g, D->h2m_ln.b, t0, d / 2, B, d / 2, ACT_GELU, nullptr, s));
-    SCV_TRY(launch_linear(lin_args(t0, d / 2, D->h2m_b, t1, d, B, ACT_GELU), 0, s));
-    SCV_TRY(launch_linear(lin_args(t1, d, D->h2m_c, memory_out + col, ldm, B, ACT_NONE), 0, s));
+    SCV_TRY(lin_impl(lin_args(t0, d / 2, D->h2m_b, t1, d, B, ACT_GELU)));
+    SCV_TRY(lin_impl(lin_args(t1, d, D->h2m_c, memory_out + col, ldm, B, ACT_NONE)));
     col += c.heads_n_tokens * d;
   }
   return 0;

@@ -23,6 +23,13 @@ struct DevBuf {
     cap = bytes;
     return 0;
   }
+  // like ensure(), but a (re)allocated buffer starts as zeros (padding columns nobody writes must read as 0)
+  int ensure_zeroed(size_t bytes) {
+    if (bytes <= cap) return 0;
+    SCV_TRY(ensure(bytes));
+    SCV_CUDA(cudaMemset(p, 0, bytes));
+    return 0;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   float* f() const { return static_cast<float*>(p); }
 };
@@ -177,9 +184,9 @@ struct scv_encoder {
   Lin co_a, co_b, co_c, cu_a, cu_b, cu_c, ir_a, ir_b; LNp co_ln, cu_ln, ir_ln;
   // never executed by the reference forward (element_properties=None) but present in its state_dict
   Lin prop_enc, combiner; LNp prop_ln;
-  DevBuf t0, t1, t2, fused_in, cond, sc_in, small, zsplit;
+  DevBuf t0, t1, t2, fused_in, cond, sc_in, small, zsplit, scsplit, condsplit;
 
-  ~scv_encoder() { for (DevBuf* b : {&t0, &t1, &t2, &fused_in, &cond, &sc_in, &small, &zsplit}) b->release(); }
+  ~scv_encoder() { for (DevBuf* b : {&t0, &t1, &t2, &fused_in, &cond, &sc_in, &small, &zsplit, &scsplit, &condsplit}) b->release(); }
 };
 
 // nn.Linear with an extra tcgen05-tiled weight copy whenever the tensor-core path can take the projection
@@ -257,20 +264,22 @@ static int enc_register(scv_encoder* E) {
   SCV_TRY(add_lin(W, "tc_class_head.0", 256, bb, &E->cls_a));
   SCV_TRY(add_lin(W, "tc_class_head.3", 5, 256, &E->cls_b));
   const int sc_in = L + 1 + c.magpie_dim + 1 + c.max_elements + 1 + 1 + 5;
-  SCV_TRY(add_lin(W, "sc_head.0", 512, sc_in, &E->sc_a));
+  // K = 2214 / 513 are not multiples of 4: no fp32-row tensor path, but the tiled weights are zero padded to whole 64-wide
+  // k-blocks, so a SplitTile copy of the (zero padded) input row feeds the tensor cores at large batch (scv_encoder_heads)
+  SCV_TRY(W.add_linear("sc_head.0", 512, sc_in, &E->sc_a, true, true));
   SCV_TRY(W.add_layernorm("sc_head.2", 512, &E->sc_ln));
   SCV_TRY(add_lin(W, "sc_head.4", 128, 512, &E->sc_b));
   SCV_TRY(add_lin(W, "sc_head.6", 1, 128, &E->sc_c));
   p = "hierarchical_family_head.";
-  SCV_TRY(add_lin(W, p + "coarse_head.0", 256, bb + 1, &E->co_a));
+  SCV_TRY(W.add_linear(p + "coarse_head.0", 256, bb + 1, &E->co_a, true, true));
   SCV_TRY(W.add_layernorm(p + "coarse_head.1", 256, &E->co_ln));
   SCV_TRY(add_lin(W, p + "coarse_head.4", 128, 256, &E->co_b));
   SCV_TRY(add_lin(W, p + "coarse_head.6", 7, 128, &E->co_c));
-  SCV_TRY(add_lin(W, p + "cuprate_sub_head.0", 128, bb + 1, &E->cu_a));
+  SCV_TRY(W.add_linear(p + "cuprate_sub_head.0", 128, bb + 1, &E->cu_a, true, true));
   SCV_TRY(W.add_layernorm(p + "cuprate_sub_head.1", 128, &E->cu_ln));
   SCV_TRY(add_lin(W, p + "cuprate_sub_head.4", 64, 128, &E->cu_b));
   SCV_TRY(add_lin(W, p + "cuprate_sub_head.6", 6, 64, &E->cu_c));
-  SCV_TRY(add_lin(W, p + "iron_sub_head.0", 64, bb + 1, &E->ir_a));
+  SCV_TRY(W.add_linear(p + "iron_sub_head.0", 64, bb + 1, &E->ir_a, true, true));
   SCV_TRY(W.add_layernorm(p + "iron_sub_head.1", 64, &E->ir_ln));
   SCV_TRY(add_lin(W, p + "iron_sub_head.4", 2, 64, &E->ir_b));
   return 0;
@@ -390,15 +399,20 @@ int scv_encoder_heads(scv_encoder* E, int32_t B, const float* z, const scv_encod
   const scv_encoder_config& c = E->cfg;
   const int L = c.latent_dim, f = c.fusion_dim, md = c.magpie_dim, El = c.max_elements;
   const int bb = c.decoder_hidden[c.n_decoder_hidden - 1];
-  const int ld_cond = round_up(bb + 1, 4);
-  const int sc_dim = L + 1 + md + 1 + El + 1 + 1 + 5, ld_sc = round_up(sc_dim, 4);
+  const int ld_cond = round_up(bb + 1, 8);
+  const int sc_dim = L + 1 + md + 1 + El + 1 + 1 + 5, ld_sc = round_up(sc_dim, 8);
+  // Large batches: the two ragged-K projections (sc_head.0: K = 2214, the family heads: K = 513) go to the tensor cores
+  // through a SplitTile copy of their zero-padded input rows (52.8 K rows: 4.4 ms of fp32 CUDA-core work otherwise).
+  // Smaller calls keep the fp32 CUDA-core kernel (every product exact): the heads feed the decoder's conditioning, and the
+  // greedy decode is held to token-exactness against the fp32 oracle.
+  const bool ragged_tc = B >= tun().cond_tc_min_rows;      // default 16384 (common.cuh)
   int wide = std::max(std::max(L / 4, 512), bb);
   for (int j = 0; j < c.n_decoder_hidden; ++j) wide = std::max(wide, c.decoder_hidden[j]);
   SCV_TRY(E->t0.ensure((size_t)B * wide * sizeof(float)));
   SCV_TRY(E->t1.ensure((size_t)B * wide * sizeof(float)));
   SCV_TRY(E->t2.ensure((size_t)B * wide * sizeof(float)));
-  SCV_TRY(E->cond.ensure((size_t)B * ld_cond * sizeof(float)));
-  SCV_TRY(E->sc_in.ensure((size_t)B * ld_sc * sizeof(float)));
+  SCV_TRY(E->cond.ensure_zeroed((size_t)B * ld_cond * sizeof(float)));
+  SCV_TRY(E->sc_in.ensure_zeroed((size_t)B * ld_sc * sizeof(float)));
   SCV_TRY(E->small.ensure((size_t)B * 32 * sizeof(float)));
   float *t0 = E->t0.f(), *t1 = E->t1.f(), *t2 = E->t2.f(), *cond = E->cond.f(), *sci = E->sc_in.f();
   float* sc_pred = E->small.f();            // [B]
@@ -463,22 +477,34 @@ int scv_encoder_heads(scv_encoder* E, int32_t B, const float* z, const scv_encod
   SCV_TRY(lin(z, L, E->hp_a, t0, 256, B, ACT_RELU, s, nullptr, 0, z_split));
   SCV_TRY(lin(t0, 256, E->hp_b, sci + c_hp, ld_sc, B, ACT_NONE, s));
   // SC head over the concatenation (:756-766): Linear, GELU, LayerNorm, Linear, GELU, Linear
-  SCV_TRY(lin(sci, ld_sc, E->sc_a, t0, 512, B, ACT_GELU, s));
+  if (ragged_tc) {
+    SCV_TRY(E->scsplit.ensure(split_tile_bytes(B, ld_sc)));
+    SCV_TRY(launch_layernorm_split(sci, ld_sc, nullptr, nullptr, E->scsplit.p, B, ld_sc, 0, nullptr, s));
+    SCV_TRY(lin(sci, ld_sc, E->sc_a, t0, 512, B, ACT_GELU, s, nullptr, 0, E->scsplit.p));
+  } else {
+    SCV_TRY(lin(sci, ld_sc, E->sc_a, t0, 512, B, ACT_GELU, s));
+  }
   SCV_TRY(ln(t0, 512, E->sc_ln, t0, 512, B, ACT_NONE, s));
   SCV_TRY(lin(t0, 512, E->sc_b, t1, 128, B, ACT_GELU, s));
   SCV_TRY(lin(t1, 128, E->sc_c, sc_pred, 1, B, ACT_NONE, s));
   // hierarchical family head on cat[h, sigmoid(sc_pred)] (:256-266)
   sigmoid_col_kernel<<<ceil_div(B, 256), 256, 0, s>>>(sc_pred, 1, cond + bb, ld_cond, B);
   SCV_LAUNCH_CHECK();
-  SCV_TRY(lin(cond, ld_cond, E->co_a, t0, 256, B, ACT_NONE, s));
+  const void* cond_split = nullptr;
+  if (ragged_tc) {
+    SCV_TRY(E->condsplit.ensure(split_tile_bytes(B, ld_cond)));
+    SCV_TRY(launch_layernorm_split(cond, ld_cond, nullptr, nullptr, E->condsplit.p, B, ld_cond, 0, nullptr, s));
+    cond_split = E->condsplit.p;
+  }
+  SCV_TRY(lin(cond, ld_cond, E->co_a, t0, 256, B, ACT_NONE, s, nullptr, 0, cond_split));
   SCV_TRY(ln(t0, 256, E->co_ln, t0, 256, B, ACT_GELU, s));
   SCV_TRY(lin(t0, 256, E->co_b, t1, 128, B, ACT_GELU, s));
   SCV_TRY(lin(t1, 128, E->co_c, coarse, 8, B, ACT_NONE, s));
-  SCV_TRY(lin(cond, ld_cond, E->cu_a, t0, 128, B, ACT_NONE, s));
+  SCV_TRY(lin(cond, ld_cond, E->cu_a, t0, 128, B, ACT_NONE, s, nullptr, 0, cond_split));
   SCV_TRY(ln(t0, 128, E->cu_ln, t0, 128, B, ACT_GELU, s));
   SCV_TRY(lin(t0, 128, E->cu_b, t1, 64, B, ACT_GELU, s));
   SCV_TRY(lin(t1, 64, E->cu_c, cup, 8, B, ACT_NONE, s));
-  SCV_TRY(lin(cond, ld_cond, E->ir_a, t0, 64, B, ACT_NONE, s));
+  SCV_TRY(lin(cond, ld_cond, E->ir_a, t0, 64, B, ACT_NONE, s, nullptr, 0, cond_split));
   SCV_TRY(ln(t0, 64, E->ir_ln, t0, 64, B, ACT_GELU, s));
   SCV_TRY(lin(t0, 64, E->ir_b, iron, 2, B, ACT_NONE, s));
   FinalizeArgs fa;
