@@ -129,8 +129,19 @@ typedef struct scv_forward_args {
   float* out_stop;          /* [batch, L] or NULL */
   float* out_type;          /* [batch, L, 5] or NULL */
   float* out_dup;           /* [batch, L] or NULL; needs the site_dup_head weights */
+  uint32_t flags;           /* SCV_FORWARD_NO_KEY_PADDING: attend PAD inputs like any other key (generation semantics) */
 } scv_forward_args;
+#define SCV_FORWARD_NO_KEY_PADDING 1u
 int scv_decoder_forward(scv_decoder* dec, const scv_forward_args* args, void* stream);
+
+/* The greedy epilogue of generate_with_kv_cache (:1415-1509: type mask, stop boost, hard stop, length boost, / temperature,
+ * first-occurrence argmax) applied to EVERY position of a teacher-forced pass at once (draft verification):
+ * row r = (sequence r / seq_len, position r % seq_len).  logits [R, vocab], type_logits [R, 5] or NULL (then type_masks is
+ * ignored), stop_logits [R] or NULL (then stop_boost is ignored), type_masks [5, vocab] bytes or NULL, finished_before [R]
+ * bytes (1 = the sequence emitted END at an earlier position: no hard stop), out_tokens [R]. */
+int scv_greedy_positions(const float* logits, const float* type_logits, const float* stop_logits, const uint8_t* type_masks,
+                         const uint8_t* finished_before, int64_t n_rows, int32_t seq_len, int32_t vocab, int32_t max_len,
+                         float temperature, float stop_boost, float hard_stop_threshold, int64_t* out_tokens, void* stream);
 
 /* Debug taps (tests): copy engine-internal fp32 state of the LAST executed step to `dst`.
  * what: 0 final hidden [B,d]; 1 raw logits [B,V]; 2 type logits [B,5]; 3 stop logit [B] */

@@ -42,7 +42,7 @@ class ForwardArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("seq_len", C.c_int32), ("n_memory", C.c_int32), ("memory", C.c_void_p),
         ("tokens", C.c_void_p), ("ld_tokens", C.c_int32), ("out_logits", C.c_void_p), ("out_stop", C.c_void_p),
-        ("out_type", C.c_void_p), ("out_dup", C.c_void_p)]
+        ("out_type", C.c_void_p), ("out_dup", C.c_void_p), ("flags", C.c_uint32)]
 
 
 class EncoderConfig(C.Structure):
@@ -95,6 +95,7 @@ class EncoderHeadsOut(C.Structure):
 FLAG_H2_UNIFORM_FALLBACK = 1
 FLAG_SYNC_EVERY_STEP = 2
 FLAG_COMPACT_FINISHED = 4
+FORWARD_NO_KEY_PADDING = 1
 
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test walks
 SIGNATURES = {
@@ -126,6 +127,8 @@ SIGNATURES = {
     "scv_slerp_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "scv_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scv_greedy_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "scv_tokens_canonical_hash": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "scv_element_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

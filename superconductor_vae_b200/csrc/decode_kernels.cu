@@ -6,6 +6,7 @@
 
 #include <cstdlib>
 
+#include "../../include/scvae_b200.h"
 #include "decode_kernels.cuh"
 #include "sampler_device.cuh"
 
@@ -976,6 +977,63 @@ int launch_step_end(StepState* st, int max_steps, cudaStream_t s) {
   SCV_LAUNCH_CHECK();
   return 0;
 }
+
+// Greedy epilogue over every position of a teacher-forced pass (scv_greedy_positions): one warp per (sequence, position)
+// row; step = position.  Same per-element arithmetic as the decode's greedy sampler (adjust_logit, / temperature,
+// first-occurrence argmax with NaN as maximum); nothing is committed, the chosen ids go to out_tokens.
+__global__ void __launch_bounds__(256) greedy_positions_kernel(SamplerArgs a, int seq_len, long long n_rows, int vec_ok,
+                                                               long long* __restrict__ out_tokens) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int step = (int)(r % seq_len);
+  int tok;
+  if (vec_ok) {
+    tok = greedy_row_token(a, (int)r, step, lane);
+  } else {
+    const RowCtx c = make_row_ctx(a, (int)r, step);
+    const float* lg = a.logits + (size_t)r * a.ldl;
+    float bv = -INFINITY;
+    int bi = INT_MAX;
+    for (int v = lane; v < a.V; v += 32) {
+      float l = adjust_logit(c, v, lg[v], c.mk != nullptr ? c.mk[v] : 1u, 0u);
+      if (a.temperature != 1.0f) l = l / a.temperature;
+      if (arg_better(l, v, bv, bi)) { bv = l; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    tok = bi;
+  }
+  if (lane == 0) out_tokens[r] = tok;
+}
+
+}  // namespace scv
+
+extern "C" int scv_greedy_positions(const float* logits, const float* type_logits, const float* stop_logits, const uint8_t* type_masks,
+                                    const uint8_t* finished_before, int64_t n_rows, int32_t seq_len, int32_t vocab, int32_t max_len,
+                                    float temperature, float stop_boost, float hard_stop_threshold, int64_t* out_tokens, void* stream) {
+  using namespace scv;
+  SCV_REQUIRE(logits && finished_before && out_tokens && n_rows > 0 && seq_len > 0 && vocab > kEndIdx, "greedy_positions: bad arguments");
+  SCV_REQUIRE(n_rows < (1ll << 31), "greedy_positions: %lld rows (at most 2^31 - 1)", (long long)n_rows);
+  SamplerArgs a;
+  a.logits = logits; a.ldl = vocab; a.type_logits = type_logits; a.ldt = 5; a.stop_logits = stop_logits;
+  a.type_masks = type_logits != nullptr ? type_masks : nullptr;
+  a.B = (int)n_rows; a.V = vocab; a.max_len = max_len; a.temperature = temperature;
+  a.stop_boost = stop_logits != nullptr ? stop_boost : 0.f; a.hard_stop = hard_stop_threshold;
+  a.finished = const_cast<unsigned char*>(finished_before);
+  const int vec_ok = vocab % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.type_masks) & 3u) == 0;
+  const long long blocks = (n_rows + 7) / 8;
+  greedy_positions_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, seq_len, n_rows, vec_ok,
+                                                                                            reinterpret_cast<long long*>(out_tokens));
+  SCV_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace scv {
 
 __global__ void host_gate_kernel(volatile int* flag) {
   // bounded wait (50 ms): if the host ever blocked in a launch call while the gate is closed, the gate opens by itself

@@ -1107,7 +1107,8 @@ int scv_decoder_forward(scv_decoder* D, const scv_forward_args* A, void* stream)
     AttnArgs sa;
     sa.q = qkv; sa.ldq = 3 * d; sa.kcache = qkv + d; sa.vcache = qkv + 2 * d; sa.seq_stride = (long long)L * 3 * d;
     sa.row_stride = 3 * d; sa.out = attn; sa.ldo = d; sa.B = R; sa.nhead = c.nhead; sa.hd = hd; sa.scale = scale;
-    sa.fixed_len = -1; sa.rows_per_seq = L; sa.key_skip = skip; sa.max_n = std::max(L, M); sa.host_len_hint = (L + 1) / 2;
+    sa.fixed_len = -1; sa.rows_per_seq = L; sa.key_skip = (A->flags & SCV_FORWARD_NO_KEY_PADDING) ? nullptr : skip;
+    sa.max_n = std::max(L, M); sa.host_len_hint = (L + 1) / 2;
     sa.out_split = static_cast<unsigned char*>(attn_s); sa.kb_out = d / 64;
     SCV_TRY(launch_attention(sa, s));
     LinearArgs o = lin_args(attn, d, Lr.sa_out, x, d, R, ACT_NONE);

@@ -225,8 +225,9 @@ class EnhancedTransformerDecoder(nn.Module):
             logits, stop, typ, dup = self._forward_pass(memory, mixed_inputs)                   # pass 2 (:1058-1082)
             return logits, logits.argmax(dim=-1), stop, typ, dup
 
-    def _forward_pass(self, memory: torch.Tensor, inputs: torch.Tensor, heads: bool = True):
-        """One parallel pass of the layer stack over ``inputs`` [B, L] (PAD inputs are masked as keys, :952)."""
+    def _forward_pass(self, memory: torch.Tensor, inputs: torch.Tensor, heads: bool = True, key_padding: bool = True):
+        """One parallel pass of the layer stack over ``inputs`` [B, L] (PAD inputs are masked as keys, :952, unless
+        ``key_padding=False``: generation attends every earlier position)."""
         L = _lib.lib()
         device = memory.device
         B, M, seq = memory.size(0), memory.size(1), inputs.size(1)
@@ -237,7 +238,8 @@ class EnhancedTransformerDecoder(nn.Module):
         dup = torch.empty((B, seq), dtype=torch.float32, device=device) if has_dup else None
         args = _lib.ForwardArgs(batch=B, seq_len=seq, n_memory=M, memory=_lib.ptr(memory), tokens=_lib.ptr(inputs),
                                 ld_tokens=inputs.size(1), out_logits=_lib.ptr(logits), out_stop=_lib.ptr(stop),
-                                out_type=_lib.ptr(typ), out_dup=_lib.ptr(dup))
+                                out_type=_lib.ptr(typ), out_dup=_lib.ptr(dup),
+                                flags=0 if key_padding else _lib.FORWARD_NO_KEY_PADDING)
         with torch.cuda.device(device):
             _lib.check(L.scv_decoder_forward(self._engine, C.byref(args), _lib.current_stream()), "forward")
         return logits, stop, typ, dup
@@ -446,6 +448,87 @@ class EnhancedTransformerDecoder(nn.Module):
             gen = tokens[:, :steps_done].contiguous()
             return (gen, lps[:, :steps_done].contiguous() if lps is not None else None,
                     ents[:, :steps_done].contiguous() if ents is not None else None)
+
+    def generate_with_draft(self, z, draft_tokens, encoder_skip=None, stoich_pred=None, temperature: float = 0.001,
+                            max_len: Optional[int] = None, cached_memory: Optional[torch.Tensor] = None,
+                            stop_boost: float = 0.0, hard_stop_threshold: float = 0.0,
+                            heads_pred: Optional[Dict[str, torch.Tensor]] = None, type_masks: Optional[torch.Tensor] = None,
+                            max_passes: int = 4) -> Tuple[torch.Tensor, int, int]:
+        """Greedy decoding by DRAFT VERIFICATION (replaces the reference's disabled n-gram speculative
+        sampler, models/autoregressive_decoder.py:1643-1984): instead of one dependent step per token, every position of a
+        drafted sequence is checked in ONE teacher-forced pass (the f3 engine pass with generation's attention semantics
+        + the decode's greedy epilogue at every position).  If the pass reproduces the draft up to its END the row is done;
+        otherwise the pass's own predictions become the next draft (a Jacobi / fixed-point iteration: the correct prefix
+        grows by at least one token per pass, so the result is EXACTLY the greedy sequence however bad the draft is).
+        Rows that have not converged after ``max_passes`` are finished by the ordinary KV-cache decode.
+
+        ``draft_tokens`` [B, <= max_len - 1] are z-conditioned guesses, e.g. the sequence decoded for a neighbouring
+        latent of a SLERP walk, or the previous epoch's greedy sequence of the same sample (both differ from the true
+        sequence in a few positions at most); shorter drafts are padded.  Greedy only (``temperature < 0.01``).
+        Returns ``(tokens [B, L], n_passes, n_fallback_rows)``: identical to ``generate_with_kv_cache`` up to and including
+        each row's first END, PAD after it (like ``compact_finished``)."""
+        if not (0.0 < temperature < 0.01):
+            raise ValueError("generate_with_draft is greedy decoding: 0 < temperature < 0.01 (the reference's argmax branch)")
+        self.eval()
+        max_len = min(max_len or self.max_len, self.pos_encoding.pe.shape[1])
+        with torch.no_grad():
+            L_ = self._sync_engine()
+            memory = self._checked_memory(cached_memory) if cached_memory is not None else \
+                self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
+            device = memory.device
+            B, steps = memory.size(0), max_len - 1
+            if steps < 1:
+                raise RuntimeError("max_len leaves no decoding step")
+            masks_u8 = None
+            if type_masks is not None:
+                masks_u8 = type_masks.to(device=device).to(torch.uint8).contiguous()
+                if tuple(masks_u8.shape) != (N_TOKEN_TYPES, self.vocab_size):
+                    raise RuntimeError(f"type_masks must be [{N_TOKEN_TYPES}, {self.vocab_size}], got {tuple(masks_u8.shape)}")
+            draft = draft_tokens.to(device=device, dtype=torch.int64)
+            if draft.dim() != 2 or draft.size(0) != B:
+                raise RuntimeError(f"draft_tokens must be [{B}, <= {steps}], got {tuple(draft.shape)}")
+            cur = torch.zeros((B, steps), dtype=torch.int64, device=device)
+            n = min(steps, draft.size(1))
+            cur[:, :n] = draft[:, :n].clamp(0, self.vocab_size - 1)
+            start = torch.full((B, 1), START_IDX, dtype=torch.int64, device=device)
+            pos = torch.arange(steps, device=device).unsqueeze(0)
+            pred = cur
+            done = torch.zeros(B, dtype=torch.bool, device=device)
+            passes = 0
+            while passes < max(1, int(max_passes)):
+                passes += 1
+                inputs = torch.cat([start, cur[:, :-1]], dim=1).contiguous()
+                logits, stop, typ, _ = self._forward_pass(memory, inputs, key_padding=False)
+                is_end = cur == END_IDX
+                fin_before = ((torch.cumsum(is_end.to(torch.int32), dim=1) - is_end.to(torch.int32)) > 0).to(torch.uint8).contiguous()
+                pred = torch.empty((B, steps), dtype=torch.int64, device=device)
+                with torch.cuda.device(device):
+                    _lib.check(L_.scv_greedy_positions(
+                        _lib.ptr(logits), _lib.ptr(typ) if masks_u8 is not None else None,
+                        _lib.ptr(stop) if stop_boost > 0 else None, _lib.ptr(masks_u8), _lib.ptr(fin_before), B * steps, steps,
+                        self.vocab_size, max_len, float(temperature), float(stop_boost), float(hard_stop_threshold),
+                        _lib.ptr(pred), _lib.current_stream()), "greedy_positions")
+                # a row has converged when the pass reproduces its own inputs up to and including its first END
+                p_end = pred == END_IDX
+                first_end = torch.where(p_end.any(dim=1), p_end.int().argmax(dim=1), torch.full((B,), steps - 1, device=device))
+                live = pos <= first_end.unsqueeze(1)
+                done = ((pred == cur) | ~live).all(dim=1)
+                cur = pred
+                if bool(done.all()):
+                    break
+            tokens = pred.clone()
+            rest = (~done).nonzero().flatten()
+            if rest.numel() > 0:                      # drafts too far off: finish those rows step by step
+                t_, _, _ = self.generate_with_kv_cache(None, temperature=temperature, max_len=max_len,
+                                                       cached_memory=memory[rest].contiguous(), stop_boost=stop_boost,
+                                                       hard_stop_threshold=hard_stop_threshold, type_masks=type_masks)
+                tokens[rest] = 0
+                tokens[rest, :t_.shape[1]] = t_
+            t_end = tokens == END_IDX
+            after = (torch.cumsum(t_end.to(torch.int32), dim=1) - t_end.to(torch.int32)) > 0
+            tokens.masked_fill_(after, PAD_IDX)
+            ends = torch.where(t_end.any(dim=1), t_end.int().argmax(dim=1) + 1, torch.full((B,), steps, device=device))
+            return tokens[:, :int(ends.max())].contiguous(), passes, int(rest.numel())
 
     def sample_for_reinforce(self, z, encoder_skip=None, stoich_pred=None, temperature: float = 0.8,
                              max_len: Optional[int] = None, cached_memory: Optional[torch.Tensor] = None,

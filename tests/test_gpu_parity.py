@@ -546,6 +546,43 @@ def test_scheduled_sampling_forward_matches_reference(golden_dir, name, shape):
     assert a.shape == c["logits"].shape and torch.equal(a, b)
 
 
+# ------------------------------------------------------------------------------------------ draft verification (f4)
+@pytest.mark.parametrize("name", ["tiny", "c512_b32"])
+def test_generate_with_draft_is_exactly_greedy(golden_dir, name):
+    """greedy decoding by draft verification (one teacher-forced pass checks every position; wrong positions
+    are replaced by the pass's own predictions and re-checked) returns exactly the tokens of the step-by-step decode - the
+    reference goldens - whatever the draft: the true sequence (1 pass), the true sequence with corrupted positions, pure
+    garbage (converges within L passes), and garbage with a 2-pass budget (unconverged rows fall back to the KV-cache decode)."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, name)
+    kw = dict(stoich_pred=_cuda(stoich), max_len=shape.max_len, heads_pred=_cuda(heads), type_masks=_cuda(masks),
+              stop_boost=10.0, hard_stop_threshold=0.8)
+    ref, _, _ = dec.generate_with_kv_cache(_cuda(z), temperature=0.001, **kw)
+    assert torch.equal(ref.cpu().to(torch.int16), g["greedy_masked_tokens"])
+    is_end = ref == 2
+    after = (torch.cumsum(is_end.int(), dim=1) - is_end.int()) > 0
+    want = ref.masked_fill(after, 0)                                   # PAD after each row's first END
+
+    def check(draft, max_passes):
+        t, passes, fallback = dec.generate_with_draft(_cuda(z), draft, max_passes=max_passes, **kw)
+        assert t.shape[1] <= want.shape[1] and torch.equal(t, want[:, :t.shape[1]]) and int(want[:, t.shape[1]:].abs().sum()) == 0
+        return passes, fallback
+    assert check(ref, 4) == (1, 0)                                     # a correct draft is accepted in one pass
+    gen = torch.Generator().manual_seed(3)
+    bad = ref.clone().cpu()
+    for r in range(bad.shape[0]):                                      # two wrong tokens per row
+        for p in torch.randint(0, bad.shape[1], (2,), generator=gen).tolist():
+            bad[r, p] = int(torch.randint(3, shape.vocab_size, (1,), generator=gen))
+    passes, fallback = check(bad.to(DEV), shape.max_len)
+    assert fallback == 0 and passes <= shape.max_len - 1
+    garbage = torch.randint(3, shape.vocab_size, tuple(ref.shape), generator=gen).to(DEV)
+    passes, fallback = check(garbage, shape.max_len)
+    assert fallback == 0
+    passes, fallback = check(garbage, 2)
+    assert passes == 2 and fallback > 0
+    with pytest.raises(ValueError):
+        dec.generate_with_draft(_cuda(z), ref, temperature=1.0, **kw)
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_config2_4096_latents_properties(golden_dir):
     """BASELINE config 2 at full size (4096 latents, masks + stop head, greedy): bit-exact vs the oracle on the
