@@ -719,18 +719,34 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_phase1_kernel(Sampler
 // Plain greedy decoding (temperature < 0.01, no entropy): one warp per row, no staging -- the adjusted logits are
 // consumed as they stream in (16-byte loads, 4 mask bytes at a time) and only the running argmax is kept.  Same
 // per-element arithmetic as phase 1 above (adjust, / temperature, first-occurrence argmax with NaN as maximum).
+// Four warps per row (two rows per CTA): a row's 19 KB of logits is ten dependent rounds of loads for one warp; dealt to
+// four warps the rounds run side by side (the logits sit in L2, the kernel is load-latency bound) and the warps' candidates
+// are merged with the same first-occurrence rule.
+constexpr int kGreedyWarpsPerRow = 4;
 __global__ void __launch_bounds__(256) sampler_greedy_kernel(SamplerArgs a) {
+  __shared__ float cand_v[8];
+  __shared__ int cand_i[8];
   pdl_wait();
   if (a.st->done) return;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= a.B) return;
-  if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (8 / kGreedyWarpsPerRow) + warp / kGreedyWarpsPerRow, part = warp % kGreedyWarpsPerRow;
+  const bool live = b < a.B && !(a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]);
   const int step = a.st->step;
-  const int tok = greedy_row_token(a, b, step, lane);
+  float best = -INFINITY;
+  int tok = INT_MAX;
+  if (live) tok = greedy_row_token(a, b, step, lane, part, kGreedyWarpsPerRow, &best);
+  if (lane == 0) { cand_v[warp] = best; cand_i[warp] = tok; }
+  __syncthreads();
   if (threadIdx.x == 0) pdl_launch_dependents();
   // (the batch-global degenerate flag, :1464-1466, only changes how probabilities are sampled; argmax ignores it,
   // and with a type mask every row would hit the same atomic: 4096 serialised updates cost ~75 us per step)
-  if (lane == 0) commit_token(a, b, step, tok, 0.f);            // (:1507)
+  if (live && part == 0 && lane == 0) {
+    float bv = cand_v[warp];
+    int bi = cand_i[warp];
+    for (int w = 1; w < kGreedyWarpsPerRow; ++w)
+      if (arg_better(cand_v[warp + w], cand_i[warp + w], bv, bi)) { bv = cand_v[warp + w]; bi = cand_i[warp + w]; }
+    commit_token(a, b, step, bi, 0.f);                          // (:1507)
+  }
 }
 
 // Phase 2: entropy, temperature, multinomial (or argmax) and log-prob, given the batch-global flag.
@@ -948,7 +964,7 @@ int launch_sampler(const SamplerArgs& a_in, int which, cudaStream_t s) {
   const bool vec_ok = a.V % 4 == 0 && a.ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15u) == 0 &&
                       (reinterpret_cast<uintptr_t>(a.type_masks) & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.seen) & 3u) == 0;
   if (which == 1 && !two_phase && vec_ok) {
-    SCV_CUDA(launch_k(sampler_greedy_kernel, dim3(ceil_div(a.B, 8)), dim3(256), 0, s, a));
+    SCV_CUDA(launch_k(sampler_greedy_kernel, dim3(ceil_div(a.B, 8 / kGreedyWarpsPerRow)), dim3(256), 0, s, a));
     SCV_LAUNCH_CHECK();
   } else if (which == 1) {
     SCV_CUDA(launch_k(sampler_phase1_kernel, dim3(a.B), dim3(kSamplerThreads), smem, s, a, two_phase ? 0 : 1));

@@ -83,7 +83,10 @@ __device__ __forceinline__ int commit_token(const SamplerArgs& a, int b, int ste
 
 // Plain greedy choice of row b (temperature < 0.01, no entropy): one warp per row, 16-byte loads, the adjustments
 // applied per element, running first-occurrence argmax.  Every lane returns the token.
-__device__ __forceinline__ int greedy_row_token(const SamplerArgs& a, int b, int step, int lane) {
+// part / nparts: the row's vocabulary is dealt to nparts warps in interleaved blocks of 512 ids; best_out (optional)
+// receives the value of the returned id so that the warps' candidates can be merged with arg_better.
+__device__ __forceinline__ int greedy_row_token(const SamplerArgs& a, int b, int step, int lane, int part = 0, int nparts = 1,
+                                                float* best_out = nullptr) {
   const RowCtx c = make_row_ctx(a, b, step);
   const float4* lg = reinterpret_cast<const float4*>(a.logits + (size_t)b * a.ldl);
   const uint32_t* mk4 = reinterpret_cast<const uint32_t*>(c.mk);
@@ -93,7 +96,7 @@ __device__ __forceinline__ int greedy_row_token(const SamplerArgs& a, int b, int
   int bi = INT_MAX;
   const int n4 = a.V >> 2;
   constexpr int UNR = 4;
-  for (int i0 = lane; i0 < n4; i0 += 32 * UNR) {
+  for (int i0 = lane + 32 * UNR * part; i0 < n4; i0 += 32 * UNR * nparts) {
     float4 x[UNR];
     uint32_t m[UNR], sn[UNR];
 #pragma unroll
@@ -125,6 +128,7 @@ __device__ __forceinline__ int greedy_row_token(const SamplerArgs& a, int b, int
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
   }
+  if (best_out != nullptr) *best_out = bv;
   return bi;
 }
 
