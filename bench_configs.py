@@ -75,6 +75,17 @@ def main():
                           "entropy and mask (stop_boost 10, no hard masks so the reference's H2 fallback cannot trip)",
                           "rows": B * k, "executed_decode_steps": int(t.shape[1]), "ms": ms,
                           "formulas_per_s": B * k / (ms / 1e3), "mean_len": float(mk.sum(1).mean())}))
+        # the same rollouts with the k samples of a latent sharing its memory tokens inside the engine (_n_samples):
+        # identical outputs (tests/test_gpu_parity.py), the projected memory K / V are built and streamed once per latent
+        zb, stb = Sy.make_latents(B, 2048, 1234).to(dev), Sy.make_conditioning(B, 13, 1234)[0].to(dev)
+        hpb = {n: v.to(dev) for n, v in Sy.make_conditioning(B, 13, 1234)[1].items()}
+        fn2 = lambda: dec.sample_for_reinforce(zb, stoich_pred=stb, temperature=1.2, max_len=64, stop_boost=10.0,
+                                               heads_pred=hpb, _seed=7, _n_samples=k)
+        ms2, (t2, _, _, _) = timed(fn2)
+        emit(({"config": "3-shared", "what": "the same RLOO rollouts through `_n_samples=4`: base batch in, the 4 samples of a "
+               "latent share its memory tokens and their projected K / V (scv_generate_args.memory_rows)", "rows": B * k,
+               "executed_decode_steps": int(t2.shape[1]), "ms": ms2, "formulas_per_s": B * k / (ms2 / 1e3),
+               "same_tokens_as_repeated_inputs": bool(torch.equal(t, t2))}))
         # f1: the token-level reward of those rollouts (compute_reward_gpu_native, V14 continuous reward + semantic
         # fraction values, as scripts/train_v12_clean.py:2745-2752 calls it): one kernel
         from superconductor_vae_b200 import reward as R

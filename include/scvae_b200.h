@@ -109,6 +109,10 @@ typedef struct scv_generate_args {
   float* out_entropy;      /* same shape or NULL */
   int32_t* out_steps;      /* HOST: number of executed steps L (columns >= L are not written) */
   const int64_t* forced_tokens; /* optional [batch, max_len-1]: teacher-forced replay (tests) */
+  int32_t memory_rows;     /* 0: `memory` has `batch` rows.  B0 > 0: `memory` has B0 rows and row r of the batch is conditioned on
+                              memory row r % B0 - the reference's RLOO layout, z.repeat(k, 1) (scripts/train_v12_clean.py:2677-2688),
+                              without materialising the k copies: the projected memory K / V are built once per latent and the
+                              k samples of a latent read the same K / V.  batch % B0 == 0, batch > 64. */
 } scv_generate_args;
 
 /* Enqueues the decode loop and synchronises `stream` once at the end to read *out_steps. */

@@ -35,7 +35,7 @@ class GenerateArgs(C.Structure):
         ("type_masks", C.c_void_p), ("want_log_probs", C.c_int32), ("want_entropy", C.c_int32),
         ("flags", C.c_uint32), ("seed", C.c_uint64), ("offset", C.c_uint64),
         ("out_tokens", C.c_void_p), ("out_log_probs", C.c_void_p), ("out_entropy", C.c_void_p),
-        ("out_steps", C.POINTER(C.c_int32)), ("forced_tokens", C.c_void_p)]
+        ("out_steps", C.POINTER(C.c_int32)), ("forced_tokens", C.c_void_p), ("memory_rows", C.c_int32)]
 
 
 class ForwardArgs(C.Structure):

@@ -228,19 +228,23 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   // another sub-batch's stream to run beside it ("co-residency").
   const int n_items = a.B * a.nhead, wpb = blockDim.x >> 5;
   TraceRec* trc = threadIdx.x == 0 ? trace_begin(a.trace, a.fixed_len >= 0 ? 2u : 1u) : nullptr;
+  // shared memory tokens: when the launch holds whole groups of seq_mod rows, item i is sample i % k of latent i / k
+  const int k_local = (a.seq_mod > 0 && a.row_map == nullptr && a.B % a.seq_mod == 0 && a.slot_base % a.seq_mod == 0) ? a.B / a.seq_mod : 0;
   for (int gw = blockIdx.x * wpb + warp_in_block; gw < n_items; gw += gridDim.x * wpb) {
-  const int b = gw / a.nhead, h = gw % a.nhead;
+  const int bi = gw / a.nhead, h = gw % a.nhead;
+  const int b = k_local > 1 ? (bi % k_local) * a.seq_mod + bi / k_local : bi;
   const int hd = a.hd;
   if (a.row_map != nullptr && a.slot_base + b >= a.st->pad[1]) continue;       // slot of a finished row (compaction)
   // sequence whose K / V this query row attends to
-  const int sb = a.row_map != nullptr ? a.row_map[a.slot_base + b] : (a.rows_per_seq > 0 ? b / a.rows_per_seq : b);
+  int sb = a.row_map != nullptr ? a.row_map[a.slot_base + b] : (a.rows_per_seq > 0 ? b / a.rows_per_seq : b);
+  if (a.seq_mod > 0) sb = (a.row_map != nullptr ? sb : a.slot_base + b) % a.seq_mod;
   const int n = a.fixed_len >= 0 ? a.fixed_len : (a.rows_per_seq > 0 ? b - sb * a.rows_per_seq + 1 : a.st->step + 1);
   float* sc = sc_all + (size_t)warp_in_block * a.max_n;
   const int grp = lane / LPP, e0 = 4 * (lane % LPP);
   const bool e_ok = e0 < hd;
 
   const bool paged = a.page_table != nullptr;
-  const int* pt = paged ? a.page_table + (size_t)(a.row_map != nullptr ? sb : b) * a.pages_per_seq : nullptr;
+  const int* pt = paged ? a.page_table + (size_t)(a.row_map != nullptr ? a.row_map[a.slot_base + b] : b) * a.pages_per_seq : nullptr;
   auto row_off = [&](int p) -> size_t {
     if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
     return (size_t)sb * a.seq_stride + (size_t)p * a.row_stride + h * hd;
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(256, 1) attention_cross_bulk_kernel(AttnArgs a
 
 // bytes of dynamic shared memory of the bulk kernel, or 0 when the shape does not fit two stages
 static size_t cross_bulk_smem(const AttnArgs& a, int warps) {
-  if (a.fixed_len < 0 || a.page_table != nullptr || a.rows_per_seq != 0 || a.key_skip != nullptr || a.row_map != nullptr) return 0;
+  if (a.fixed_len < 0 || a.page_table != nullptr || a.rows_per_seq != 0 || a.key_skip != nullptr || a.row_map != nullptr || a.seq_mod != 0) return 0;
   const size_t kv = (size_t)a.fixed_len * a.row_stride * sizeof(float), q = (size_t)a.nhead * a.hd * sizeof(float);
   if (a.seq_stride != (long long)a.fixed_len * a.row_stride) return 0;                  // one contiguous block per sequence
   if (a.vcache - a.kcache <= 0 || a.vcache - a.kcache >= a.row_stride) return 0;        // V inside the token's row
@@ -583,6 +587,7 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   ProfScope prof(a.fixed_len >= 0 ? PC_ATTN_CROSS : PC_ATTN_SELF, s, 4.0 * a.B * a.nhead * a.hd * n_hint,
                  4.0 * a.B * a.nhead * a.hd * (2.0 * n_hint + 2.0 + (a.knew ? 4.0 : 0.0)));
   SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
+  SCV_REQUIRE(a.seq_mod == 0 || v4, "attention: shared memory tokens need head_dim %% 4 == 0 and 16-byte aligned rows");
   SCV_REQUIRE(a.row_map == nullptr || v4, "attention: compaction of finished rows needs head_dim %% 4 == 0 and 16-byte aligned rows");
   const size_t bulk_smem = (v4 && tun().attn_bulk != 0 && a.B >= tun().attn_bulk_min_rows) ? cross_bulk_smem(a, warps) : 0;
   if (bulk_smem != 0) {

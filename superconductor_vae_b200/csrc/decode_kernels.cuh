@@ -58,6 +58,9 @@ struct AttnArgs {
   // compaction of finished rows: query row b is slot slot_base + b; its sequence (page table row, projected memory) is
   // row_map[slot]; page_table / kcache / vcache are then NOT offset to the sub-batch
   const int* row_map = nullptr; int slot_base = 0;
+  // shared memory tokens (RLOO): the sequence of query row r is (slot_base + r) % seq_mod (0 = off); the launch's rows
+  // are walked so that the samples of one latent are adjacent (they then hit the same K / V in L2)
+  int seq_mod = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 

@@ -45,12 +45,12 @@ constexpr int kMaxSub = 4;
 
 // Everything that is baked into the kernel arguments of one decode step.
 struct GraphKey {
-  int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced, prof;
+  int B, M, steps_max, n_sub, top_k, has_masks, want_lp, want_ent, has_forced, prof, mem_rows;
   unsigned flags;
   float temperature, top_p, stop_boost, hard_stop, site_dup;
   bool operator==(const GraphKey& o) const {
     return B == o.B && M == o.M && steps_max == o.steps_max && n_sub == o.n_sub && top_k == o.top_k &&
-           has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced && prof == o.prof &&
+           has_masks == o.has_masks && want_lp == o.want_lp && want_ent == o.want_ent && has_forced == o.has_forced && prof == o.prof && mem_rows == o.mem_rows &&
            flags == o.flags && temperature == o.temperature && top_p == o.top_p && stop_boost == o.stop_boost &&
            hard_stop == o.hard_stop && site_dup == o.site_dup;
   }
@@ -346,7 +346,8 @@ static bool use_tensor_cores(const scv_decoder_config& c, int B) {
          c.vocab_size % 4 == 0 && c.d_model <= 1024;
 }
 
-static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = false) {
+static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = false, int Bm = 0) {
+  if (Bm <= 0) Bm = B;                               // rows of the memory (fewer than B when RLOO samples share it)
   const scv_decoder_config& c = D->cfg;
   const size_t d = c.d_model, f = sizeof(float);
   const int pps = ceil_div(c.pe_len, kPagePos);
@@ -362,7 +363,7 @@ static int ensure_workspace(scv_decoder* D, int B, int M, bool need_site_dup = f
   SCV_TRY(D->logits.ensure((size_t)B * c.vocab_size * f));
   SCV_TRY(D->tlog.ensure((size_t)B * 8 * f));
   SCV_TRY(D->slog.ensure((size_t)B * f));
-  SCV_TRY(D->ckv.ensure((size_t)c.num_layers * B * M * 2 * d * f));
+  SCV_TRY(D->ckv.ensure((size_t)c.num_layers * Bm * M * 2 * d * f));
   SCV_TRY(D->kvpool.ensure((size_t)B * pps * c.num_layers * 2 * kPagePos * d * f));
   SCV_TRY(D->cur.ensure((size_t)B * sizeof(int)));
   SCV_TRY(D->fin.ensure((size_t)B));
@@ -533,7 +534,7 @@ static int build_cluster_program(scv_decoder* D, const scv_generate_args* A, int
   const scv_decoder_config& c = D->cfg;
   D->cl_active = false;
   const int d = c.d_model, hd = d / c.nhead, dff = c.dim_feedforward, V = c.vocab_size, pps = ceil_div(c.pe_len, kPagePos);
-  if (tun().cluster == 0 || B > tun().cluster_max_rows || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
+  if (A->memory_rows > 0 || tun().cluster == 0 || B > tun().cluster_max_rows || prof_enabled() || (A->flags & SCV_FLAG_SYNC_EVERY_STEP)) return 0;
   if (!cluster_shape_ok(d, c.nhead, dff, V, c.pe_len, M)) return 0;
   // Clusters that can be resident at once (8 CTAs of ~200 KB each inside one GPC: 15-16 on a B200); all of a decode's
   // clusters should run together (a late cluster is still decoded correctly, just later), so R is the smallest rows-per-
@@ -767,12 +768,13 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
     SCV_TRY(launch_linear(q, 0, s));
     AttnArgs ca;
     ca.q = q2; ca.ldq = d;
-    float* ckv = D->ckv.as<float>() + ((size_t)li * Bfull + ob) * M * 2 * d;
+    const int Bm = A->memory_rows > 0 ? A->memory_rows : Bfull;          // rows of the projected memory (RLOO samples share it)
+    float* ckv = D->ckv.as<float>() + ((size_t)li * Bm + (A->memory_rows > 0 ? 0 : ob)) * M * 2 * d;
     ca.kcache = ckv; ca.vcache = ckv + d; ca.seq_stride = (long long)M * 2 * d; ca.row_stride = 2 * d;
     ca.out = attn; ca.ldo = d; ca.B = B; ca.nhead = c.nhead; ca.hd = hd; ca.scale = scale;
     ca.fixed_len = M; ca.max_n = std::max(c.pe_len, M); ca.st = st;
     ca.out_split = static_cast<unsigned char*>(attn_s); ca.kb_out = d / 64;
-    ca.row_map = row_map; ca.slot_base = r0;
+    ca.row_map = row_map; ca.slot_base = r0; ca.seq_mod = A->memory_rows > 0 ? A->memory_rows : 0;
     SCV_TRY(launch_attention(ca, s));
     LinearArgs co = lin_args(attn, d, L.ca_out, x, d, B, ACT_NONE, done);
     co.residual = x; co.ldr = d; co.a_split = attn_s;
@@ -844,7 +846,10 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   SCV_REQUIRE(steps_max >= 1, "generate: max_len %d leaves no step to run", A->max_len);
   const int B = A->batch, M = A->n_memory, d = c.d_model;
   set_pdl_for_call(true);
-  SCV_TRY(ensure_workspace(D, B, M, A->site_dup_threshold > 0.f));
+  const int Bm = A->memory_rows > 0 ? A->memory_rows : B;
+  SCV_REQUIRE(A->memory_rows == 0 || (B % A->memory_rows == 0 && B > 64 && B > A->memory_rows),
+              "generate: memory_rows %d needs batch %d to be a larger multiple of it (and > 64 rows)", A->memory_rows, B);
+  SCV_TRY(ensure_workspace(D, B, M, A->site_dup_threshold > 0.f, Bm));
   StepState* st = D->state.as<StepState>();
   const bool want_compact = (A->flags & SCV_FLAG_COMPACT_FINISHED) != 0;
   SCV_TRY(launch_init_rows(D->cur.as<int>(), D->fin.as<unsigned char>(), B, st, A->seed, A->offset, s,
@@ -875,17 +880,17 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // (the reference re-projects them inside nn.MultiheadAttention at every step, :1302-1307)
   void* mem_split = nullptr;
   if (use_tensor_cores(c, B)) {      // split the memory tokens once instead of once per layer and column tile
-    SCV_TRY(D->msplit.ensure(split_tile_bytes(B * M, d)));
+    SCV_TRY(D->msplit.ensure(split_tile_bytes(Bm * M, d)));
     mem_split = D->msplit.p;
-    SCV_TRY(launch_layernorm_split(A->memory, d, nullptr, nullptr, mem_split, B * M, d, 0, nullptr, s));
+    SCV_TRY(launch_layernorm_split(A->memory, d, nullptr, nullptr, mem_split, Bm * M, d, 0, nullptr, s));
   }
   for (int li = 0; li < c.num_layers; ++li) {
     const DecLayer& L = D->layers[li];
     LinearArgs a;
     a.a_split = mem_split;
     a.x = A->memory; a.ldx = d; a.w = L.ca_in_w + (size_t)d * L.ca_in_ld; a.ldw = L.ca_in_ld; a.wt = L.ca_kv_wt;
-    a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * B * M * 2 * d; a.ldy = 2 * d;
-    a.M = B * M; a.N = 2 * d; a.K = d;
+    a.bias = L.ca_in_b + d; a.y = D->ckv.as<float>() + (size_t)li * Bm * M * 2 * d; a.ldy = 2 * d;
+    a.M = Bm * M; a.N = 2 * d; a.K = d;
     SCV_TRY(launch_linear(a, 0, s));
   }
   D->pinned[0] = D->pinned[1] = 0;
@@ -944,7 +949,7 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   // instead of ~150-300); cached per call configuration.
   const bool use_graph = tun().graph != 0 && !sync_each && steps_max >= 3;
   const GraphKey key{B, M, steps_max, n_sub, A->top_k, A->type_masks != nullptr, A->want_log_probs, A->want_entropy,
-                     A->forced_tokens != nullptr, prof ? 1 : 0, A->flags, A->temperature, A->top_p, A->stop_boost,
+                     A->forced_tokens != nullptr, prof ? 1 : 0, A->memory_rows, A->flags, A->temperature, A->top_p, A->stop_boost,
                      A->hard_stop_threshold, A->site_dup_threshold};
   cudaGraphExec_t exec = nullptr;
   if (use_graph)

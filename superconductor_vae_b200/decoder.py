@@ -375,8 +375,14 @@ class EnhancedTransformerDecoder(nn.Module):
                                stop_boost: float = 0.0, hard_stop_threshold: float = 0.0,
                                heads_pred: Optional[Dict[str, torch.Tensor]] = None,
                                type_masks: Optional[torch.Tensor] = None, site_dup_threshold: float = 0.0,
-                               *, _forced_tokens: Optional[torch.Tensor] = None, _seed: Optional[int] = None
+                               *, _forced_tokens: Optional[torch.Tensor] = None, _seed: Optional[int] = None,
+                               _n_samples: int = 1
                                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Reference signature and semantics (:1321-1557).  Keyword-only extension ``_n_samples = k`` (RLOO): the
+        conditioning inputs (or ``cached_memory``) are the BASE batch [B0, ...] and k * B0 rows are decoded in the
+        reference's ``repeat`` layout (row i * B0 + b = sample i of latent b, scripts/train_v12_clean.py:2677-2688) without
+        materialising the k copies: memory tokens and their projected K / V are built once per latent and shared by its
+        samples.  Same outputs as passing ``z.repeat(k, 1)`` etc."""
         self.eval()                                                         # side effect kept (:1368)
         max_len = max_len or self.max_len
         pe_max = self.pos_encoding.pe.shape[1]
@@ -388,6 +394,13 @@ class EnhancedTransformerDecoder(nn.Module):
                 self._create_memory(z, encoder_skip, stoich_pred, heads_pred)
             device = memory.device
             B, M = memory.size(0), memory.size(1)
+            memory_rows = 0
+            if _n_samples > 1:
+                if B * _n_samples > 64 and B * _n_samples <= int(self.max_rows_per_call):
+                    memory_rows, B = B, B * _n_samples                      # shared by the samples inside the engine
+                else:                                                       # tiny or chunked batches: plain copies
+                    memory = memory.repeat(_n_samples, 1, 1)
+                    B = memory.size(0)
             steps_max = max_len - 1
             if steps_max < 1:
                 raise RuntimeError("max_len leaves no decoding step (the reference fails in torch.cat here)")
@@ -420,7 +433,8 @@ class EnhancedTransformerDecoder(nn.Module):
                     hi = min(B, lo + chunk)
                     out_steps = C.c_int32(0)
                     args = _lib.GenerateArgs(
-                        batch=hi - lo, n_memory=M, max_len=max_len, memory=memory[lo:hi].data_ptr(),
+                        batch=hi - lo, n_memory=M, max_len=max_len, memory_rows=memory_rows,
+                        memory=(memory if memory_rows else memory[lo:hi]).data_ptr(),
                         temperature=float(temperature), top_k=int(top_k) if top_k else 0,
                         top_p=float(top_p) if top_p is not None else 1.0, stop_boost=float(stop_boost),
                         hard_stop_threshold=float(hard_stop_threshold), site_dup_threshold=float(site_dup_threshold or 0.0),

@@ -136,14 +136,18 @@ def sample_for_reinforce_sharded(decoder, z: torch.Tensor, k: int, *, stoich_pre
     B = z.shape[0]
     lo, hi = shard_bounds(B, ws, rank)
     sl = slice(lo, hi)
-    rep = lambda t: t[sl].repeat(k, *([1] * (t.dim() - 1)))
-    hp = {n_: rep(v) for n_, v in heads_pred.items()} if heads_pred is not None else None
+    cut = lambda t: t[sl]
+    hp = {n_: cut(v) for n_, v in heads_pred.items()} if heads_pred is not None else None
     kw = dict(gen_kwargs)
-    for name in PER_ROW_KWARGS:
+    forced = kw.pop("_forced_tokens", None)
+    for name in ("encoder_skip", "cached_memory"):
         if kw.get(name) is not None:
-            kw[name] = rep(kw[name])
-    toks, lp, ent, _ = decoder.sample_for_reinforce(rep(z), stoich_pred=rep(stoich_pred) if stoich_pred is not None else None,
-                                                    heads_pred=hp, **kw)
+            kw[name] = cut(kw[name])
+    if forced is not None:                                  # forced tokens are per SAMPLE row: expand like the outputs
+        kw["_forced_tokens"] = forced[rloo_shard_rows(B, k, ws, rank).to(forced.device)]
+    # the k samples of a latent share its memory tokens inside the engine (_n_samples): nothing is repeated here
+    toks, lp, ent, _ = decoder.sample_for_reinforce(cut(z), stoich_pred=cut(stoich_pred) if stoich_pred is not None else None,
+                                                    heads_pred=hp, _n_samples=k, **kw)
     n = B * k
     tdt = token_dtype_for(getattr(decoder, "vocab_size", 1 << 30))
     out_t = restore_rloo_order(gather_rows(toks.to(tdt), n, 0, group), B, k, ws).to(torch.int64)

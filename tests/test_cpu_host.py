@@ -190,8 +190,12 @@ class _FakeDecoder:
         toks = (key.unsqueeze(1) * 7 + torch.arange(L).unsqueeze(0)).to(torch.int64) % 4000 + 3
         return toks, (toks.float() * 0.25 if return_log_probs else None), None
 
-    def sample_for_reinforce(self, z, stoich_pred=None, heads_pred=None, **kw):
-        t, lp, _ = self.generate_with_kv_cache(z, stoich_pred=stoich_pred, heads_pred=heads_pred, return_log_probs=True, **kw)
+    def sample_for_reinforce(self, z, stoich_pred=None, heads_pred=None, _n_samples=1, **kw):
+        k = _n_samples                                     # the engine expands the base rows itself (repeat layout)
+        rep = lambda t: None if t is None else t.repeat(k, *([1] * (t.dim() - 1)))
+        t, lp, _ = self.generate_with_kv_cache(rep(z), stoich_pred=rep(stoich_pred),
+                                               heads_pred={n: rep(v) for n, v in heads_pred.items()} if heads_pred else None,
+                                               return_log_probs=True, **kw)
         return t, lp, lp * 2, torch.ones_like(lp)
 
 

@@ -674,6 +674,29 @@ def test_compact_finished_matches_reference_semantics_up_to_end(rows):
             assert int(ends.max()) - int(ends.min()) >= 5                          # the rollout really is ragged
 
 
+@pytest.mark.parametrize("base,k", [(96, 4), (1024, 4), (700, 3)])
+def test_rloo_samples_sharing_memory_match_repeated_inputs(base, k):
+    """RLOO rollouts with `_n_samples = k` (the k samples of a latent share its memory tokens and their projected K / V
+    inside the engine, include/scvae_b200.h memory_rows) against the reference's way of passing z.repeat(k, 1) etc.
+    (scripts/train_v12_clean.py:2677-2688): bit-identical tokens, log-probs and entropy in the same sample-major layout
+    (one stream at 384 rows, two sub-batch streams at 4096 rows, a row count that does not split into equal sub-batches)."""
+    sd = W.make_decoder_state_dict(W.C512, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    z = W.make_latents(base, 2048, 321)
+    stoich, heads = W.make_conditioning(base, 13, 321)
+    kw = dict(temperature=1.2, max_len=64, stop_boost=10.0, _seed=23)
+    rep = lambda t: t.repeat(k, *([1] * (t.dim() - 1)))
+    t0, lp0, en0, mk0 = dec.sample_for_reinforce(_cuda(rep(z)), stoich_pred=_cuda(rep(stoich)),
+                                                 heads_pred=_cuda({n: rep(v) for n, v in heads.items()}), **kw)
+    t1, lp1, en1, mk1 = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), _n_samples=k, **kw)
+    assert t1.shape == t0.shape and t1.shape[0] == base * k
+    assert torch.equal(t0, t1) and torch.equal(lp0, lp1) and torch.equal(en0, en1) and torch.equal(mk0, mk1)
+    mem = dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(heads))
+    t2, _, _ = dec.generate_with_kv_cache(None, temperature=1.2, max_len=64, stop_boost=10.0, cached_memory=mem, _seed=23,
+                                          _n_samples=k)
+    assert torch.equal(t2, t0)
+
+
 def test_tunables_never_change_tokens():
     """scv_tune moves work between streams / grids only: the opt-in launch configurations (grid-stride attention grid,
     forced GEMM pipeline depth, 1 / 3 sub-batch streams, bulk-copy staged cross-attention, no graph replay) decode the
