@@ -381,6 +381,151 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-attention over SHARED memory tokens (RLOO: the k samples of a latent attend to the same projected K / V).
+// One warp per (latent, head): every 16-byte piece of the latent's K / V is loaded ONCE into registers and used for up to
+// KS query rows (the samples, rows j, j + seq_mod, j + 2 seq_mod, ... of the launch), so the stream through L2 and the
+// load instructions shrink by the group size, not only the HBM traffic.  Per query row the arithmetic and its order are
+// those of attention_decode_v4_kernel (same chunks of UNR * PPI positions, same reduction tree, same accumulation
+// order), so the output bits are identical.
+// ---------------------------------------------------------------------------------------------
+template <int LPP, int KS>
+__global__ void __launch_bounds__(256) attention_cross_shared_kernel(AttnArgs a, int k_local) {
+  extern __shared__ float sc_all[];
+  pdl_wait();
+  if (a.st != nullptr && a.st->done) return;
+  constexpr int PPI = 32 / LPP, UNR = 4;
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int n_items = a.seq_mod * a.nhead, n = a.fixed_len, hd = a.hd;
+  TraceRec* trc = threadIdx.x == 0 ? trace_begin(a.trace, 4u) : nullptr;
+  float* sc = sc_all + (size_t)warp_in_block * KS * a.max_n;
+  const int grp = lane / LPP, e0 = 4 * (lane % LPP);
+  const bool e_ok = e0 < hd;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long kv_delta = a.vcache - a.kcache;
+  for (int gw = blockIdx.x * wpb + warp_in_block; gw < n_items; gw += gridDim.x * wpb) {
+    const int j = gw / a.nhead, h = gw % a.nhead;
+    const float* kbase = a.kcache + (size_t)j * a.seq_stride + h * hd + e0;
+    for (int s0 = 0; s0 < k_local; s0 += KS) {
+      const int ns = min(KS, k_local - s0);
+      float4 q4[KS];
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+        q4[s] = (s < ns && e_ok) ? *reinterpret_cast<const float4*>(a.q + (size_t)((s0 + s) * a.seq_mod + j) * a.ldq + h * hd + e0) : zero4;
+      for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+        float4 kv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int p = p0 + u * PPI + grp;
+          kv[u] = (p < n && e_ok) ? __ldcs(reinterpret_cast<const float4*>(kbase + (size_t)p * a.row_stride)) : zero4;
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          if (s < ns) {
+            float d[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+              d[u] = fmaf(q4[s].x, kv[u].x, fmaf(q4[s].y, kv[u].y, fmaf(q4[s].z, kv[u].z, q4[s].w * kv[u].w)));
+            if constexpr (LPP == 16) {
+              const int sub = lane & 15;
+              const bool up8 = (sub & 8) != 0, up4 = (sub & 4) != 0;
+              const float r0 = __shfl_xor_sync(0xffffffffu, up8 ? d[0] : d[2], 8);
+              const float r1 = __shfl_xor_sync(0xffffffffu, up8 ? d[1] : d[3], 8);
+              const float e0s = (up8 ? d[2] : d[0]) + r0, e1s = (up8 ? d[3] : d[1]) + r1;
+              float f = (up4 ? e1s : e0s) + __shfl_xor_sync(0xffffffffu, up4 ? e0s : e1s, 4);
+              f += __shfl_xor_sync(0xffffffffu, f, 2);
+              f += __shfl_xor_sync(0xffffffffu, f, 1);
+              const int u_mine = 2 * (sub >> 3) + ((sub >> 2) & 1);
+              const int p = p0 + u_mine * PPI + grp;
+              if ((sub & 3) == 0 && p < n) sc[s * a.max_n + p] = f * a.scale;
+            } else {
+#pragma unroll
+              for (int u = 0; u < UNR; ++u) {
+                float dd = d[u];
+#pragma unroll
+                for (int o = LPP / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+                const int p = p0 + u * PPI + grp;
+                if ((lane % LPP) == 0 && p < n) sc[s * a.max_n + p] = dd * a.scale;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      for (int s = 0; s < ns; ++s) {
+        float* scs = sc + s * a.max_n;
+        float m = -INFINITY;
+        for (int p = lane; p < n; p += 32) m = fmaxf(m, scs[p]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int p = lane; p < n; p += 32) {
+          const float e = expf(scs[p] - m);
+          scs[p] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        for (int p = lane; p < n; p += 32) scs[p] = scs[p] / sum;
+      }
+      __syncwarp();
+      float4 acc[KS];
+#pragma unroll
+      for (int s = 0; s < KS; ++s) acc[s] = zero4;
+      for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+        float4 vv[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int p = p0 + u * PPI + grp;
+          ok[u] = p < n && e_ok;
+          vv[u] = ok[u] ? __ldcs(reinterpret_cast<const float4*>(kbase + kv_delta + (size_t)p * a.row_stride)) : zero4;
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          if (s < ns) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const float w = ok[u] ? sc[s * a.max_n + p0 + u * PPI + grp] : 0.f;
+              acc[s].x = fmaf(w, vv[u].x, acc[s].x); acc[s].y = fmaf(w, vv[u].y, acc[s].y);
+              acc[s].z = fmaf(w, vv[u].z, acc[s].z); acc[s].w = fmaf(w, vv[u].w, acc[s].w);
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 0 && gw + gridDim.x * wpb >= n_items && s0 + KS >= k_local) pdl_launch_dependents();
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        if (s < ns) {
+          float4 r = acc[s];
+#pragma unroll
+          for (int o = LPP; o < 32; o <<= 1) {
+            r.x += __shfl_xor_sync(0xffffffffu, r.x, o); r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
+            r.z += __shfl_xor_sync(0xffffffffu, r.z, o); r.w += __shfl_xor_sync(0xffffffffu, r.w, o);
+          }
+          if (grp == 0 && e_ok) {
+            const int b = (s0 + s) * a.seq_mod + j;
+            if (a.out_split == nullptr) {
+              *reinterpret_cast<float4*>(a.out + (size_t)b * a.ldo + h * hd + e0) = r;
+            } else {
+              uint32_t hi0, lo0, hi1, lo1;
+              split_pair(r.x, r.y, hi0, lo0);
+              split_pair(r.z, r.w, hi1, lo1);
+              const int col = h * hd + e0;
+              const int mt = b >> 7, ri = b & 127, kb = col >> 6, cj = (col & 63) >> 3;
+              uint8_t* dst = a.out_split + ((size_t)mt * a.kb_out + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4) +
+                             (size_t)((col & 7) >> 2) * 8;
+              *reinterpret_cast<uint2*>(dst) = make_uint2(hi0, hi1);
+              *reinterpret_cast<uint2*>(dst + 16384) = make_uint2(lo0, lo1);
+            }
+          }
+        }
+      }
+      __syncwarp();          // the score buffers are reused by the next group of samples / the next item
+    }
+  }
+  trace_end(trc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cross-attention with bulk-copy staging (decode only: one query row per sequence, contiguous K / V).
 // A sequence's projected memory tokens of one layer are ONE contiguous block ([M][k(d) | v(d)] fp32 = 96 KB for
 // M = 24, d = 512), so instead of thousands of per-thread 16-byte loads a single elected thread streams whole blocks
@@ -589,6 +734,23 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
   SCV_REQUIRE(a.seq_mod == 0 || v4, "attention: shared memory tokens need head_dim %% 4 == 0 and 16-byte aligned rows");
   SCV_REQUIRE(a.row_map == nullptr || v4, "attention: compaction of finished rows needs head_dim %% 4 == 0 and 16-byte aligned rows");
+  // shared memory tokens, whole groups of seq_mod rows in this launch: one warp serves the k samples of a (latent, head)
+  const int k_shared = (a.seq_mod > 0 && a.row_map == nullptr && a.fixed_len >= 0 && a.knew == nullptr && a.page_table == nullptr &&
+                        a.rows_per_seq == 0 && a.key_skip == nullptr && a.B % a.seq_mod == 0 && a.slot_base % a.seq_mod == 0)
+                           ? a.B / a.seq_mod : 0;
+  if (k_shared > 1 && v4 && tun().attn_shared != 0) {
+    constexpr int KS = 4;
+    const size_t smem_s = (size_t)warps * KS * a.max_n * sizeof(float);
+    int blocks_s = ceil_div(a.seq_mod * a.nhead, warps);
+    if (tun().attn_ctas_per_sm > 0) blocks_s = std::min(blocks_s, tun().attn_ctas_per_sm * sm_count());
+    const int lanes = a.hd / 4;
+    if (lanes <= 4) SCV_CUDA(launch_k(attention_cross_shared_kernel<4, KS>, dim3(blocks_s), dim3(warps * 32), smem_s, s, a, k_shared));
+    else if (lanes <= 8) SCV_CUDA(launch_k(attention_cross_shared_kernel<8, KS>, dim3(blocks_s), dim3(warps * 32), smem_s, s, a, k_shared));
+    else if (lanes <= 16) SCV_CUDA(launch_k(attention_cross_shared_kernel<16, KS>, dim3(blocks_s), dim3(warps * 32), smem_s, s, a, k_shared));
+    else SCV_CUDA(launch_k(attention_cross_shared_kernel<32, KS>, dim3(blocks_s), dim3(warps * 32), smem_s, s, a, k_shared));
+    SCV_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t bulk_smem = (v4 && tun().attn_bulk != 0 && a.B >= tun().attn_bulk_min_rows) ? cross_bulk_smem(a, warps) : 0;
   if (bulk_smem != 0) {
     static bool attr_dev[64] = {};

@@ -909,6 +909,9 @@ int scv_decoder_generate(scv_decoder* D, const scv_generate_args* A, void* strea
   {
     const int forced = tun().subbatches;
     n_sub = forced > 0 ? forced : (B >= tun().sub_min_rows ? 2 : 1);
+    // shared memory tokens: a launch over ALL rows lets one warp serve every sample of a (latent, head); row ranges would
+    // split a latent's samples between the streams (config 3: 177.9 ms against 185.4 with two ranges)
+    if (forced <= 0 && Bm < B && tun().attn_shared != 0) n_sub = 1;
     if (prof_enabled()) n_sub = 1;       // per-kernel timing wants one kernel at a time
     n_sub = std::max(1, std::min(n_sub, kMaxSub));
     while (n_sub > 1 && round_up(ceil_div(B, n_sub), 128) * (n_sub - 1) >= B) --n_sub;

@@ -233,6 +233,35 @@ def test_max_len_is_clamped_to_pe_buffer(golden_dir):
     assert torch.equal(t.cpu().to(torch.int16), g["greedy_plain_tokens"])
 
 
+def test_wrong_shapes_raise_like_the_reference(golden_dir):
+    """The kernels read raw pointers with the configured strides, so every tensor is checked against the batch and the
+    feature dims first: what the reference rejects in F.linear / view / cat (RuntimeError) is rejected here too."""
+    shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
+    zc, sc, hc = _cuda(z), _cuda(stoich), _cuda(heads)
+    B = z.shape[0]
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(zc[:, :-1], stoich_pred=sc, temperature=0.001)                     # latent_dim
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(zc, stoich_pred=torch.zeros((B, 37), device=DEV), temperature=0.001)   # V12 stoich on a 13-dim model
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(zc, stoich_pred=sc[:-1], temperature=0.001)                        # batch
+    bad = dict(hc)
+    bad["tc_class_logits"] = hc["tc_class_logits"][:, :3]
+    with pytest.raises(RuntimeError):
+        dec.precompute_memory(zc, None, sc, bad)                                                      # heads_input width
+    bad = dict(hc)
+    bad["tc_pred"] = hc["tc_pred"][:-1]
+    with pytest.raises(RuntimeError):
+        dec.precompute_memory(zc, None, sc, bad)                                                      # stale head tensor (:838-843)
+    mem = dec.precompute_memory(zc, None, sc, hc)
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(None, temperature=0.001, cached_memory=mem[:, :, :-1])             # d_model
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(None, temperature=0.001, cached_memory=mem, type_masks=_cuda(masks)[:, :-1])
+    with pytest.raises(RuntimeError):
+        dec.generate_with_kv_cache(None, temperature=0.001, cached_memory=mem, _forced_tokens=torch.zeros((B + 1, 3), dtype=torch.long))
+
+
 def test_cached_memory_and_chunking_are_equivalent(golden_dir):
     shape, g, sd, dec, z, stoich, heads, masks = _setup(golden_dir, "tiny")
     mem = dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(heads))
@@ -674,25 +703,34 @@ def test_compact_finished_matches_reference_semantics_up_to_end(rows):
             assert int(ends.max()) - int(ends.min()) >= 5                          # the rollout really is ragged
 
 
-@pytest.mark.parametrize("base,k", [(96, 4), (1024, 4), (700, 3)])
-def test_rloo_samples_sharing_memory_match_repeated_inputs(base, k):
+@pytest.mark.parametrize("base,k,shape", [(96, 4, "C512"), (1024, 4, "C512"), (700, 3, "C512"), (512, 6, "C512"), (160, 5, "C576"),
+                                          (70, 2, "TINY")])
+def test_rloo_samples_sharing_memory_match_repeated_inputs(base, k, shape):
     """RLOO rollouts with `_n_samples = k` (the k samples of a latent share its memory tokens and their projected K / V
     inside the engine, include/scvae_b200.h memory_rows) against the reference's way of passing z.repeat(k, 1) etc.
     (scripts/train_v12_clean.py:2677-2688): bit-identical tokens, log-probs and entropy in the same sample-major layout
-    (one stream at 384 rows, two sub-batch streams at 4096 rows, a row count that does not split into equal sub-batches)."""
-    sd = W.make_decoder_state_dict(W.C512, 0)
-    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
-    z = W.make_latents(base, 2048, 321)
-    stoich, heads = W.make_conditioning(base, 13, 321)
-    kw = dict(temperature=1.2, max_len=64, stop_boost=10.0, _seed=23)
+    (one stream at 384 rows, 4096 rows, a row count that does not split into equal sub-batches, more samples than the
+    group kernel serves in one pass), for the group kernel over all rows (default), the group kernel inside two sub-batch
+    row ranges (which split a latent's samples, or do not hold whole groups and fall back) and the per-row kernel."""
+    shp = getattr(W, shape)
+    sd = W.make_decoder_state_dict(shp, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shp.nhead, device=DEV)
+    z = W.make_latents(base, shp.latent_dim, 321)
+    stoich, heads = W.make_conditioning(base, shp.stoich_input_dim, 321)
+    kw = dict(temperature=1.2, max_len=min(64, shp.max_len), stop_boost=10.0, _seed=23)
     rep = lambda t: t.repeat(k, *([1] * (t.dim() - 1)))
     t0, lp0, en0, mk0 = dec.sample_for_reinforce(_cuda(rep(z)), stoich_pred=_cuda(rep(stoich)),
                                                  heads_pred=_cuda({n: rep(v) for n, v in heads.items()}), **kw)
-    t1, lp1, en1, mk1 = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), _n_samples=k, **kw)
-    assert t1.shape == t0.shape and t1.shape[0] == base * k
-    assert torch.equal(t0, t1) and torch.equal(lp0, lp1) and torch.equal(en0, en1) and torch.equal(mk0, mk1)
+    try:
+        for tune in (dict(attn_shared=1, subbatches=0), dict(attn_shared=1, subbatches=2), dict(attn_shared=0, subbatches=0)):
+            _lib.tune(**tune)
+            t1, lp1, en1, mk1 = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), _n_samples=k, **kw)
+            assert t1.shape == t0.shape and t1.shape[0] == base * k, tune
+            assert torch.equal(t0, t1) and torch.equal(lp0, lp1) and torch.equal(en0, en1) and torch.equal(mk0, mk1), tune
+    finally:
+        _lib.tune(attn_shared=1, subbatches=0)
     mem = dec.precompute_memory(_cuda(z), None, _cuda(stoich), _cuda(heads))
-    t2, _, _ = dec.generate_with_kv_cache(None, temperature=1.2, max_len=64, stop_boost=10.0, cached_memory=mem, _seed=23,
+    t2, _, _ = dec.generate_with_kv_cache(None, temperature=1.2, max_len=kw["max_len"], stop_boost=10.0, cached_memory=mem, _seed=23,
                                           _n_samples=k)
     assert torch.equal(t2, t0)
 
