@@ -88,6 +88,8 @@ struct Tunables {
                            // 0.76-0.92 ms per step against 0.77-0.84 ms for the grid-barrier kernel
   int cluster_max_rows;    // SCV_CLUSTER_MAX_ROWS: ... up to this many rows (<= 64)
   int cluster_rows;        // SCV_CLUSTER_ROWS: rows per cluster (0 = automatic: 1 up to 16 rows, 2 up to 32, else 4)
+  int gemm_bn64;           // SCV_GEMM_BN64: projections with at most this many 128-row tiles (0 = never) whose grid of 128 x 64
+  int gemm_bn64_max_ctas;  // SCV_GEMM_BN64_MAX_CTAS: tiles has at most this many CTAs use that narrower tile
   int attn_shared;         // SCV_ATTN_SHARED: shared memory tokens (RLOO) go through attention_cross_shared_kernel: one warp per
                            // (latent, head) serves all of the latent's samples (0 = the per-row kernel, samples adjacent for L2)
 };

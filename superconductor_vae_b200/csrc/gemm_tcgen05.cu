@@ -30,7 +30,7 @@ using namespace tc;
 namespace {
 
 template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
   constexpr int STAGE_BYTES = stage_bytes(BN);
   constexpr uint32_t TMEM_COLS = BN;
   constexpr uint32_t W_BYTES = BN * 128;
@@ -76,7 +76,11 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
   pdl_wait();
   const bool skip = a.done_flag != nullptr && *a.done_flag != 0;     // every row finished: nothing left to compute
   // weight tiles are packed per 128 output rows: a 256-wide CTA tile is two of them (same k-block, KB tiles apart)
-  const __nv_bfloat16* wtile0 = a.wt + (size_t)n_tile * (BN / 128) * KB * (TILE_BYTES / 2);
+  // (a 64-wide CTA tile is the upper or lower half of one: 64 rows x 128 B are contiguous and keep the swizzle pattern)
+  constexpr int NW = BN >= 128 ? BN / 128 : 1;
+  constexpr uint32_t W_COPY = BN >= 128 ? TILE_BYTES : W_BYTES;
+  const __nv_bfloat16* wtile0 = BN >= 128 ? a.wt + (size_t)n_tile * (BN / 128) * KB * (TILE_BYTES / 2)
+                                          : a.wt + (size_t)(n_tile >> 1) * KB * (TILE_BYTES / 2) + (size_t)(n_tile & 1) * (W_BYTES / 2);
 
   if (skip) {
     // fall through to the teardown
@@ -93,8 +97,8 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
           mbar_arrive_expect_tx(full_bar(s), 2 * TILE_BYTES + W_BYTES);
           bulk_copy_g2s(st_base, atile0 + (size_t)kb * (2 * TILE_BYTES), 2 * TILE_BYTES, full_bar(s));
 #pragma unroll
-          for (int h = 0; h < BN / 128; ++h)
-            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+          for (int h = 0; h < NW; ++h)
+            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), W_COPY, full_bar(s));
         }
       }
     } else {
@@ -107,8 +111,8 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN == 128) ? 2 : 
         if (gtid == 0) {
           mbar_expect_tx(full_bar(s), W_BYTES);
 #pragma unroll
-          for (int h = 0; h < BN / 128; ++h)
-            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), TILE_BYTES, full_bar(s));
+          for (int h = 0; h < NW; ++h)
+            bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), W_COPY, full_bar(s));
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -332,7 +336,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
 #define SCV_SET_ALL(S, N)                                                                             \
   SCV_SET_SMEM(false, false, false, S, N); SCV_SET_SMEM(false, true, false, S, N); SCV_SET_SMEM(true, false, false, S, N); \
   SCV_SET_SMEM(true, true, false, S, N); SCV_SET_SMEM(false, false, true, S, N); SCV_SET_SMEM(true, false, true, S, N)
-    SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256);
+    SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256); SCV_SET_ALL(4, 64);
 #undef SCV_SET_ALL
 #undef SCV_SET_SMEM
   }
@@ -366,7 +370,18 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
     else if (res) SCV_LAUNCH(false, false, true, S, N);                                              \
     else SCV_LAUNCH(false, false, false, S, N);                                                      \
   } while (0)
-  if (wide) {
+  // Few row tiles (a few hundred rows): a 128-wide tile leaves most SMs idle while each CTA's MMAs and epilogue are the
+  // critical path of a ~6 us kernel; 128 x 64 tiles halve both (64 columns is where the UMMA's math time equals its
+  // A-operand read, so narrower tiles gain nothing).  Same k order per output element: identical bits.
+  const int n64 = ceil_div(a.N, 64);
+  // Measured in the decode (tests/batch_sweep.py): 9-10 % per step at 64-512 rows, 2-5 % at 1024-2048, but 3 % SLOWER at 4096
+  // rows (two streams x 16 row tiles: the A tiles are re-read by twice as many CTAs out of an L2 that is the bottleneck
+  // there), hence the bound on the row tiles.
+  const bool narrow = !wide && mt <= tun().gemm_bn64 && n64 * mt <= tun().gemm_bn64_max_ctas;
+  if (narrow) {
+    dim3 grid(n64, mt);
+    SCV_LAUNCH_MODE(4, 64);
+  } else if (wide) {
     dim3 grid(n128 / 2, mt);
     SCV_LAUNCH_MODE(3, 256);
   } else {

@@ -106,6 +106,31 @@ def test_op_linear_tcgen05_matches_fp64(M, N, K, act, residual):
     assert float((y.cpu().double() - ref).abs().max()) <= 5e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (200, 132, 72), (64, 4752, 512), (384, 512, 2048)])
+def test_op_linear_narrow_tile_is_bit_identical(M, N, K):
+    """The 128 x 64 tile used for projections with few row tiles walks k in the same order as the 128 x 128 tile."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn((M, K), generator=g).to(DEV)
+    w = (torch.randn((N, K), generator=g) / math.sqrt(K)).to(DEV).contiguous()
+    b, r = torch.randn((N,), generator=g).to(DEV), torch.randn((M, N), generator=g).to(DEV)
+    L = _lib.lib()
+    wt = torch.zeros(int(L.scv_op_tiled_elems(N, K)), dtype=torch.bfloat16, device=DEV)
+    _lib.check(L.scv_op_pack_tiled(_lib.ptr(w), _lib.ptr(wt), N, K, _lib.current_stream()))
+    ys = []
+    try:
+        for bn64 in (0, 8):
+            _lib.tune(gemm_bn64=bn64)
+            for act, res in ((0, True), (1, False)):
+                y = torch.full((M, N), float("nan"), device=DEV)
+                _lib.check(L.scv_op_linear(_lib.ptr(x), K, _lib.ptr(wt), 0, _lib.ptr(b), _lib.ptr(r) if res else None, N,
+                                           _lib.ptr(y), N, M, N, K, act, 2, _lib.current_stream()))
+                torch.cuda.synchronize()
+                ys.append(y)
+    finally:
+        _lib.tune(gemm_bn64=8)
+    assert torch.equal(ys[0], ys[2]) and torch.equal(ys[1], ys[3]) and not bool(torch.isnan(ys[2]).any())
+
+
 def test_op_layernorm_matches_fp32():
     g = torch.Generator().manual_seed(3)
     for M, N in ((1, 64), (37, 512), (130, 576), (9, 1024)):
@@ -745,11 +770,11 @@ def test_tunables_never_change_tokens():
     z = W.make_latents(B, 2048, 1234)
     stoich, heads = W.make_conditioning(B, 13, 1234)
     kw = dict(temperature=0.001, max_len=64, type_masks=_cuda(OV.type_masks()), stop_boost=10.0, hard_stop_threshold=0.8)
-    defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, attn_bulk=0, attn_bulk_piece_kb=0)
+    defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, attn_bulk=0, attn_bulk_piece_kb=0, gemm_bn64=8)
     base, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
     try:
         for cfg in (dict(attn_ctas_per_sm=3, gemm_stages=2), dict(subbatches=1), dict(subbatches=3), dict(attn_bulk=1),
-                    dict(attn_bulk=1, attn_bulk_piece_kb=16), dict(graph=0)):
+                    dict(attn_bulk=1, attn_bulk_piece_kb=16), dict(graph=0), dict(gemm_bn64=0), dict(gemm_bn64=16), dict(gemm_bn64=16, subbatches=3)):
             _lib.tune(**{**defaults, **cfg})
             t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
             assert torch.equal(t, base), cfg
