@@ -133,6 +133,17 @@ def test_rloo_order_roundtrip():
     assert torch.equal(parallel.restore_rloo_order(gathered, B, k, ws), full)
 
 
+def _plain(objs):
+    """Tensors as numpy arrays: torch.multiprocessing queues pass tensors by shared-memory handle, which the receiver can only
+    open while the sending process is alive - a worker that exits right after q.put() makes the test flaky."""
+    return tuple(o.numpy() if isinstance(o, torch.Tensor) else o for o in objs)
+
+
+def _tensors(objs):
+    import numpy as np
+    return tuple(torch.from_numpy(o) if isinstance(o, np.ndarray) else o for o in objs)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -151,7 +162,7 @@ def _gather_worker(rank, ws, port, q):
     out = parallel.gather_rows(local, n, pad_value=0)
     lp = parallel.gather_rows(local.float() * 0.5, n, pad_value=0.0)
     if rank == 0:
-        q.put((out, lp))
+        q.put(_plain((out, lp)))
     dist.destroy_process_group()
 
 
@@ -162,7 +173,7 @@ def test_gather_rows_world_size_2():
     procs = [ctx.Process(target=_gather_worker, args=(r, ws, port, q)) for r in range(ws)]
     for p in procs:
         p.start()
-    out, lp = q.get(timeout=120)
+    out, lp = _tensors(q.get(timeout=300))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -234,7 +245,7 @@ def _sharded_worker(rank, ws, port, q):
         cg.push(rows, counts)
     chunked = cg.finish()
     if rank == 0:
-        q.put((t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked))
+        q.put(_plain((t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked)))
     dist.destroy_process_group()
 
 
@@ -245,7 +256,7 @@ def test_generate_sharded_slices_every_per_row_input_world_size_2():
     procs = [ctx.Process(target=_sharded_worker, args=(r, ws, port, q)) for r in range(ws)]
     for p in procs:
         p.start()
-    t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked = q.get(timeout=120)
+    t, lp, full, full_lp, tm, fm, tr, fr, lpr, flr, bad, chunked = _tensors(q.get(timeout=300))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
