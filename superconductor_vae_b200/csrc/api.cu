@@ -44,7 +44,8 @@ Tunables& tun() {
                        env_int("SCV_GRAPH", 1), env_int("SCV_SUB_MIN_ROWS", 2048), env_int("SCV_ATTN_BULK", 0),
                        env_int("SCV_ATTN_BULK_MIN_ROWS", 256), env_int("SCV_ATTN_BULK_PIECE_KB", 0),
                        env_int("SCV_COND_TC_MIN_ROWS", 16384), env_int("SCV_CLUSTER", 0), env_int("SCV_CLUSTER_MAX_ROWS", 64), env_int("SCV_CLUSTER_ROWS", 0),
-                       env_int("SCV_GEMM_BN64", 8), env_int("SCV_GEMM_BN64_MAX_CTAS", 148), env_int("SCV_ATTN_SHARED", 1)};
+                       env_int("SCV_GEMM_BN64", 8), env_int("SCV_GEMM_BN64_MAX_CTAS", 148),
+                       env_int("SCV_GEMM_MC", 0), env_int("SCV_GEMM_MC_MIN_ROW_TILES", 9), env_int("SCV_ATTN_SHARED", 1)};
   return t;
 }
 unsigned tune_epoch() { return g_tune_epoch; }
@@ -254,7 +255,8 @@ int scv_tune(const char* key, int32_t value) {
               k == "attn_bulk_min_rows" ? &t.attn_bulk_min_rows : k == "attn_bulk_piece_kb" ? &t.attn_bulk_piece_kb :
               k == "cond_tc_min_rows" ? &t.cond_tc_min_rows : k == "cluster" ? &t.cluster : k == "cluster_max_rows" ? &t.cluster_max_rows : k == "cluster_rows" ? &t.cluster_rows :
               k == "attn_shared" ? &t.attn_shared : k == "gemm_bn64" ? &t.gemm_bn64 :
-              k == "gemm_bn64_max_ctas" ? &t.gemm_bn64_max_ctas : nullptr;
+              k == "gemm_bn64_max_ctas" ? &t.gemm_bn64_max_ctas : k == "gemm_mc" ? &t.gemm_mc :
+              k == "gemm_mc_min_row_tiles" ? &t.gemm_mc_min_row_tiles : nullptr;
   SCV_REQUIRE(slot != nullptr, "tune: unknown key '%s'", key);
   if (*slot != value) { *slot = value; ++g_tune_epoch; }
   return 0;

@@ -90,6 +90,9 @@ struct Tunables {
   int cluster_rows;        // SCV_CLUSTER_ROWS: rows per cluster (0 = automatic: 1 up to 16 rows, 2 up to 32, else 4)
   int gemm_bn64;           // SCV_GEMM_BN64: projections with at most this many 128-row tiles (0 = never) whose grid of 128 x 64
   int gemm_bn64_max_ctas;  // SCV_GEMM_BN64_MAX_CTAS: tiles has at most this many CTAs use that narrower tile
+  int gemm_mc;             // SCV_GEMM_MC: projections over SplitTile input run as clusters of two column tiles that share the A tile:
+                           // each CTA loads one half (hi / lo) and multicasts it to both (2/3 of the L2 -> SM operand traffic)
+  int gemm_mc_min_row_tiles;   // SCV_GEMM_MC_MIN_ROW_TILES: ... for launches with at least this many 128-row tiles
   int attn_shared;         // SCV_ATTN_SHARED: shared memory tokens (RLOO) go through attention_cross_shared_kernel: one warp per
                            // (latent, head) serves all of the latent's samples (0 = the per-row kernel, samples adjacent for L2)
 };
@@ -114,6 +117,21 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// launch_k with thread-block clusters of cluster_x CTAs along x
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, unsigned cluster_x,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -29,8 +29,15 @@ using namespace tc;
 
 namespace {
 
-template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN>
+// MC (multicast): the launch is made of clusters of two CTAs with neighbouring column tiles of the same row tile.  They need
+// the same A tile, so CTA `rank` loads only its half of it (rank 0 the hi tile, rank 1 the lo tile) and the copy is delivered
+// to both CTAs' shared memory (cp.async.bulk ... .multicast::cluster, signalling both full barriers); a stage is free when
+// the MMAs of BOTH CTAs that read it are done (each commit arrives on both empty barriers).  Per k-block a CTA then pulls
+// 32 KB instead of 48 KB out of L2 (ncu: the K = 2048 projection moves 210 MB through the crossbar in 21 us, i.e. it runs at
+// the L2's ~10 TB/s).
+template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN, bool MC = false>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
+  static_assert(!MC || (A_SPLIT && BN == 128), "multicast: SplitTile input, 128-wide tiles");
   constexpr int STAGE_BYTES = stage_bytes(BN);
   constexpr uint32_t TMEM_COLS = BN;
   constexpr uint32_t W_BYTES = BN * 128;
@@ -55,10 +62,12 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
   if (a.done_flag != nullptr && a.done_flag[6] > 0 && a.row_base + m0 >= a.done_flag[6]) return;
   TraceRec* trc = tid == 0 ? trace_begin(a.trace, 100u + (uint32_t)(a.N >> 7)) : nullptr;
 
+  uint32_t rank = 0;
+  if constexpr (MC) rank = cluster_rank();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), A_SPLIT ? 1 : GROUP_THREADS);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -70,6 +79,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (MC) cluster_sync();       // the peer's barriers exist before anything is copied into it or signalled on it
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Everything above (barrier init, TMEM allocation) touched no global memory and overlapped the previous kernel's
   // tail; from here on this kernel reads what its predecessors wrote.
@@ -95,7 +105,11 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
           mbar_wait(empty_bar(s), phase ^ 1u);
           const uint32_t st_base = base + s * STAGE_BYTES;
           mbar_arrive_expect_tx(full_bar(s), 2 * TILE_BYTES + W_BYTES);
-          bulk_copy_g2s(st_base, atile0 + (size_t)kb * (2 * TILE_BYTES), 2 * TILE_BYTES, full_bar(s));
+          if constexpr (MC)
+            bulk_copy_g2s_multicast(st_base + rank * TILE_BYTES, atile0 + (size_t)kb * (2 * TILE_BYTES) + (size_t)rank * TILE_BYTES,
+                                    TILE_BYTES, full_bar(s), (uint16_t)3);
+          else
+            bulk_copy_g2s(st_base, atile0 + (size_t)kb * (2 * TILE_BYTES), 2 * TILE_BYTES, full_bar(s));
 #pragma unroll
           for (int h = 0; h < NW; ++h)
             bulk_copy_g2s(st_base + (2 + h) * TILE_BYTES, wtile0 + ((size_t)h * KB + kb) * (TILE_BYTES / 2), W_COPY, full_bar(s));
@@ -265,7 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
           umma_bf16(tmem_base, umma_desc_sw128(st_base + kk * 32), bd, (kb | kk) != 0 ? 1u : 0u, kIdesc);
           umma_bf16(tmem_base, umma_desc_sw128(st_base + TILE_BYTES + kk * 32), bd, 1u, kIdesc);
         }
-        umma_commit(empty_bar(s));       // frees the stage once the MMAs that read it have finished
+        if constexpr (MC) umma_commit_multicast(empty_bar(s), (uint16_t)3);
+        else umma_commit(empty_bar(s));  // frees the stage once the MMAs that read it have finished
       }
       umma_commit(accum_bar);            // accumulator complete -> epilogue
     }
@@ -277,6 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+  if constexpr (MC) cluster_sync();       // nobody leaves while the peer's commits may still arrive on its barriers
   trace_end(trc);
 }
 
@@ -337,6 +353,11 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_SET_SMEM(false, false, false, S, N); SCV_SET_SMEM(false, true, false, S, N); SCV_SET_SMEM(true, false, false, S, N); \
   SCV_SET_SMEM(true, true, false, S, N); SCV_SET_SMEM(false, false, true, S, N); SCV_SET_SMEM(true, false, true, S, N)
     SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256); SCV_SET_ALL(4, 64);
+#define SCV_SET_MC(O, R, S) \
+  SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, O, R, S, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, 128)))
+    SCV_SET_MC(false, false, 2); SCV_SET_MC(true, false, 2); SCV_SET_MC(false, true, 2);
+    SCV_SET_MC(false, false, 4); SCV_SET_MC(true, false, 4); SCV_SET_MC(false, true, 4);
+#undef SCV_SET_MC
 #undef SCV_SET_ALL
 #undef SCV_SET_SMEM
   }
@@ -378,7 +399,16 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // rows (two streams x 16 row tiles: the A tiles are re-read by twice as many CTAs out of an L2 that is the bottleneck
   // there), hence the bound on the row tiles.
   const bool narrow = !wide && mt <= tun().gemm_bn64 && n64 * mt <= tun().gemm_bn64_max_ctas;
-  if (narrow) {
+  const bool mc = !narrow && !wide && as && tun().gemm_mc != 0 && n128 % 2 == 0 && mt >= tun().gemm_mc_min_row_tiles;
+  if (mc) {
+    dim3 grid(n128, mt);
+    const int stages = tun().gemm_stages == 2 || tun().gemm_stages == 4 ? tun().gemm_stages : (n128 * mt <= 148 ? 4 : 2);
+#define SCV_LAUNCH_MC(O, R, S) \
+  SCV_CUDA(launch_k_cluster(gemm_tcgen05_kernel<true, O, R, S, 128, true>, grid, dim3(NUM_THREADS), (size_t)smem_bytes(S, 128), s, 2u, t))
+    if (stages == 4) { if (os) SCV_LAUNCH_MC(true, false, 4); else if (res) SCV_LAUNCH_MC(false, true, 4); else SCV_LAUNCH_MC(false, false, 4); }
+    else { if (os) SCV_LAUNCH_MC(true, false, 2); else if (res) SCV_LAUNCH_MC(false, true, 2); else SCV_LAUNCH_MC(false, false, 2); }
+#undef SCV_LAUNCH_MC
+  } else if (narrow) {
     dim3 grid(n64, mt);
     SCV_LAUNCH_MODE(4, 64);
   } else if (wide) {

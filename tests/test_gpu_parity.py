@@ -770,11 +770,12 @@ def test_tunables_never_change_tokens():
     z = W.make_latents(B, 2048, 1234)
     stoich, heads = W.make_conditioning(B, 13, 1234)
     kw = dict(temperature=0.001, max_len=64, type_masks=_cuda(OV.type_masks()), stop_boost=10.0, hard_stop_threshold=0.8)
-    defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, attn_bulk=0, attn_bulk_piece_kb=0, gemm_bn64=8)
+    defaults = dict(attn_ctas_per_sm=0, gemm_stages=0, subbatches=0, graph=1, attn_bulk=0, attn_bulk_piece_kb=0, gemm_bn64=8, gemm_mc=0, gemm_mc_min_row_tiles=9)
     base, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
     try:
         for cfg in (dict(attn_ctas_per_sm=3, gemm_stages=2), dict(subbatches=1), dict(subbatches=3), dict(attn_bulk=1),
-                    dict(attn_bulk=1, attn_bulk_piece_kb=16), dict(graph=0), dict(gemm_bn64=0), dict(gemm_bn64=16), dict(gemm_bn64=16, subbatches=3)):
+                    dict(attn_bulk=1, attn_bulk_piece_kb=16), dict(graph=0), dict(gemm_bn64=0), dict(gemm_bn64=16), dict(gemm_bn64=16, subbatches=3),
+                    dict(gemm_mc=1, gemm_mc_min_row_tiles=1), dict(gemm_mc=1, gemm_mc_min_row_tiles=1, subbatches=1, gemm_stages=4)):
             _lib.tune(**{**defaults, **cfg})
             t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), **kw)
             assert torch.equal(t, base), cfg
