@@ -399,7 +399,8 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // rows (two streams x 16 row tiles: the A tiles are re-read by twice as many CTAs out of an L2 that is the bottleneck
   // there), hence the bound on the row tiles.
   const bool narrow = !wide && mt <= tun().gemm_bn64 && n64 * mt <= tun().gemm_bn64_max_ctas;
-  const bool mc = !narrow && !wide && as && tun().gemm_mc != 0 && n128 % 2 == 0 && mt >= tun().gemm_mc_min_row_tiles;
+  const bool mc = !narrow && !wide && as && tun().gemm_mc != 0 && n128 % 2 == 0 && mt >= tun().gemm_mc_min_row_tiles &&
+                  t.kblocks >= tun().gemm_mc_min_kblocks;
   if (mc) {
     dim3 grid(n128, mt);
     const int stages = tun().gemm_stages == 2 || tun().gemm_stages == 4 ? tun().gemm_stages : (n128 * mt <= 148 ? 4 : 2);
