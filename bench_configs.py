@@ -161,6 +161,16 @@ def main():
         out = torch.zeros((hi - lo, 63), dtype=torch.int16, device=dev)
         # the product's multi-GPU plumbing: every chunk's int16 token ids are all-gathered asynchronously (NCCL runs on its
         # own stream), so the gather of chunk k overlaps the decode of chunk k + 1 (parallel.ChunkedGather)
+        # untimed warm-up, as for every other line of this file: one decode per distinct chunk size of this rank (workspace
+        # allocation, step graphs) and one gather (NCCL communicator), so the line is the steady state of a long search
+        sizes = sorted({min(hi - lo, (k + 1) * chunk) - min(hi - lo, k * chunk) for k in range(n_chunks)} - {0})
+        for n_w in sizes:
+            z = latent.slerp_rows(anchors, i1[:n_w], i2[:n_w], tt[:n_w])
+            latent.decode_z_batch(enc, dec, z, temperature=0.001, type_masks=masks, max_len=64)
+        if world > 1:
+            wg = parallel.ChunkedGather(pad_to=63, dtype=torch.int16)
+            wg.push(out[:8], [8] * world)
+            wg.finish()
         cg = parallel.ChunkedGather(pad_to=63, dtype=torch.int16) if world > 1 else None
         torch.cuda.synchronize()
         if world > 1:
@@ -203,7 +213,7 @@ def main():
             dt_rows = (time.perf_counter() - t1) * (N / 20000.0)
             emit(({"config": 4, "what": "SLERP latents -> heads_from_latent -> greedy decode (masks + stop head), "
                               "sharded over ranks, chunked asynchronous all-gather of int16 token ids (parallel.ChunkedGather)", "latents": N, "n_gpus": world,
-                              "seconds": dt, "formulas_per_s": N / dt, "max_len_gathered": int(gathered.shape[1]),
+                              "warmup": "one untimed decode per distinct chunk size + one gather", "seconds": dt, "formulas_per_s": N / dt, "max_len_gathered": int(gathered.shape[1]),
                               "mean_formula_len": float(lens.float().mean()), "distinct_candidates": len(formulas),
                               "decode_unique_seconds": dt_unique, "decode_every_row_seconds_extrapolated": dt_rows,
                               "sample": tok.decode_batch(gathered[:2])}))
