@@ -94,6 +94,7 @@ struct Tunables {
                            // each CTA loads one half (hi / lo) and multicasts it to both (2/3 of the L2 -> SM operand traffic)
   int gemm_mc_min_row_tiles;   // SCV_GEMM_MC_MIN_ROW_TILES: ... for launches with at least this many 128-row tiles
   int gemm_mc_min_kblocks;     // SCV_GEMM_MC_MIN_KBLOCKS: ... and at least this many 64-wide k-blocks
+  int attn_pages_regs;     // SCV_ATTN_PAGES_REGS: self-attention reads a sequence's page ids once into registers (lane l = page l)
   int attn_shared;         // SCV_ATTN_SHARED: shared memory tokens (RLOO) go through attention_cross_shared_kernel: one warp per
                            // (latent, head) serves all of the latent's samples (0 = the per-row kernel, samples adjacent for L2)
 };

@@ -245,6 +245,15 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
 
   const bool paged = a.page_table != nullptr;
   const int* pt = paged ? a.page_table + (size_t)(a.row_map != nullptr ? a.row_map[a.slot_base + b] : b) * a.pages_per_seq : nullptr;
+  // The sequence's page ids are read ONCE, lane l holding page l (the table was filled by the step's first kernel): a lookup
+  // per iteration put a dependent L2 round trip in front of every batch of K / V loads, five per item at 12 positions, in a
+  // kernel whose time is (dependent round trips per item) x (waves of warps).
+  const bool pages_in_regs = paged && a.pages_per_seq <= 32 && a.pages_regs != 0;
+  int my_page = 0;
+  if (pages_in_regs && lane < a.pages_per_seq && lane <= ((n - 1) >> kPageShift)) my_page = pt[lane];
+  auto page_of = [&](int p) -> int {          // p uniform over the warp
+    return pages_in_regs ? __shfl_sync(0xffffffffu, my_page, p >> kPageShift) : pt[p >> kPageShift];
+  };
   auto row_off = [&](int p) -> size_t {
     if (paged) return (size_t)pt[p >> kPageShift] * a.page_stride + (size_t)(p & (kPagePos - 1)) * a.row_stride + h * hd;
     return (size_t)sb * a.seq_stride + (size_t)p * a.row_stride + h * hd;
@@ -253,8 +262,10 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   const float4 q4 = e_ok ? *reinterpret_cast<const float4*>(a.q + (size_t)b * a.ldq + h * hd + e0) : zero4;
 
   if (a.knew != nullptr) {   // append (torch.cat in the reference, :1266-1267)
+    const size_t new_off = paged ? (size_t)page_of(n - 1) * a.page_stride + (size_t)((n - 1) & (kPagePos - 1)) * a.row_stride + h * hd
+                                 : row_off(n - 1);
     if (grp == 0 && e_ok) {
-      const size_t off = row_off(n - 1) + e0;
+      const size_t off = new_off + e0;
       *reinterpret_cast<float4*>(a.kcache + off) = *reinterpret_cast<const float4*>(a.knew + (size_t)b * a.ldn + h * hd + e0);
       *reinterpret_cast<float4*>(a.vcache + off) = *reinterpret_cast<const float4*>(a.vnew + (size_t)b * a.ldn + h * hd + e0);
       // (plain stores: the row is read back a few lines below by the other lanes of this warp)
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
   constexpr bool kFastAddr = UNR * PPI <= kPagePos;
   const long long kv_delta = a.vcache - a.kcache;
   auto iter_base = [&](int p0) -> const float* {     // K row of position p0 for this lane's head slice
-    if (paged) return a.kcache + (size_t)pt[p0 >> kPageShift] * a.page_stride + (size_t)(p0 & (kPagePos - 1)) * a.row_stride + h * hd + e0;
+    if (paged) return a.kcache + (size_t)page_of(p0) * a.page_stride + (size_t)(p0 & (kPagePos - 1)) * a.row_stride + h * hd + e0;
     return a.kcache + (size_t)sb * a.seq_stride + (size_t)p0 * a.row_stride + h * hd + e0;
   };
   for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
@@ -718,6 +729,7 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a_in.out_split == nullptr || a_in.hd % 8 == 0, "attention: SplitTile output needs head_dim %% 8 == 0");
   AttnArgs a = a_in;
   a.trace = trace_ptr();
+  a.pages_regs = tun().attn_pages_regs;
   a.max_n = std::max(a_in.max_n, a_in.hd);     // the score buffer doubles as the staging row of the split output
   const int warps = 8;
   int blocks = ceil_div(a.B * a.nhead, warps);

@@ -61,6 +61,7 @@ struct AttnArgs {
   // shared memory tokens (RLOO): the sequence of query row r is (slot_base + r) % seq_mod (0 = off); the launch's rows
   // are walked so that the samples of one latent are adjacent (they then hit the same K / V in L2)
   int seq_mod = 0;
+  int pages_regs = 1;                                    // set by the launcher (tunable attn_pages_regs)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 
