@@ -45,7 +45,8 @@ Tunables& tun() {
                        env_int("SCV_ATTN_BULK_MIN_ROWS", 256), env_int("SCV_ATTN_BULK_PIECE_KB", 0),
                        env_int("SCV_COND_TC_MIN_ROWS", 16384), env_int("SCV_CLUSTER", 0), env_int("SCV_CLUSTER_MAX_ROWS", 64), env_int("SCV_CLUSTER_ROWS", 0),
                        env_int("SCV_GEMM_BN64", 8), env_int("SCV_GEMM_BN64_MAX_CTAS", 148),
-                       env_int("SCV_GEMM_MC", 0), env_int("SCV_GEMM_MC_MIN_ROW_TILES", 9), env_int("SCV_GEMM_MC_MIN_KBLOCKS", 1), env_int("SCV_ATTN_PAGES_REGS", 1), env_int("SCV_ATTN_SHARED", 1)};
+                       env_int("SCV_GEMM_MC", 0), env_int("SCV_GEMM_MC_MIN_ROW_TILES", 9), env_int("SCV_GEMM_MC_MIN_KBLOCKS", 1), env_int("SCV_ATTN_PAGES_REGS", 1), env_int("SCV_ATTN_FORWARD", 1), env_int("SCV_ATTN_FORWARD_MIN_CTAS", 1024),
+                       env_int("SCV_ATTN_SHARED", 1)};
   return t;
 }
 unsigned tune_epoch() { return g_tune_epoch; }
@@ -257,7 +258,8 @@ int scv_tune(const char* key, int32_t value) {
               k == "attn_shared" ? &t.attn_shared : k == "gemm_bn64" ? &t.gemm_bn64 :
               k == "gemm_bn64_max_ctas" ? &t.gemm_bn64_max_ctas : k == "gemm_mc" ? &t.gemm_mc :
               k == "gemm_mc_min_row_tiles" ? &t.gemm_mc_min_row_tiles : k == "gemm_mc_min_kblocks" ? &t.gemm_mc_min_kblocks :
-              k == "attn_pages_regs" ? &t.attn_pages_regs : nullptr;
+              k == "attn_pages_regs" ? &t.attn_pages_regs : k == "attn_forward" ? &t.attn_forward :
+              k == "attn_forward_min_ctas" ? &t.attn_forward_min_ctas : nullptr;
   SCV_REQUIRE(slot != nullptr, "tune: unknown key '%s'", key);
   if (*slot != value) { *slot = value; ++g_tune_epoch; }
   return 0;

@@ -95,6 +95,8 @@ struct Tunables {
   int gemm_mc_min_row_tiles;   // SCV_GEMM_MC_MIN_ROW_TILES: ... for launches with at least this many 128-row tiles
   int gemm_mc_min_kblocks;     // SCV_GEMM_MC_MIN_KBLOCKS: ... and at least this many 64-wide k-blocks
   int attn_pages_regs;     // SCV_ATTN_PAGES_REGS: self-attention reads a sequence's page ids once into registers (lane l = page l)
+  int attn_forward;        // SCV_ATTN_FORWARD: teacher-forced passes stage a (sequence, head)'s K / V in shared memory once
+  int attn_forward_min_ctas;   // SCV_ATTN_FORWARD_MIN_CTAS: ... when there are at least this many (sequence, head) pairs
   int attn_shared;         // SCV_ATTN_SHARED: shared memory tokens (RLOO) go through attention_cross_shared_kernel: one warp per
                            // (latent, head) serves all of the latent's samples (0 = the per-row kernel, samples adjacent for L2)
 };

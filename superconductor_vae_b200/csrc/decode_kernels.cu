@@ -392,6 +392,140 @@ __global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Attention of the teacher-forced pass (rows_per_seq = L > 0: query row r is position r % L of sequence r / L).
+// All L queries of a (sequence, head) read the same keys, so one CTA per (sequence, head) stages that head's K / V rows in
+// shared memory ONCE (the per-row kernel re-read them per query: 8.9 TB/s of L2 traffic, 56 % of a forward pass) and its
+// warps take the positions round robin.  Per query the arithmetic and its order are attention_decode_v4_kernel's (same
+// chunks of UNR * PPI positions, same reduction tree, softmax and accumulation order): identical bits.
+// ---------------------------------------------------------------------------------------------
+template <int LPP>
+__global__ void __launch_bounds__(256) attention_forward_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) float fw_smem[];
+  pdl_wait();
+  constexpr int PPI = 32 / LPP, UNR = 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int L = a.rows_per_seq, hd = a.hd, sb = blockIdx.x / a.nhead, h = blockIdx.x % a.nhead;
+  const int n_keys = a.fixed_len >= 0 ? a.fixed_len : L;
+  float* Ks = fw_smem;
+  float* Vs = Ks + (size_t)n_keys * hd;
+  float* sc = Vs + (size_t)n_keys * hd + (size_t)warp * a.max_n;
+  TraceRec* trc = threadIdx.x == 0 ? trace_begin(a.trace, 5u) : nullptr;
+  {
+    const int c4n = hd >> 2;
+    const float* kg = a.kcache + (size_t)sb * a.seq_stride + h * hd;
+    const float* vg = a.vcache + (size_t)sb * a.seq_stride + h * hd;
+    for (int i = threadIdx.x; i < n_keys * c4n; i += blockDim.x) {
+      const int p = i / c4n, c = i - p * c4n;
+      reinterpret_cast<float4*>(Ks)[i] = __ldcs(reinterpret_cast<const float4*>(kg + (size_t)p * a.row_stride) + c);
+      reinterpret_cast<float4*>(Vs)[i] = __ldcs(reinterpret_cast<const float4*>(vg + (size_t)p * a.row_stride) + c);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int grp = lane / LPP, e0 = 4 * (lane % LPP);
+  const bool e_ok = e0 < hd;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned char* ks = a.key_skip != nullptr ? a.key_skip + (size_t)sb * L : nullptr;
+  for (int pos = warp; pos < L; pos += nwarps) {
+    const int b = sb * L + pos;
+    const int n = a.fixed_len >= 0 ? a.fixed_len : pos + 1;
+    // (fetching the warp's queries eight positions ahead was measured: 80 registers, 8 % slower)
+    const float4 q4 = e_ok ? *reinterpret_cast<const float4*>(a.q + (size_t)b * a.ldq + h * hd + e0) : zero4;
+    for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+      float4 kv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int p = p0 + u * PPI + grp;
+        kv[u] = (p < n && e_ok) ? *reinterpret_cast<const float4*>(Ks + (size_t)p * hd + e0) : zero4;
+      }
+      float d[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) d[u] = fmaf(q4.x, kv[u].x, fmaf(q4.y, kv[u].y, fmaf(q4.z, kv[u].z, q4.w * kv[u].w)));
+      if constexpr (LPP == 16) {
+        const int sub = lane & 15;
+        const bool up8 = (sub & 8) != 0, up4 = (sub & 4) != 0;
+        const float r0 = __shfl_xor_sync(0xffffffffu, up8 ? d[0] : d[2], 8);
+        const float r1 = __shfl_xor_sync(0xffffffffu, up8 ? d[1] : d[3], 8);
+        const float e0s = (up8 ? d[2] : d[0]) + r0, e1s = (up8 ? d[3] : d[1]) + r1;
+        float f = (up4 ? e1s : e0s) + __shfl_xor_sync(0xffffffffu, up4 ? e0s : e1s, 4);
+        f += __shfl_xor_sync(0xffffffffu, f, 2);
+        f += __shfl_xor_sync(0xffffffffu, f, 1);
+        const int u_mine = 2 * (sub >> 3) + ((sub >> 2) & 1);
+        const int p = p0 + u_mine * PPI + grp;
+        if ((sub & 3) == 0 && p < n) sc[p] = f * a.scale;
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          float dd = d[u];
+#pragma unroll
+          for (int o = LPP / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+          const int p = p0 + u * PPI + grp;
+          if ((lane % LPP) == 0 && p < n) sc[p] = dd * a.scale;
+        }
+      }
+    }
+    __syncwarp();
+    if (ks != nullptr) {
+      for (int p = lane; p < n; p += 32)
+        if (ks[p] != 0) sc[p] = -INFINITY;
+      __syncwarp();
+    }
+    float m = -INFINITY;
+    for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[p]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int p = lane; p < n; p += 32) {
+      const float e = expf(sc[p] - m);
+      sc[p] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) sc[p] = sc[p] / sum;
+    __syncwarp();
+    float4 acc = zero4;
+    for (int p0 = 0; p0 < n; p0 += UNR * PPI) {
+      float4 vv[UNR];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int p = p0 + u * PPI + grp;
+        const bool ok = p < n && e_ok;
+        vv[u] = ok ? *reinterpret_cast<const float4*>(Vs + (size_t)p * hd + e0) : zero4;
+        w[u] = ok ? sc[p] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        acc.x = fmaf(w[u], vv[u].x, acc.x); acc.y = fmaf(w[u], vv[u].y, acc.y);
+        acc.z = fmaf(w[u], vv[u].z, acc.z); acc.w = fmaf(w[u], vv[u].w, acc.w);
+      }
+    }
+#pragma unroll
+    for (int o = LPP; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (grp == 0 && e_ok) {
+      if (a.out_split == nullptr) {
+        *reinterpret_cast<float4*>(a.out + (size_t)b * a.ldo + h * hd + e0) = acc;
+      } else {
+        uint32_t hi0, lo0, hi1, lo1;
+        split_pair(acc.x, acc.y, hi0, lo0);
+        split_pair(acc.z, acc.w, hi1, lo1);
+        const int col = h * hd + e0;
+        const int mt = b >> 7, ri = b & 127, kb = col >> 6, cj = (col & 63) >> 3;
+        uint8_t* dst = a.out_split + ((size_t)mt * a.kb_out + kb) * 32768 + (size_t)ri * 128 + (size_t)((cj ^ (ri & 7)) << 4) +
+                       (size_t)((col & 7) >> 2) * 8;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(hi0, hi1);
+        *reinterpret_cast<uint2*>(dst + 16384) = make_uint2(lo0, lo1);
+      }
+    }
+    __syncwarp();
+  }
+  trace_end(trc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cross-attention over SHARED memory tokens (RLOO: the k samples of a latent attend to the same projected K / V).
 // One warp per (latent, head): every 16-byte piece of the latent's K / V is loaded ONCE into registers and used for up to
 // KS query rows (the samples, rows j, j + seq_mod, j + 2 seq_mod, ... of the launch), so the stream through L2 and the
@@ -746,6 +880,30 @@ int launch_attention(const AttnArgs& a_in, cudaStream_t s) {
   SCV_REQUIRE(a.rows_per_seq == 0 || v4, "attention: the teacher-forced layout needs head_dim %% 4 == 0 and 16-byte aligned rows");
   SCV_REQUIRE(a.seq_mod == 0 || v4, "attention: shared memory tokens need head_dim %% 4 == 0 and 16-byte aligned rows");
   SCV_REQUIRE(a.row_map == nullptr || v4, "attention: compaction of finished rows needs head_dim %% 4 == 0 and 16-byte aligned rows");
+  // teacher-forced pass: one CTA per (sequence, head) with that head's K / V staged in shared memory
+  // (from 128 sequences on: below that its (sequence, head) CTAs are too few and the per-row kernel's warps fill the GPU better)
+  if (a.rows_per_seq > 0 && v4 && tun().attn_forward != 0 && a.page_table == nullptr && a.knew == nullptr && a.row_map == nullptr &&
+      a.seq_mod == 0 && a.B % a.rows_per_seq == 0 && (a.B / a.rows_per_seq) * a.nhead >= tun().attn_forward_min_ctas) {
+    const int n_keys = a.fixed_len >= 0 ? a.fixed_len : a.rows_per_seq;
+    const size_t smem_f = ((size_t)2 * n_keys * a.hd + (size_t)warps * a.max_n) * sizeof(float);
+    if (smem_f <= 200 * 1024) {
+      static bool attr_f[64] = {};
+      if (first_use_on_device(attr_f)) {
+        SCV_CUDA(cudaFuncSetAttribute(attention_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCV_CUDA(cudaFuncSetAttribute(attention_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCV_CUDA(cudaFuncSetAttribute(attention_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCV_CUDA(cudaFuncSetAttribute(attention_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      }
+      const dim3 grid_f((a.B / a.rows_per_seq) * a.nhead), block_f(warps * 32);
+      const int lanes = a.hd / 4;
+      if (lanes <= 4) SCV_CUDA(launch_k(attention_forward_kernel<4>, grid_f, block_f, smem_f, s, a));
+      else if (lanes <= 8) SCV_CUDA(launch_k(attention_forward_kernel<8>, grid_f, block_f, smem_f, s, a));
+      else if (lanes <= 16) SCV_CUDA(launch_k(attention_forward_kernel<16>, grid_f, block_f, smem_f, s, a));
+      else SCV_CUDA(launch_k(attention_forward_kernel<32>, grid_f, block_f, smem_f, s, a));
+      SCV_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // shared memory tokens, whole groups of seq_mod rows in this launch: one warp serves the k samples of a (latent, head)
   const int k_shared = (a.seq_mod > 0 && a.row_map == nullptr && a.fixed_len >= 0 && a.knew == nullptr && a.page_table == nullptr &&
                         a.rows_per_seq == 0 && a.key_skip == nullptr && a.B % a.seq_mod == 0 && a.slot_base % a.seq_mod == 0)

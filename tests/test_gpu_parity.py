@@ -556,6 +556,16 @@ def test_teacher_forced_forward_matches_reference(golden_dir, name, shape):
     torch.testing.assert_close(typ.cpu(), g["type_logits"], rtol=2e-3, atol=2e-3)
     torch.testing.assert_close(dup.cpu(), g["site_dup_logits"], rtol=2e-3, atol=2e-3)
     assert (gen.cpu().to(torch.int16) == g["generated"]).float().mean() > 0.98
+    # the per-(sequence, head) kernel with K / V staged in shared memory (default) and the per-row kernel give the same bits
+    try:
+        _lib.tune(attn_forward=1, attn_forward_min_ctas=1)
+        fw_out = dec(_cuda(z), g["target_tokens"].to(DEV), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads))
+        _lib.tune(attn_forward=0)
+        ref_out = dec(_cuda(z), g["target_tokens"].to(DEV), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads))
+    finally:
+        _lib.tune(attn_forward=1, attn_forward_min_ctas=1024)
+    for x, y, w in zip((logits, gen, stop, typ, dup), ref_out, fw_out):
+        assert torch.equal(x, y) and torch.equal(w, y)
     # consistency with the decode path: teacher forcing on the ids the greedy decode emitted reproduces them
     t, _, _ = dec.generate_with_kv_cache(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), temperature=0.001,
                                          max_len=g["target_tokens"].shape[1])
