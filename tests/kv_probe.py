@@ -52,3 +52,22 @@ bad = [r for r in range(rows) if not torch.equal(tc[r, : int(lens[r])], rt[r, : 
 print(f"SCV_LINEAR_IMPL={os.environ.get('SCV_LINEAR_IMPL', '0')} "
       f"rows={rows} seed={seed} chunk={chunk}: {rows - len(bad)}/{rows} rows equal to the oracle up to their END "
       f"(oracle {dt:.1f} s); differing rows: {bad[:16]}")
+# every differing row: where it leaves the oracle and how close the oracle's decision was there (a near-tie inside the
+# engine's logit tolerance of 2e-4 can fall the other way; anything larger would be a bug)
+for r in bad[:8]:
+    n_cmp = min(int(lens[r]), tc.shape[1], rt.shape[1])
+    pos = int((tc[r, :n_cmp] != rt[r, :n_cmp]).nonzero()[0])
+    trace = {}
+    DO.generate_with_kv_cache(sd, 8, z[r:r + 1], stoich_pred=stoich[r:r + 1], heads_pred={k: v[r:r + 1] for k, v in heads.items()},
+                              type_masks=masks, trace=trace, **kw)       # (same max_len: the length boost depends on it)
+    lg = trace["final_logits"][pos][0]
+    top = lg.topk(2)
+    print(f"   row {r} leaves the oracle at step {pos}: oracle picks {int(top.indices[0])} over {int(top.indices[1])} by "
+          f"{float(top.values[0] - top.values[1]):.3e} (logits {float(top.values[0]):.4f} / {float(top.values[1]):.4f}); "
+          f"engine picked {int(tc[r, pos])}")
+    if "type_logits" in trace and not bool(torch.isfinite(lg[int(tc[r, pos])])):
+        tl = trace["type_logits"][pos][0]
+        tt2 = tl.topk(2)
+        print(f"      the engine's token is outside the oracle's type mask: the oracle's type head picks class {int(tt2.indices[0])} over "
+              f"{int(tt2.indices[1])} by {float(tt2.values[0] - tt2.values[1]):.3e} (type logits {[round(float(v), 5) for v in tl]})")
+
