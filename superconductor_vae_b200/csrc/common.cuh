@@ -1,5 +1,8 @@
 // Shared helpers for the scvae_b200 engine (sm_100a only).
 #pragma once
+#ifndef SCV_SPLIT_FP16
+#define SCV_SPLIT_FP16 0
+#endif
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -220,14 +223,31 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
 
-// Two fp32 values -> packed bf16 pairs hi = bf16(x) and lo = bf16(x - hi) (element 0 in the low half).
-// hi + lo carries 16 mantissa bits of x; both MMAs against exact-bf16 weights are exact products.
+// Two fp32 values -> packed 16-bit pairs hi = r16(x) and lo = r16(x - hi) (element 0 in the low half), the operands of the
+// two MMAs the tensor-core projections issue per weight tile.
+//   bf16 (default): hi + lo carries 16 mantissa bits of x; products against exact-bf16 weights are exact in fp32.
+//   kSplitFp16 (-DSCV_SPLIT_FP16=1): r16 = fp16, 22 mantissa bits of x, weight tiles stored as fp16 too (the bf16-rounded
+//     weights are exact in fp16 down to 2^-17 in magnitude), |x| > 65504 saturates.  Measured (profiles/split_error_r02.log):
+//     the full GPU suite passes and the error against fp64 halves at K = 512 (rms 2.7e-6 -> 1.25e-6 on O(1) outputs) but
+//     stays 5e-6 at K = 2048: from there on the error is the tensor core's own fp32 accumulation (hundreds of truncating
+//     accumulate steps; an fp32 FMA loop has 3e-7), which no split can remove.  Not worth the range limit: off.
+//   (A bf16 hi with an fp16 residual would keep the range, but the hardware rejects an f16 x bf16 MMA for kind::f16 even
+//   though the instruction descriptor has separate A / B format fields: "illegal instruction" on B200.)
+constexpr bool kSplitFp16 = SCV_SPLIT_FP16 != 0;
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  const __nv_bfloat162 h = __halves2bfloat162(ha, hb);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ha), b - __bfloat162float(hb));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  if constexpr (kSplitFp16) {
+    const __half ha = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)), hb = __float2half_rn(fminf(fmaxf(b, -65504.f), 65504.f));
+    const __half2 h = __halves2half2(ha, hb);
+    const __half2 l = __floats2half2_rn(a - __half2float(ha), b - __half2float(hb));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat162 h = __halves2bfloat162(ha, hb);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ha), b - __bfloat162float(hb));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
 }
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG for the multinomial sampler ----

@@ -308,7 +308,9 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, __nv_bfloat16* 
     const int chunk = chunk_phys ^ (r & 7);                 // logical 16-byte chunk stored at this position
     const int nt = (int)(tile / kblocks), kb = (int)(tile % kblocks);
     const int n = nt * 128 + r, k = kb * 64 + chunk * 8 + e;
-    dst[i] = __float2bfloat16_rn((n < N && k < K) ? src[(int64_t)n * K + k] : 0.f);
+    const float v = (n < N && k < K) ? src[(int64_t)n * K + k] : 0.f;
+    if constexpr (kSplitFp16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);     // 16-bit storage either way
+    else dst[i] = __float2bfloat16_rn(v);
   }
 }
 

@@ -41,7 +41,7 @@ constexpr int BN2 = 256;                                  // output columns of a
 constexpr int STAGE2_BYTES = 3 * TILE_BYTES;              // A hi | A lo | this CTA's 128 weight rows
 __host__ __device__ constexpr int smem2_bytes(int stages) { return stages * STAGE2_BYTES + 1024 + 128; }
 // kind::f16: D = f32, A = B = bf16, K-major, M = 256 (pair), N = 256
-constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kIdesc2 = (1u << 4) | kIdescFormats | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -65,8 +65,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn.
+// (A and B formats: 0 = f16, 1 = bf16; common.cuh kSplitFp16)
+constexpr uint32_t kIdescFormats = kSplitFp16 ? 0u : ((1u << 7) | (1u << 10));
 __host__ __device__ constexpr uint32_t idesc_for(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | kIdescFormats | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t kIdesc) {
