@@ -561,6 +561,45 @@ class EnhancedTransformerDecoder(nn.Module):
         mask = (torch.arange(Lq, device=tokens.device).unsqueeze(0) <= end_pos.unsqueeze(1)).float()
         return tokens, lp, ent, mask
 
+    @torch.no_grad()
+    def rollout_with_rewards(self, z, targets: torch.Tensor, n_samples: int = 1, reward_config=None, constraint_config=None,
+                             family_predictions: Optional[torch.Tensor] = None, family_config=None,
+                             use_semantic_fractions: bool = False, fraction_token_start: int = 0,
+                             fraction_values: Optional[torch.Tensor] = None, **rollout_kwargs):
+        """One call for the rollout block of the reference's RL loss (scripts/train_v12_clean.py:2677-2766):
+        expand the batch to n_samples rollouts per latent (sample-major, the samples of a latent share its memory tokens),
+        sample with log-probs / entropy / mask, pad or truncate to the targets' length, score every rollout with
+        `compute_reward_gpu_native` and, when `constraint_config` is given, add `compute_constraint_rewards` - all
+        enqueued on the current stream, nothing returns to the host between the decode and the reward kernels.
+        `rollout_kwargs` are `sample_for_reinforce`'s (BASE-batch tensors).  Returns
+        (sampled_tokens, log_probs, entropy, mask, task_rewards), each with n_samples * batch rows."""
+        from . import constraints as _constraints, reward as _reward
+        k = int(n_samples)
+        if k < 1:
+            raise ValueError("n_samples must be >= 1")
+        if k > 1:
+            rollout_kwargs["_n_samples"] = k
+        tokens, lp, ent, mask = self.sample_for_reinforce(z, **rollout_kwargs)
+        T = targets.size(1)
+        if tokens.size(1) < T:                                             # (:2733-2744)
+            pad = (0, T - tokens.size(1))
+            tokens, lp = nn.functional.pad(tokens, pad, value=PAD_IDX), nn.functional.pad(lp, pad, value=0.0)
+            ent, mask = nn.functional.pad(ent, pad, value=0.0), nn.functional.pad(mask, pad, value=0.0)
+        elif tokens.size(1) > T:
+            tokens, lp, ent, mask = tokens[:, :T], lp[:, :T], ent[:, :T], mask[:, :T]
+        tgt = targets.to(tokens.device)
+        tgt = tgt.repeat(k, 1) if k > 1 else tgt                            # (:2688)
+        rewards = _reward.compute_reward_gpu_native(tokens, tgt, mask.bool(), config=reward_config, pad_idx=PAD_IDX,
+                                                    end_idx=END_IDX, use_semantic_fractions=use_semantic_fractions,
+                                                    fraction_token_start=fraction_token_start, fraction_values=fraction_values)
+        if constraint_config is not None:                                   # (:2754-2766)
+            fam = family_predictions
+            if fam is not None and k > 1:
+                fam = fam.repeat(k, 1)
+            rewards = rewards + _constraints.compute_constraint_rewards(tokens, mask, config=constraint_config,
+                                                                        family_predictions=fam, family_config=family_config)
+        return tokens, lp, ent, mask, rewards
+
     def generate_formulas_fast(self, z, encoder_skip=None, stoich_pred=None, temperature: float = 1.0,
                                max_len: Optional[int] = None, cached_memory: Optional[torch.Tensor] = None,
                                tokenizer=None) -> List[str]:

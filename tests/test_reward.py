@@ -132,6 +132,50 @@ def test_reward_of_engine_rollout_rlo_shape():
 
 
 @pytest.mark.gpu
+def test_rollout_with_rewards_is_the_reference_block_in_one_call():
+    """decoder.rollout_with_rewards = the rollout block of the reference's RL loss (scripts/train_v12_clean.py:2677-2766):
+    k samples per latent (sample-major), pad / truncate to the targets' length, task reward + constraint rewards.  Checked
+    against the same steps done one by one with the reference's way of expanding the inputs (repeat k times), and the
+    rewards of 64 rows against the oracle."""
+    import superconductor_vae_b200 as S
+    from superconductor_vae_b200 import constraints as K
+    dev = "cuda:0"
+    B, k, V = 160, 3, 4752
+    dec = S.EnhancedTransformerDecoder.from_state_dict(Sy.make_decoder_state_dict(Sy.C512, 0), nhead=8, device=dev)
+    z = Sy.make_latents(B, 2048, 11).to(dev)
+    st, hp = Sy.make_conditioning(B, 13, 11)
+    st, hp = st.to(dev), {n: v.to(dev) for n, v in hp.items()}
+    _, targets, _ = Sy.make_reward_rows(B, 40, V, 5)                   # targets shorter than max_len: the rollout is truncated
+    fv = Sy.make_fraction_values(V, 143, 7).to(dev)
+    kw = dict(stoich_pred=st, heads_pred=hp, temperature=1.2, max_len=64, stop_boost=10.0, _seed=3)
+    ccfg = K.ConstraintRewardConfig()
+    tok, lp, ent, mask, rew = dec.rollout_with_rewards(z, targets, n_samples=k, reward_config=R.GPURewardConfigV14(),
+                                                       constraint_config=ccfg, use_semantic_fractions=True,
+                                                       fraction_token_start=143, fraction_values=fv, **kw)
+    assert tok.shape == (k * B, 40) and lp.shape == tok.shape and ent.shape == tok.shape and mask.shape == tok.shape
+    rep = lambda t: t.repeat(k, *([1] * (t.dim() - 1)))
+    t0, lp0, en0, mk0 = dec.sample_for_reinforce(rep(z), stoich_pred=rep(st), heads_pred={n: rep(v) for n, v in hp.items()},
+                                                 temperature=1.2, max_len=64, stop_boost=10.0, _seed=3)
+    L0 = t0.shape[1]
+    if L0 < 40:
+        pad = (0, 40 - L0)
+        t0, lp0 = torch.nn.functional.pad(t0, pad, value=0), torch.nn.functional.pad(lp0, pad)
+        en0, mk0 = torch.nn.functional.pad(en0, pad), torch.nn.functional.pad(mk0, pad)
+    t0, lp0, en0, mk0 = t0[:, :40], lp0[:, :40], en0[:, :40], mk0[:, :40]
+    assert torch.equal(tok, t0) and torch.equal(lp, lp0) and torch.equal(ent, en0) and torch.equal(mask, mk0)
+    tg = targets.repeat(k, 1).to(dev)
+    r0 = R.compute_reward_gpu_native(t0, tg, mk0.bool(), config=R.GPURewardConfigV14(), use_semantic_fractions=True,
+                                     fraction_token_start=143, fraction_values=fv)
+    r0 = r0 + K.compute_constraint_rewards(t0, mk0, config=ccfg)
+    assert torch.equal(rew, r0)
+    ref = OR.compute_reward(t0[:64].cpu().numpy(), tg[:64].cpu().numpy(), mk0[:64].bool().cpu().numpy(), OR.RewardConfig(v14=True), 2,
+                            True, 143, fv.cpu().numpy())
+    task = R.compute_reward_gpu_native(t0[:64], tg[:64], mk0[:64].bool(), config=R.GPURewardConfigV14(), use_semantic_fractions=True,
+                                       fraction_token_start=143, fraction_values=fv)
+    assert np.abs(task.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.gpu
 def test_kernel_rows_longer_than_three_chunks():
     """70 rows of 100 positions (four 32-position chunks, ragged last one), V14 continuous and tiered digit-level paths."""
     dev = "cuda:0"
