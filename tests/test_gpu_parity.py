@@ -738,6 +738,30 @@ def test_compact_finished_matches_reference_semantics_up_to_end(rows):
             assert int(ends.max()) - int(ends.min()) >= 5                          # the rollout really is ragged
 
 
+def test_compact_finished_with_shared_memory_tokens():
+    """Both opt-ins at once: RLOO rollouts whose samples share a latent's memory tokens (`_n_samples`) while finished rows are
+    retired.  Compaction scatters a latent's samples over the slots, so cross-attention goes back to the per-row kernel with
+    the slot -> row -> latent lookup; outputs up to every row's first END equal the plain repeated-input rollout."""
+    sd = W.make_decoder_state_dict(W.C512, 0)
+    dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=8, device=DEV)
+    base, k = 300, 4
+    z = W.make_latents(base, 2048, 77)
+    stoich, heads = W.make_conditioning(base, 13, 77)
+    kw = dict(temperature=1.2, max_len=64, stop_boost=10.0, _seed=5)
+    rep = lambda t: t.repeat(k, *([1] * (t.dim() - 1)))
+    t0, lp0, en0, mk0 = dec.sample_for_reinforce(_cuda(rep(z)), stoich_pred=_cuda(rep(stoich)),
+                                                 heads_pred=_cuda({n: rep(v) for n, v in heads.items()}), **kw)
+    dec.compact_finished = True
+    try:
+        t1, lp1, en1, mk1 = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), _n_samples=k, **kw)
+    finally:
+        dec.compact_finished = False
+    assert t0.shape == t1.shape and torch.equal(mk0, mk1)
+    keep = mk0.bool()                                   # up to and including the first END
+    assert torch.equal(t1[keep], t0[keep]) and torch.equal(lp1[keep], lp0[keep]) and torch.equal(en1[keep], en0[keep])
+    assert int(t1[~keep].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("base,k,shape", [(96, 4, "C512"), (1024, 4, "C512"), (700, 3, "C512"), (512, 6, "C512"), (160, 5, "C576"),
                                           (70, 2, "TINY")])
 def test_rloo_samples_sharing_memory_match_repeated_inputs(base, k, shape):
