@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) attention_forward_kernel(AttnArgs a) {
 // order), so the output bits are identical.
 // ---------------------------------------------------------------------------------------------
 template <int LPP, int KS>
-__global__ void __launch_bounds__(256) attention_cross_shared_kernel(AttnArgs a, int k_local) {
+__global__ void __launch_bounds__(256, 4) attention_cross_shared_kernel(AttnArgs a, int k_local) {
   extern __shared__ float sc_all[];
   pdl_wait();
   if (a.st != nullptr && a.st->done) return;
