@@ -216,8 +216,20 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs a) {
 // reads 32 / LPP positions (512 B for head_dim 64) and the dot-product reduction runs over LPP lanes only.  The
 // first version above issued one 4-byte load per lane and position and was instruction-issue bound (ncu r01b:
 // issue slots 49 % busy at 47 % of DRAM peak); this one moves the same bytes with ~4x fewer instructions.
+// Registers: left alone the compiler takes 48 (5 CTAs = 40 warps per SM); the kernel waits on memory (ncu: 10-17 warps stalled
+// on the long scoreboard per issued instruction, 55 % warps active), so it is capped at 40 registers = 6 CTAs per SM (8 bytes
+// spilled).  Same box, alternating builds: 67.1 ms per 4096-latent decode against 68.9 (63-step decode 225.5 against 230.8);
+// 32 registers (8 CTAs, 52 bytes spilled) 67.2-67.9.  -DSCV_ATTN_MIN_CTAS=0 restores the uncapped build.
+#ifndef SCV_ATTN_MIN_CTAS
+#define SCV_ATTN_MIN_CTAS 6
+#endif
+#if SCV_ATTN_MIN_CTAS > 0
+#define SCV_ATTN_BOUNDS __launch_bounds__(256, SCV_ATTN_MIN_CTAS)
+#else
+#define SCV_ATTN_BOUNDS __launch_bounds__(256)
+#endif
 template <int LPP>
-__global__ void __launch_bounds__(256) attention_decode_v4_kernel(AttnArgs a) {
+__global__ void SCV_ATTN_BOUNDS attention_decode_v4_kernel(AttnArgs a) {
   extern __shared__ float sc_all[];
   pdl_wait();
   if (a.st != nullptr && a.st->done) return;
