@@ -36,8 +36,16 @@ int64_t scv_launch_count(void);
 /* Run-time tunables of the launch configuration (no reference counterpart: the reference has no launch configuration).
  * Keys: "attn_ctas_per_sm" (0 = one CTA per 8 (row, head) items; k > 0 = persistent attention grid of k CTAs per SM so
  * that another sub-batch's projections can run on the same SMs), "gemm_stages" (0 auto / 2 / 4), "subbatches"
- * (0 auto; row ranges decoded on separate streams), "sub_min_rows", "graph" (0 / 1: CUDA-graph step replay).
- * Defaults come from the SCV_* environment variables read at load.  Unknown keys return 1. */
+ * (0 auto; row ranges decoded on separate streams), "sub_min_rows", "graph" (0 / 1: CUDA-graph step replay),
+ * "gemm_bn64" / "gemm_bn64_max_ctas" (128 x 64 projection tiles for launches of at most that many row tiles / CTAs),
+ * "gemm_mc" / "gemm_mc_min_row_tiles" / "gemm_mc_min_kblocks" (opt-in: column-tile pairs share the A tile by multicast),
+ * "attn_bulk" / "attn_bulk_min_rows" / "attn_bulk_piece_kb" (opt-in: bulk-copy staged cross-attention), "attn_shared"
+ * (shared memory tokens: one warp per (latent, head) serves all samples), "attn_forward" / "attn_forward_min_ctas"
+ * (teacher-forced passes: K / V of a (sequence, head) staged in shared memory), "attn_pages_regs", "cond_tc_min_rows"
+ * (rows from which the small conditioning projections use the tensor cores), "cluster" / "cluster_max_rows" /
+ * "cluster_rows" (opt-in cluster-parallel small-batch kernel).  No setting changes a token (tests/test_gpu_parity.py
+ * test_tunables_never_change_tokens).  Defaults come from the SCV_* environment variables read at load (common.cuh
+ * Tunables).  Unknown keys return 1. */
 int scv_tune(const char* key, int32_t value);
 
 /* Debug: CTA residency trace of the step kernels (projection and attention CTAs log kernel id, SM, start and end time).
