@@ -298,7 +298,12 @@ struct LinearArgs {
   const void* next_w = nullptr; size_t next_w_bytes = 0;   // tiled weights of the NEXT projection: prefetched into L2
   // LayerNorm(y) written as a SplitTile by the same kernel (gemm_tcgen05_ln.cu; callers check tc_res_ln_ok first)
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr; void* ln_out_split = nullptr;
+  // *nonfinite_flag |= 1 when an output (fp32 rows only) is NaN / +-inf (mode 1) or NaN (mode 2); null: no check.  Lets the
+  // sampling path learn "some adjusted logit of the batch is not finite" (reference :1464-1466) from the kernels that
+  // produce the logits and the stop logit instead of a separate pass over all logits.
+  int* nonfinite_flag = nullptr; int nonfinite_mode = 0;
 };
+__device__ __forceinline__ bool nonfinite_hit(float v, int mode) { return mode == 2 ? isnan(v) : (isnan(v) || isinf(v)); }
 int launch_linear_simt(const LinearArgs& a, cudaStream_t s);
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s);
 bool tc_persistent_ok(const LinearArgs& a);

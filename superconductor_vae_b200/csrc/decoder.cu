@@ -799,8 +799,17 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   oa.a_split = xn_s; oa.y_split = h2_s; oa.row_base = r0;
   next(oa, D->out_b.wt, c.vocab_size, d);
   SCV_TRY(launch_linear(oa, 0, s));
+  // Sampling modes run two sampler kernels because the reference's uniform fallback is BATCH-global (H2, :1464-1466): the
+  // first only finds out whether any adjusted logit of the batch is NaN / +-inf.  Without a type mask and without the hard
+  // stop (the two adjustments that write -inf) that is the case exactly when a raw logit is non-finite or a stop logit is
+  // NaN, which the kernels producing them report on the fly - so the first sampler kernel (a pass over all B x V logits)
+  // is not launched.  With the row-local fallback (flags bit 0 clear) its result is never read at all.
+  const bool two_phase_here = !(A->temperature < 0.01f) || A->want_entropy;
+  const bool skip_phase1 = two_phase_here && (((A->flags & 1u) == 0) ||
+                                              (A->type_masks == nullptr && !(A->stop_boost > 0.f && A->hard_stop_threshold > 0.f)));
   LinearArgs ob_ = lin_args(h2, d, D->out_b, logits, c.vocab_size, B, ACT_NONE, done);
   ob_.a_split = h2_s; ob_.row_base = r0;
+  if (skip_phase1 && (A->flags & 1u) != 0) { ob_.nonfinite_flag = &st->degenerate; ob_.nonfinite_mode = 1; }
   SCV_TRY(launch_linear(ob_, 0, s));
   if (A->type_masks != nullptr) {
     SCV_TRY(norm(D->tt_ln, h1));
@@ -814,12 +823,15 @@ static int decode_rows(scv_decoder* D, const scv_generate_args* A, int steps_max
   }
   if (A->stop_boost > 0.f) {
     SCV_TRY(launch_linear(lin_args(x, d, D->stop_a, t3, d / 4, B, ACT_GELU, done), 0, s));
-    SCV_TRY(launch_linear(lin_args(t3, d / 4, D->stop_b, slog, 1, B, ACT_NONE, done), 0, s));
+    LinearArgs sb_ = lin_args(t3, d / 4, D->stop_b, slog, 1, B, ACT_NONE, done);
+    if (skip_phase1 && (A->flags & 1u) != 0) { sb_.nonfinite_flag = &st->degenerate; sb_.nonfinite_mode = 2; }   // sigmoid(+-inf) is finite
+    SCV_TRY(launch_linear(sb_, 0, s));
   }
   if (A->site_dup_threshold > 0.f) {      // site_dup_head (:1427); position 0 never gates but the launch list stays fixed
     SCV_TRY(launch_linear(lin_args(x, d, D->dup_a, t3, d / 4, B, ACT_GELU, done), 0, s));
     SCV_TRY(launch_linear(lin_args(t3, d / 4, D->dup_b, D->dlog.as<float>() + r0, 1, B, ACT_NONE, done), 0, s));
   }
+  if (skip_phase1) return 0;
   return launch_sampler(sp, 1, s);
 }
 

@@ -35,7 +35,10 @@ namespace {
 // the MMAs of BOTH CTAs that read it are done (each commit arrives on both empty barriers).  Per k-block a CTA then pulls
 // 32 KB instead of 48 KB out of L2 (ncu: the K = 2048 projection moves 210 MB through the crossbar in 21 us, i.e. it runs at
 // the L2's ~10 TB/s).
-template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN, bool MC = false>
+// NFC: report NaN / +-inf outputs through TcArgs::nonfinite_flag (logits projection of the sampling modes).  A template
+// flag, not a run-time test: the run-time test alone, never taken, cost 2.5 % of the 4096-latent decode (68.9 against 67.1-67.6
+// ms on one box with alternating builds) by lengthening every fp32 epilogue.
+template <bool A_SPLIT, bool OUT_SPLIT, bool HAS_RES, int STAGES, int BN, bool MC = false, bool NFC = false>
 __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 1) gemm_tcgen05_kernel(TcArgs a) {
   static_assert(!MC || (A_SPLIT && BN == 128), "multicast: SplitTile input, 128-wide tiles");
   constexpr int STAGE_BYTES = stage_bytes(BN);
@@ -214,6 +217,11 @@ __global__ void __launch_bounds__(NUM_THREADS, (STAGES == 2 && BN <= 128) ? 2 : 
               float o2 = apply_act_t<ACT>(v.z + bv.z, a.act), o3 = apply_act_t<ACT>(v.w + bv.w, a.act);
               if constexpr (HAS_RES) { o0 += rv[cc][it].x; o1 += rv[cc][it].y; o2 += rv[cc][it].z; o3 += rv[cc][it].w; }
               *reinterpret_cast<float4*>(a.y + (size_t)gm * a.ldy + gn) = make_float4(o0, o1, o2, o3);
+              if constexpr (NFC) {
+                if (nonfinite_hit(o0, a.nonfinite_mode) || nonfinite_hit(o1, a.nonfinite_mode) || nonfinite_hit(o2, a.nonfinite_mode) ||
+                    nonfinite_hit(o3, a.nonfinite_mode))
+                  atomicOr(a.nonfinite_flag, 1);
+              }
             }
           }
         }
@@ -345,8 +353,10 @@ bool tc_shape_ok(const LinearArgs& a) {
 
 int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_REQUIRE(tc_shape_ok(a), "tcgen05 linear: shape/alignment not supported (M=%d N=%d K=%d)", a.M, a.N, a.K);
-  if (tc_2cta_ok(a)) return launch_linear_tcgen05_2cta(a, s);
-  if (tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
+  if (a.nonfinite_flag == nullptr) {       // (the opt-in variants do not carry the non-finite check)
+    if (tc_2cta_ok(a)) return launch_linear_tcgen05_2cta(a, s);
+    if (tc_persistent_ok(a)) return launch_linear_tcgen05_persistent(a, s);
+  }
   static bool attr_dev[64] = {};
   if (first_use_on_device(attr_dev)) {
 #define SCV_SET_SMEM(A, O, R, S, N) \
@@ -355,6 +365,8 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   SCV_SET_SMEM(false, false, false, S, N); SCV_SET_SMEM(false, true, false, S, N); SCV_SET_SMEM(true, false, false, S, N); \
   SCV_SET_SMEM(true, true, false, S, N); SCV_SET_SMEM(false, false, true, S, N); SCV_SET_SMEM(true, false, true, S, N)
     SCV_SET_ALL(2, 128); SCV_SET_ALL(4, 128); SCV_SET_ALL(3, 256); SCV_SET_ALL(4, 64);
+    SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false, false, 2, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  smem_bytes(2, 128)));
 #define SCV_SET_MC(O, R, S) \
   SCV_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true, O, R, S, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, 128)))
     SCV_SET_MC(false, false, 2); SCV_SET_MC(true, false, 2); SCV_SET_MC(false, true, 2);
@@ -371,6 +383,7 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   t.next_w = static_cast<const uint8_t*>(a.next_w); t.next_w_bytes = (uint32_t)a.next_w_bytes;
   t.trace = trace_ptr();
   t.row_base = a.row_base;
+  t.nonfinite_flag = a.y_split == nullptr ? a.nonfinite_flag : nullptr; t.nonfinite_mode = a.nonfinite_mode;
   // 2 MMAs (hi, lo) per weight tile: algorithmic flops stay 2MNK, the tensor pipe executes twice that
   ProfScope prof(PC_GEMM_TC, s, 2.0 * a.M * a.N * a.K,
                  2.0 * a.N * a.K + 4.0 * a.M * a.K + 4.0 * a.M * a.N * (a.residual ? 2 : 1));
@@ -401,6 +414,13 @@ int launch_linear_tcgen05(const LinearArgs& a, cudaStream_t s) {
   // rows (two streams x 16 row tiles: the A tiles are re-read by twice as many CTAs out of an L2 that is the bottleneck
   // there), hence the bound on the row tiles.
   const bool narrow = !wide && mt <= tun().gemm_bn64 && n64 * mt <= tun().gemm_bn64_max_ctas;
+  if (t.nonfinite_flag != nullptr) {
+    SCV_REQUIRE(as && !os && !res, "tcgen05 linear: the non-finite check needs SplitTile input, fp32 output, no residual");
+    dim3 grid(n128, mt);
+    SCV_CUDA(launch_k(gemm_tcgen05_kernel<true, false, false, 2, 128, false, true>, grid, dim3(NUM_THREADS), (size_t)smem_bytes(2, 128), s, t));
+    SCV_LAUNCH_CHECK();
+    return 0;
+  }
   const bool mc = !narrow && !wide && as && tun().gemm_mc != 0 && n128 % 2 == 0 && mt >= tun().gemm_mc_min_row_tiles &&
                   t.kblocks >= tun().gemm_mc_min_kblocks;
   if (mc) {

@@ -147,6 +147,7 @@ linear_simt_kernel(LinearArgs a, int x_vec_ok) {
           v = apply_act(v, a.act);
           if (a.residual != nullptr) v += a.residual[(size_t)gm * a.ldr + gn];
           a.y[(size_t)gm * a.ldy + gn] = v;
+          if (a.nonfinite_flag != nullptr && nonfinite_hit(v, a.nonfinite_mode)) atomicOr(a.nonfinite_flag, 1);
         }
     }
 }
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(256) linear_rowwarp_kernel(LinearArgs a) {
       v = apply_act(v, a.act);
       if (a.residual != nullptr) v += a.residual[(size_t)row * a.ldr + n];
       a.y[(size_t)row * a.ldy + n] = v;
+      if (a.nonfinite_flag != nullptr && nonfinite_hit(v, a.nonfinite_mode)) atomicOr(a.nonfinite_flag, 1);
     }
   }
 }

@@ -119,6 +119,7 @@ struct TcArgs {
   const float* ln_gamma; const float* ln_beta; uint8_t* ln_out;   // gemm_tcgen05_ln.cu: LayerNorm of the output row
   void* trace;                                                    // CTA residency trace (common.cuh), normally null
   int row_base;                                                   // first row of the launch inside the call's batch
+  int* nonfinite_flag; int nonfinite_mode;                        // LinearArgs::nonfinite_flag (fp32 output only)
 };
 
 

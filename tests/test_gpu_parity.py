@@ -417,6 +417,40 @@ def test_h2_uniform_fallback_with_masks(golden_dir):
         torch.testing.assert_close(lp.cpu()[:, s], ref, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("rows", [5, 300])
+def test_h2_uniform_fallback_without_masks_is_reported_by_the_projections(rows):
+    """Without a type mask / hard stop the batch-global "some adjusted logit is NaN or +-inf" test of the reference
+    (:1464-1466) is not a separate pass over the logits: the logits projection and the stop head report non-finite outputs
+    themselves (LinearArgs::nonfinite_flag).  One NaN vocabulary bias or a NaN stop bias makes EVERY row sample uniformly
+    (log-prob = -log V, entropy = log V, like the oracle); an infinite stop bias does not (sigmoid(inf) = 1 is finite);
+    clean weights do not.  5 rows: persistent small-batch machinery; 300 rows: tensor-core projections."""
+    shape = W.TINY
+    lnv = math.log(shape.vocab_size)
+    z = W.make_latents(rows, shape.latent_dim, 3)
+    stoich, heads = W.make_conditioning(rows, shape.stoich_input_dim, 3)
+    kw = dict(temperature=1.2, max_len=shape.max_len, stop_boost=10.0)
+    for key, idx, val, degenerate in (("output_proj.4.bias", 7, float("nan"), True), ("output_proj.4.bias", 7, float("inf"), True),
+                                      ("stop_head.2.bias", 0, float("nan"), True), ("stop_head.2.bias", 0, float("inf"), False),
+                                      (None, 0, 0.0, False)):
+        sd = W.make_decoder_state_dict(shape, 0)
+        if key is not None:
+            sd[key] = sd[key].clone()
+            sd[key][idx] = val
+        dec = S.EnhancedTransformerDecoder.from_state_dict(sd, nhead=shape.nhead, device=DEV)
+        t, lp, en, mk = dec.sample_for_reinforce(_cuda(z), stoich_pred=_cuda(stoich), heads_pred=_cuda(heads), _seed=9, **kw)
+        rt, rlp, ren = DO.generate_with_kv_cache(sd, shape.nhead, z, stoich_pred=stoich, heads_pred=heads, return_log_probs=True,
+                                                 return_entropy=True, forced_tokens=t.cpu(), **kw)
+        L = min(t.shape[1], rt.shape[1])
+        if degenerate:
+            torch.testing.assert_close(lp.cpu(), torch.full_like(lp.cpu(), -lnv), rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(en.cpu(), torch.full_like(en.cpu(), lnv), rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(rlp[:, :L], torch.full_like(rlp[:, :L], -lnv), rtol=1e-5, atol=1e-5)      # the oracle agrees
+        else:
+            assert float((lp.cpu() + lnv).abs().max()) > 1e-3
+            torch.testing.assert_close(lp.cpu()[:, :L], rlp[:, :L], rtol=1e-3, atol=1e-3)
+            torch.testing.assert_close(en.cpu()[:, :L], ren[:, :L], rtol=1e-3, atol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------ encoder
 def test_encoder_matches_reference_golden(golden_dir):
     g = _golden(golden_dir, "encoder_default")
